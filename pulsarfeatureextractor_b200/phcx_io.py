@@ -1,0 +1,167 @@
+"""
+PHCX candidate files: writer for synthetic candidates and the host-side packer (reader).
+
+The reference reads a candidate with ``gzip`` + ``xml.dom.minidom`` and per-character Python
+hex loops (PHCXFile.py:90-186, PHCXOperations.py:172-182,237-297,353-383) and, for the Lyon
+statistics, parses every file twice (Candidate.py:218,277).  Here a file is scanned once with
+compiled regular expressions and ``bytes.fromhex`` straight into rows of a pinned
+structure-of-arrays batch.  Quirks kept:
+
+* section index 1 for HTRU ``.phcx.gz`` and 0 for SUPERB ``.phcx``
+  (PHCXFile.py:80, SUPERBPHCXFile.py:80); the Lyon DM statistics always use DataBlock[0]
+  (PHCXOperations.py:538);
+* ``DmIndex``: tokens are the text between new-lines; dm_start is token 1, dm_end the last
+  *complete* token (PHCXOperations.py:172-182);
+* the DM curve is the max of the first 127 values of every 128-block of DataBlock[section]
+  and the x index of block k is 128k-1 (PHCXOperations.py:237-259);
+* hex decoding skips new-lines and stops at the first pair that is not hexadecimal
+  (PHCXFile.py:166-184).
+"""
+import gzip
+import re
+
+import numpy as np
+
+_HEX_RE = re.compile(rb"^(?:[0-9A-Fa-f]{2})*")
+
+
+def _tag_blocks(text, tag):
+    """All (attribute string, body) of <tag ...>body</tag>, in document order."""
+    pat = re.compile(rb"<" + tag + rb"(\s[^>]*)?>(.*?)</" + tag + rb">", re.S)
+    return [(m.group(1) or b"", m.group(2)) for m in pat.finditer(text)]
+
+
+def _attr(attrs, name):
+    m = re.search(name + rb"\s*=\s*['\"]([^'\"]*)['\"]", attrs)
+    if m is None:
+        raise KeyError(name.decode())
+    return m.group(1)
+
+
+def _hex_to_u8(body):
+    body = body.replace(b"\n", b"")
+    m = _HEX_RE.match(body)
+    return np.frombuffer(bytes.fromhex(m.group(0).decode("ascii")), dtype=np.uint8)
+
+
+def dm_curve_reduce(block):
+    """max of the first 127 values of each complete 128-block (PHCXOperations.py:237-259)."""
+    nblk = block.size // 128
+    if nblk == 0:
+        return np.zeros(0, dtype=np.uint8)
+    return block[: nblk * 128].reshape(nblk, 128)[:, :127].max(axis=1)
+
+
+class PHCXCandidate(object):
+    __slots__ = ("profile", "subbands", "dmcurve", "dmstat", "params")
+
+
+def read_phcx(path, section=None):
+    """Parse one candidate.  ``section`` defaults to 1 for ``.gz`` names, else 0
+    (Candidate.py:141-150 dispatch)."""
+    if section is None:
+        section = 1 if ".gz" in path else 0
+    if ".gz" in path:
+        with gzip.open(path, "rb") as fh:
+            text = fh.read()
+    else:
+        with open(path, "rb") as fh:
+            text = fh.read()
+    c = PHCXCandidate()
+    c.profile = _hex_to_u8(_tag_blocks(text, b"Profile")[section][1])
+    attrs, body = _tag_blocks(text, b"SubBands")[section]
+    nbins = int(_attr(attrs, b"nBins"))
+    nsub = int(_attr(attrs, b"nSub"))
+    c.subbands = _hex_to_u8(body).reshape(nsub, nbins)
+    blocks = _tag_blocks(text, b"DataBlock")
+    block = _hex_to_u8(blocks[section][1])
+    c.dmcurve = dm_curve_reduce(block)
+    c.dmstat = _hex_to_u8(blocks[0][1])
+    tokens = _tag_blocks(text, b"DmIndex")[section][1].split(b"\n")[:-1]
+    dm_start = float(tokens[1])
+    dm_end = float(tokens[len(tokens) - 1])
+
+    def scalar(tag):
+        return float(_tag_blocks(text, tag)[section][1])
+
+    c.params = np.array([scalar(b"Snr"), scalar(b"Dm"), scalar(b"BaryPeriod"), scalar(b"Width"),
+                         dm_start, dm_end, float(block.size), 0.0], dtype=np.float64)
+    return c
+
+
+def _hex_lines(a, per_line=40):
+    h = bytes(np.ascontiguousarray(a, dtype=np.uint8)).hex().upper()
+    step = per_line * 2
+    return "\n".join(h[i:i + step] for i in range(0, len(h), step))
+
+
+def _section(name, snr, dm, period_s, width, profile, subbands, dm_index, datablock):
+    nsub, nbin = subbands.shape
+    idx = "\n".join("%.4f" % v for v in dm_index)
+    return (
+        " <Section name='%s'>\n"
+        "  <BestValues>\n"
+        "   <TopoPeriod units='seconds'>%.12f</TopoPeriod>\n"
+        "   <BaryPeriod units='seconds'>%r</BaryPeriod>\n"
+        "   <Dm units='cm^-3pc'>%r</Dm>\n"
+        "   <Accn units='m/s/s'>0.0</Accn>\n"
+        "   <Jerk units='m/s/s/s'>0.0</Jerk>\n"
+        "   <Snr>%r</Snr>\n"
+        "   <Width units='periods'>%r</Width>\n"
+        "  </BestValues>\n"
+        "  <SubIntegrations nBins='%d' nSub='1' format='02X' min='0' max='1'>\n%s\n\t</SubIntegrations>\n"
+        "  <SubBands nBins='%d' nSub='%d' format='02X' min='0' max='1'>\n%s\n\t</SubBands>\n"
+        "  <Profile nBins='%d' format='02X' min='0' max='1'>\n%s\n\t</Profile>\n"
+        "  <SnrBlock>\n"
+        "   <PeriodIndex nVals='1' format='16.12f'>\n%.12f\n</PeriodIndex>\n"
+        "   <DmIndex nVals='%d' format='6.4f'>\n%s\n</DmIndex>\n"
+        "   <AccnIndex nVals='1' format='6.4f'>\n0.0000\n</AccnIndex>\n"
+        "   <JerkIndex nVals='1' format='6.4f'>\n0.0000\n</JerkIndex>\n"
+        "   <DataBlock format='02X' min='0' max='1'>\n%s\n\t</DataBlock>\n"
+        "  </SnrBlock>\n"
+        " </Section>\n"
+    ) % (name, period_s, period_s, float(dm), float(snr), float(width),
+         nbin, _hex_lines(profile),
+         nbin, nsub, _hex_lines(subbands.reshape(-1)),
+         nbin, _hex_lines(profile),
+         period_s, len(dm_index), idx, _hex_lines(datablock))
+
+
+def expand_dm_block(curve):
+    """A DataBlock whose max-of-127 reduction gives ``curve`` back: every 128-block holds the
+    curve value once and smaller values elsewhere; the 128th value (ignored by the reference,
+    PHCXOperations.py:251-257) is set to 255 to exercise that quirk."""
+    curve = np.asarray(curve, dtype=np.uint8)
+    blk = (curve[:, None].astype(np.int32) * (np.arange(128)[None, :] % 7) // 7).astype(np.uint8)
+    blk[np.arange(curve.size), (np.arange(curve.size) * 5) % 127] = curve
+    blk[:, 127] = 255
+    return blk.reshape(-1)
+
+
+def write_phcx(path, profile, subbands, dmcurve, dmstat, params, gz=True):
+    """Write a two-section PHCX file.  Section 0 ('FFT') carries ``dmstat`` as its DataBlock
+    (Lyon DM statistics read it, PHCXOperations.py:538) and a decoy profile; section 1
+    ('FFT-Pdmpd') carries the candidate the Bates scores read.  With ``gz=False`` a SUPERB-style
+    single-section file is written (section index 0 holds everything)."""
+    snr, dm, period_s, width, dm_start, dm_end = [float(v) for v in params[:6]]
+    block1 = expand_dm_block(dmcurve)
+    n_idx = 64
+    dm_index = np.linspace(dm_start, dm_end, n_idx)
+    parts = ["<?xml version='1.0'?>\n<phcf>\n <head>\n  <SourceID>SYNTHETIC</SourceID>\n </head>\n"]
+    if gz:
+        decoy = (255 - np.asarray(profile, dtype=np.uint8))
+        parts.append(_section("FFT", snr * 0.5, dm + 1.0, period_s * 1.0001, width * 2, decoy,
+                              np.asarray(subbands)[::-1], dm_index * 0.5, dmstat))
+        parts.append(_section("FFT-Pdmpd", snr, dm, period_s, width, profile, np.asarray(subbands),
+                              dm_index, block1))
+    else:
+        parts.append(_section("FFT-Pdmpd", snr, dm, period_s, width, profile, np.asarray(subbands),
+                              dm_index, block1))
+    parts.append("</phcf>\n")
+    data = "".join(parts).encode("ascii")
+    if gz:
+        with gzip.open(path, "wb", compresslevel=1) as fh:
+            fh.write(data)
+    else:
+        with open(path, "wb") as fh:
+            fh.write(data)
