@@ -35,7 +35,7 @@ edge-case candidates, and tests/golden/*.npz holds reference outputs generated t
 
 Python 2 semantics pinned here: int/int division sites
 POI:206 (always-rotate), PO:1106/1166 (cut = n//2), PO:1041 (bins//2 - 1), PO:1628 (w//2),
-PFDO:202 (n//2).  ``PY2_DIV`` switches them (default True = reference-faithful).
+PFDO:202 (n//2), POI:158 (range // 60 when the IQR is 0 and the data are integers).  ``PY2_DIV`` switches them (default True = reference-faithful).
 """
 import math
 import warnings
@@ -48,6 +48,10 @@ PY2_DIV = True
 # one corrcoef over the whole matrix instead of nsub(nsub-1)/2 pair calls (ulp-level
 # differences only); the pair loop of PO:1666-1678 is the default.
 FAST_CORR = False
+# "Perturbed twin" (SURVEY.md section 8c tolerances): the same oracle with the residual expressions
+# re-associated (algebraically identical, a few ulp different).  oracle-vs-twin scatter is the
+# noise floor any independent implementation is judged against on ill-conditioned fits.
+TWIN = False
 
 # --- per-candidate status bits (mirrored in include/pfx.h) --------------------------------
 ST_HIST_ZERO_BINS = 1 << 0    # numpy.histogram(bins=0) -> ValueError        (PO:657,678)
@@ -107,6 +111,17 @@ class FitLog(object):
 def _div(a, b):
     """int/int division at the sites SURVEY 8c D1 lists."""
     return a // b if PY2_DIV else a / b
+
+
+def _is_intlike(v):
+    return isinstance(v, (int, np.integer)) or (isinstance(v, np.ndarray) and v.dtype.kind in "iub")
+
+
+def _classic_div(a, b):
+    """Python 2 ``/``: floor division when both operands are integers, true division otherwise."""
+    if PY2_DIV and _is_intlike(a) and _is_intlike(b):
+        return a // b
+    return a / b
 
 
 def _seqsum(a):
@@ -231,6 +246,8 @@ def fit_sine(y, maxima, log=None):
 
     def resid(p, x, y, amp, bg):
         f, phi = p
+        if TWIN:
+            return (y - abs(bg)) - abs(amp) * np.sin(phi + (2 * np.pi * x) * f)
         return y - (abs(amp) * np.sin(2 * np.pi * f * x + phi) + abs(bg))
 
     phi0 = _phi0_sine(y[0], bg, freq)
@@ -252,6 +269,9 @@ def fit_sine_sqr(y, maxima, log=None):
 
     def resid(p, x, y, amp, bg):
         f, phi = p
+        if TWIN:
+            sn = np.sin(phi + (2 * np.pi * x) * f)
+            return (y + abs(bg)) - abs(amp) * (sn * sn)
         return y - (abs(amp) * pow(np.sin(2 * np.pi * f * x + phi), 2)) + abs(bg)
 
     if y[0] == 0:
@@ -299,7 +319,9 @@ def freedman_diaconis_bins(data):
     if binwidth <= 0:
         binwidth = 60
     rnge = _builtin_max(data) - _builtin_min(data)
-    return int(np.ceil(rnge / binwidth))
+    # POI:158: with the integer fallback width 60 and integer data this is int/int under
+    # Python 2 (floor), e.g. range 252 -> 4 bins, not ceil(4.2) = 5.
+    return int(np.ceil(_classic_div(rnge, binwidth)))
 
 
 def derivative(y):
@@ -314,8 +336,15 @@ def _histogram(data, nbins):
         raise CandidateFailure(ST_HIST_ZERO_BINS)
 
 
+def _gexp(x, mu, sigma):
+    """exp(-((x-mu)/sigma)^2 / 2) as the reference writes it, or re-associated for the twin."""
+    if TWIN:
+        return np.exp(-0.5 * ((x - mu) * (1.0 / sigma)) ** 2)
+    return np.exp((-((x - mu) / sigma) ** 2) / 2)
+
+
 def _gauss3(x, sigma, mu, maximum):
-    return abs(maximum) * np.exp((-((x - mu) / sigma) ** 2) / 2)
+    return abs(maximum) * _gexp(x, mu, sigma)
 
 
 def fit_gaussian_hist(edges, counts, log=None, slot=FIT_PROFHIST):
@@ -385,14 +414,14 @@ def fit_gaussian_fixed(edges, counts, bins, log=None):
 
     def resid(p, x, y, xmax):
         s, mx = p
-        return y - (abs(mx) * np.exp((-((x - xmax) / s) ** 2) / 2))
+        return y - (abs(mx) * _gexp(x, xmax, s))
 
     if len(y) < 2:
         raise CandidateFailure(ST_LSQ_IMPROPER)          # leastsq: N=2 must not exceed M
     p = _lsq(resid, [sigma0, max0], (x, y, xmax), log, FIT_FIXED)
     with np.errstate(all="ignore"):
         fwhm = abs(FWHM_K_NP * p[0])
-        fit = abs(p[1]) * np.exp((-((x - xmax) / p[0]) ** 2) / 2)
+        fit = abs(p[1]) * _gexp(x, xmax, p[0])
         chisq = _chisq(y, fit, len(y)) / len(y)
     return p, fwhm, chisq, fit, xmax
 
@@ -422,7 +451,7 @@ def fit_gaussian_bg(y, log=None, slot=FIT_T1):
 
     def model(x, p):
         s, mu, mx, bg = p
-        return abs(mx) * np.exp((-((x - mu) / abs(s)) ** 2) / 2) + (bg)
+        return abs(mx) * _gexp(x, mu, abs(s)) + (bg)
 
     def resid(p, x, y):
         return y - model(x, p)
@@ -500,13 +529,13 @@ def _dg_strip_peak(y):
 
 def _gauss4abs(x, p):
     s, mu, mx, bg = p
-    return abs(mx) * np.exp((-((x - mu) / s) ** 2) / 2) + abs(bg)
+    return abs(mx) * _gexp(x, mu, s) + abs(bg)
 
 
 def _gauss8(x, p):
     s1, m1, a1, b1, s2, m2, a2, b2 = p
-    return ((abs(a1) * np.exp((-((x - m1) / abs(s1)) ** 2) / 2)) +
-            (abs(a2) * np.exp((-((x - m2) / abs(s2)) ** 2) / 2)) + (abs(b1) + abs(b2)) / 2)
+    return ((abs(a1) * _gexp(x, m1, abs(s1))) +
+            (abs(a2) * _gexp(x, m2, abs(s2))) + (abs(b1) + abs(b2)) / 2)
 
 
 def fit_double_gaussian(y, log=None):
@@ -683,6 +712,9 @@ def dm_fittings_phcx(curve_y, curve_x, length_all, snr, dm, period_ms, width, dm
 
         def model(x, p):
             amp, prop, shift = p
+            if TWIN:
+                weff = np.sqrt(wint + pow((prop * (kdm * df / pow(f, 3))) * abs((dm + shift) - x), 2))
+                return amp * np.sqrt(period_ms / weff - 1.0)
             weff = np.sqrt(wint + pow(prop * kdm * abs((dm + shift) - x) * df / pow(f, 3), 2))
             return amp * np.sqrt((period_ms - weff) / weff)
 

@@ -1,0 +1,337 @@
+// pfx_api.cu -- context management and the C ABI of libpfx (include/pfx.h).
+//
+// Execution model.  One candidate is scored by one warp (Bates groups) or by 8 lanes (Lyon
+// statistics).  Every Bates kernel is persistent: the grid is sized to SM count x resident blocks
+// and each warp pulls candidate indices from a global atomic counter, because the work per
+// candidate is heavy-tailed (a Levenberg-Marquardt solve takes 30 to 1800 function evaluations).
+// All per-candidate working data (profile, histogram, Jacobian, R factor) live in shared memory;
+// HBM is touched once to read the candidate and once to write its feature row.
+#include "pfx_internal.cuh"
+
+using namespace pfx;
+
+int pfx::set_err(pfx_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+extern "C" int pfx_version(void) { return PFX_VERSION; }
+
+extern "C" int pfx_create(int device, pfx_ctx** out) {
+    if (!out) return PFX_ERR_INVALID;
+    *out = nullptr;
+    pfx_ctx* ctx = (pfx_ctx*)calloc(1, sizeof(pfx_ctx));
+    if (!ctx) return PFX_ERR_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        free(ctx);
+        return PFX_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (cudaMalloc(&ctx->counters, sizeof(u64) * COUNTER_SLOTS * COUNTERS_PER_SLOT) != cudaSuccess) {
+        free(ctx);
+        return PFX_ERR_NOMEM;
+    }
+    ctx->scratch_bytes = sizeof(u64) * COUNTER_SLOTS * COUNTERS_PER_SLOT;
+    for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
+    *out = ctx;
+    return PFX_OK;
+}
+
+extern "C" void pfx_destroy(pfx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->counters);
+    if (ctx->hist_scratch) cudaFree(ctx->hist_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+        cudaStreamDestroy(ctx->streams[i]);
+    }
+    for (int i = 0; i < N_EVENTS; ++i) cudaEventDestroy(ctx->ev[i]);
+    free(ctx);
+}
+
+extern "C" const char* pfx_last_error(const pfx_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+extern "C" int pfx_device_info(const pfx_ctx* ctx, int* sm_count, int* smem_per_block, size_t* scratch_bytes) {
+    if (!ctx) return PFX_ERR_INVALID;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (smem_per_block) *smem_per_block = ctx->smem_optin;
+    if (scratch_bytes) *scratch_bytes = ctx->scratch_bytes;
+    return PFX_OK;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------
+static int check_shape(pfx_ctx* ctx, const pfx_shape* s, int64_t n) {
+    if (!ctx) return PFX_ERR_INVALID;
+    if (!s) return set_err(ctx, PFX_ERR_INVALID, "shape is NULL");
+    if (n < 0) return set_err(ctx, PFX_ERR_INVALID, "n < 0");
+    if (s->dtype < PFX_U8 || s->dtype > PFX_F64 || s->dm_dtype < PFX_U8 || s->dm_dtype > PFX_F64 ||
+        s->dmstat_dtype < PFX_U8 || s->dmstat_dtype > PFX_F64)
+        return set_err(ctx, PFX_ERR_INVALID, "bad dtype");
+    if (s->family != PFX_FAMILY_PHCX && s->family != PFX_FAMILY_PFD)
+        return set_err(ctx, PFX_ERR_INVALID, "bad family");
+    return PFX_OK;
+}
+
+static void rotate_counters(pfx_ctx* ctx) { ctx->counter_slot = (ctx->counter_slot + 1) % COUNTER_SLOTS; }
+
+// =============================================================================================
+// device-pointer entry points
+// =============================================================================================
+extern "C" int pfx_lyon8_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                             const void* dmstat, double* feat, int64_t feat_ld, void* stream) {
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    if (!profile || !dmstat || !feat || feat_ld < PFX_NLYON) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_lyon(ctx, shape, n, profile, dmstat, feat, feat_ld, (cudaStream_t)stream);
+}
+
+extern "C" int pfx_sinusoid_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                                double* feat, int64_t feat_ld, int8_t* ier, int32_t* status, void* stream) {
+    (void)status;
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    if (!profile || !feat || feat_ld < 4) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    rotate_counters(ctx);
+    return launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, (cudaStream_t)stream, 0);
+}
+
+extern "C" int pfx_gaussian_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                                double* feat, int64_t feat_ld, int8_t* ier, int32_t* status, void* stream) {
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    if (!profile || !feat || !status || feat_ld < 11) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    rotate_counters(ctx);
+    {
+        cudaStream_t st = (cudaStream_t)stream;
+        rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 0);
+        if (rc) return rc;
+        return launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+    }
+}
+
+extern "C" int pfx_dmfit_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                             const void* dmcurve, const double* params, double* feat, int64_t feat_ld,
+                             int8_t* ier, int32_t* status, void* stream) {
+    (void)profile;
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    if (!dmcurve || !params || !feat || !status || feat_ld < 19) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    rotate_counters(ctx);
+    return launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, (cudaStream_t)stream, 0);
+}
+
+extern "C" int pfx_subband_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                               const void* subbands, const double* params, double* feat, int64_t feat_ld,
+                               int32_t* status, void* stream) {
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    if (!profile || !subbands || !params || !feat || !status || feat_ld < 22)
+        return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    rotate_counters(ctx);
+    return launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, (cudaStream_t)stream, 0);
+}
+
+static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t features,
+                          const void* profile, const void* subbands, const void* dmcurve,
+                          const void* dmstat, const double* params, double* feat, int64_t feat_ld,
+                          int8_t* ier, int32_t* status, cudaStream_t st, bool timed) {
+    const bool bates = (features & PFX_FEAT_BATES) != 0, lyon = (features & PFX_FEAT_LYON) != 0;
+    const int ncol = (bates ? PFX_NBATES : 0) + (lyon ? PFX_NLYON : 0);
+    if (ncol == 0) return set_err(ctx, PFX_ERR_INVALID, "no feature set selected");
+    if (!profile || !feat || feat_ld < ncol) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    if (bates && (!subbands || !dmcurve || !params || !status)) return set_err(ctx, PFX_ERR_INVALID, "Bates scores need subbands, dmcurve, params and status");
+    if (lyon && !dmstat) return set_err(ctx, PFX_ERR_INVALID, "Lyon statistics need dmstat");
+    rotate_counters(ctx);
+    int launches = 0;
+    int e = 0;
+    if (timed) cudaEventRecord(ctx->ev[e++], st);
+    int rc;
+    if (lyon) {
+        rc = launch_lyon(ctx, shape, n, profile, dmstat, feat + (bates ? PFX_NBATES : 0), feat_ld, st);
+        if (rc) return rc;
+        ++launches;
+    }
+    if (timed) cudaEventRecord(ctx->ev[e++], st);
+    if (bates) {
+        PFX_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n, st));
+        if (ier) PFX_CUDA(ctx, cudaMemsetAsync(ier, 0, (size_t)n * PFX_NIER, st));
+        rc = launch_fill_nan(ctx, feat, n, feat_ld, PFX_NBATES, st);
+        if (rc) return rc;
+        ++launches;
+        rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, 0);
+        if (rc) return rc;
+        if (timed) cudaEventRecord(ctx->ev[e++], st);
+        rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+        if (rc) return rc;
+        if (timed) cudaEventRecord(ctx->ev[e++], st);
+        rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
+        if (rc) return rc;
+        if (timed) cudaEventRecord(ctx->ev[e++], st);
+        rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, st, 3);
+        if (rc) return rc;
+        if (timed) cudaEventRecord(ctx->ev[e++], st);
+        rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, st, 4);
+        if (rc) return rc;
+        if (timed) cudaEventRecord(ctx->ev[e++], st);
+        launches += 5;
+    }
+    ctx->last_launches = launches;
+    if (timed) ctx->ev_valid = bates;
+    return PFX_OK;
+}
+
+extern "C" int pfx_score_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t features,
+                             const void* profile, const void* subbands, const void* dmcurve,
+                             const void* dmstat, const double* params, double* feat, int64_t feat_ld,
+                             int8_t* ier, int32_t* status, void* stream) {
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return score_dev_impl(ctx, shape, n, features, profile, subbands, dmcurve, dmstat, params, feat, feat_ld,
+                          ier, status, (cudaStream_t)stream, true);
+}
+
+extern "C" int pfx_last_timing(pfx_ctx* ctx, pfx_timing* out) {
+    if (!ctx || !out) return PFX_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->launches = ctx->last_launches;
+    if (!ctx->ev_valid) return PFX_OK;
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    PFX_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+    cudaEventElapsedTime(&out->lyon, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&out->sinusoid, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&out->histgauss, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&out->gauss, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&out->dmfit, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&out->subband, ctx->ev[5], ctx->ev[6]);
+    cudaEventElapsedTime(&out->total, ctx->ev[0], ctx->ev[6]);
+    return PFX_OK;
+}
+
+// =============================================================================================
+// host-pointer entry point: chunked, double-buffered H2D -> kernels -> D2H
+// =============================================================================================
+namespace {
+struct StageLayout {
+    size_t profile, subbands, dmcurve, dmstat, params, feat, ier, status, total;
+};
+inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+StageLayout stage_layout(const pfx_shape* s, int64_t chunk, bool bates, bool lyon, int ncol) {
+    StageLayout L;
+    size_t off = 0;
+    L.profile = off; off += up256((size_t)chunk * s->nbin * elem_size(s->dtype));
+    L.subbands = off; if (bates) off += up256((size_t)chunk * s->nsub * s->nbin * elem_size(s->dtype));
+    L.dmcurve = off; if (bates) off += up256((size_t)chunk * s->n_dm * elem_size(s->dm_dtype));
+    L.dmstat = off; if (lyon) off += up256((size_t)chunk * s->n_dmstat * elem_size(s->dmstat_dtype));
+    L.params = off; if (bates) off += up256((size_t)chunk * PFX_NPARAM * 8);
+    L.feat = off; off += up256((size_t)chunk * ncol * 8);
+    L.ier = off; if (bates) off += up256((size_t)chunk * PFX_NIER);
+    L.status = off; if (bates) off += up256((size_t)chunk * 4);
+    L.total = off;
+    return L;
+}
+}  // namespace
+
+extern "C" int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t features,
+                              const void* profile, const void* subbands, const void* dmcurve,
+                              const void* dmstat, const double* params, double* feat, int64_t feat_ld,
+                              int8_t* ier, int32_t* status, int64_t chunk) {
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    const bool bates = (features & PFX_FEAT_BATES) != 0, lyon = (features & PFX_FEAT_LYON) != 0;
+    const int ncol = (bates ? PFX_NBATES : 0) + (lyon ? PFX_NLYON : 0);
+    if (ncol == 0) return set_err(ctx, PFX_ERR_INVALID, "no feature set selected");
+    if (!profile || !feat || feat_ld < ncol) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    if (bates && (!subbands || !dmcurve || !params || !status)) return set_err(ctx, PFX_ERR_INVALID, "Bates scores need subbands, dmcurve, params and status");
+    if (lyon && !dmstat) return set_err(ctx, PFX_ERR_INVALID, "Lyon statistics need dmstat");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (chunk <= 0) chunk = bates ? 32768 : 1 << 20;
+    if (chunk > n) chunk = n;
+    const StageLayout L = stage_layout(shape, chunk, bates, lyon, ncol);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage_bytes[b] < L.total) {
+            if (ctx->stage[b]) {
+                cudaDeviceSynchronize();
+                cudaFree(ctx->stage[b]);
+                ctx->scratch_bytes -= ctx->stage_bytes[b];
+                ctx->stage[b] = nullptr;
+                ctx->stage_bytes[b] = 0;
+            }
+            PFX_CUDA(ctx, cudaMalloc(&ctx->stage[b], L.total));
+            ctx->stage_bytes[b] = L.total;
+            ctx->scratch_bytes += L.total;
+        }
+    }
+    const size_t es = elem_size(shape->dtype), eds = elem_size(shape->dm_dtype), ess = elem_size(shape->dmstat_dtype);
+    int launches = 0;
+    int64_t done = 0;
+    int b = 0;
+    while (done < n) {
+        const int64_t cn = (n - done < chunk) ? n - done : chunk;
+        cudaStream_t st = ctx->streams[b];
+        char* base = (char*)ctx->stage[b];
+        PFX_CUDA(ctx, cudaMemcpyAsync(base + L.profile, (const char*)profile + (size_t)done * shape->nbin * es,
+                                      (size_t)cn * shape->nbin * es, cudaMemcpyHostToDevice, st));
+        if (bates) {
+            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.subbands,
+                                          (const char*)subbands + (size_t)done * shape->nsub * shape->nbin * es,
+                                          (size_t)cn * shape->nsub * shape->nbin * es, cudaMemcpyHostToDevice, st));
+            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.dmcurve, (const char*)dmcurve + (size_t)done * shape->n_dm * eds,
+                                          (size_t)cn * shape->n_dm * eds, cudaMemcpyHostToDevice, st));
+            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.params, (const char*)(params + (size_t)done * PFX_NPARAM),
+                                          (size_t)cn * PFX_NPARAM * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (lyon)
+            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.dmstat, (const char*)dmstat + (size_t)done * shape->n_dmstat * ess,
+                                          (size_t)cn * shape->n_dmstat * ess, cudaMemcpyHostToDevice, st));
+        rc = score_dev_impl(ctx, shape, cn, features, base + L.profile, base + L.subbands, base + L.dmcurve,
+                            base + L.dmstat, (const double*)(base + L.params), (double*)(base + L.feat), ncol,
+                            bates && ier ? (int8_t*)(base + L.ier) : nullptr, (int32_t*)(base + L.status), st, false);
+        if (rc) return rc;
+        launches += ctx->last_launches;
+        if (feat_ld == ncol) {
+            PFX_CUDA(ctx, cudaMemcpyAsync(feat + (size_t)done * feat_ld, base + L.feat, (size_t)cn * ncol * 8,
+                                          cudaMemcpyDeviceToHost, st));
+        } else {
+            PFX_CUDA(ctx, cudaMemcpy2DAsync(feat + (size_t)done * feat_ld, (size_t)feat_ld * 8, base + L.feat,
+                                            (size_t)ncol * 8, (size_t)ncol * 8, (size_t)cn,
+                                            cudaMemcpyDeviceToHost, st));
+        }
+        if (bates) {
+            if (ier)
+                PFX_CUDA(ctx, cudaMemcpyAsync(ier + (size_t)done * PFX_NIER, base + L.ier, (size_t)cn * PFX_NIER,
+                                              cudaMemcpyDeviceToHost, st));
+            PFX_CUDA(ctx, cudaMemcpyAsync(status + done, base + L.status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+        }
+        done += cn;
+        b ^= 1;
+    }
+    PFX_CUDA(ctx, cudaStreamSynchronize(ctx->streams[0]));
+    PFX_CUDA(ctx, cudaStreamSynchronize(ctx->streams[1]));
+    ctx->last_launches = launches;
+    ctx->ev_valid = false;
+    return PFX_OK;
+}

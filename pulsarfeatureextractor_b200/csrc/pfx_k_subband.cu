@@ -1,0 +1,40 @@
+// pfx_k_subband.cu -- scores 20-22 (ProfileOperations.py:1585-1686, PHCXOperations.py:387-415).
+#include "pfx_internal.cuh"
+
+using namespace pfx;
+
+namespace {
+// ---- scores 20-22 --------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_THREADS, 4)
+k_subband(const void* __restrict__ profile, const void* __restrict__ subbands, int dtype,
+          long long n, int nbin, int nsub, const double* __restrict__ params, double* feat,
+          long long ld, int32_t* status, u64* counter, int work_doubles) {
+    extern __shared__ double smem[];
+    Group<WARP> g;
+    double* ws = smem + (threadIdx.x / WARP) * work_doubles;
+    for (;;) {
+        const long long c = next_candidate(g, counter);
+        if (c >= n) break;
+        unsigned st = subband_candidate(g, ws, profile, subbands, dtype, c, nbin, nsub,
+                                        params[c * PFX_NPARAM + 3], feat + c * ld);
+        if (st && g.leader()) atomicOr(status + c, (int)st);
+    }
+}
+
+}  // namespace
+
+int pfx::launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile,
+                          const void* subbands, const double* params, double* feat, int64_t ld,
+                          int32_t* status, cudaStream_t st, int ck) {
+    if (s->nsub < 1 || s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "bad sub-band shape");
+    const int wd = align_up(sub_work_doubles(s->nbin, s->nsub), 2);
+    const size_t smem = (size_t)wd * 8 * GROUPS_PER_BLOCK;
+    int grid;
+    int rc = persistent_grid(ctx, k_subband, BLOCK_THREADS, smem, &grid);
+    if (rc) return rc;
+    k_subband<<<grid, BLOCK_THREADS, smem, st>>>(profile, subbands, s->dtype, n, s->nbin, s->nsub, params, feat,
+                                                  ld, status, take_counter(ctx, ck, st), wd);
+    PFX_CUDA(ctx, cudaGetLastError());
+    return PFX_OK;
+}
+

@@ -1,0 +1,495 @@
+// pfx_lm.cuh -- group-parallel Levenberg-Marquardt: MINPACK lmdif as scipy.optimize.leastsq
+// drives it (default ftol = xtol = 1.49012e-8, gtol = 0, maxfev = 200(n+1), epsfcn = eps,
+// factor = 100, mode 1 scaling), which is what every fit of the reference calls
+// (ProfileOperations.py:449,549,949,1045,1246,1379,1473; PHCXOperations.py:212;
+// PFDOperations.py:369).  The algorithm (fdjac2 forward differences, column-pivoted Householder
+// qrfac, lmpar/qrsolv, the 0.25/0.75 trust-region update and the four convergence tests) is
+// MINPACK's; the mapping is not: the m residual rows are striped over the lanes of a group,
+// the m x n Jacobian lives in shared memory column by column, inner products are lane-partial
+// sums joined by a butterfly, and the n x n trust-region sub-problem is solved by the group
+// leader on a copy of R in shared memory while the other lanes wait at a __syncwarp.
+#pragma once
+
+#include "pfx_group.cuh"
+
+namespace pfx {
+
+constexpr int NPMAX = 8;
+constexpr double LM_EPSMCH = 2.220446049250313e-16;
+constexpr double LM_DWARF = 2.2250738585072014e-308;
+constexpr double LM_TOL = 1.49012e-8;
+
+// small per-group scratch in shared memory (leader writes, everyone reads after a sync)
+struct LmShared {
+    double r[NPMAX * NPMAX];  // column major: r[i + NPMAX*j] = R(i,j) upper, S^T strictly lower
+    double diag[NPMAX];
+    double qtf[NPMAX];
+    double step[NPMAX];
+    double sdiag[NPMAX];
+    double wa1[NPMAX];
+    double wa2[NPMAX];
+    double bc[4];
+    int ipvt[NPMAX];
+    int pad[NPMAX];
+};
+
+PFX_HD inline double enorm_seq(int n, const double* x) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += x[i] * x[i];
+    return sqrt(s);
+}
+
+// MINPACK qrsolv on the n x n system, r column major with leading dimension NPMAX.
+PFX_HD inline void qrsolv_seq(int n, double* r, const int* ipvt, const double* diag,
+                              const double* qtb, double* x, double* sdiag, double* wa) {
+    const int ld = NPMAX;
+    for (int j = 0; j < n; ++j) {
+        for (int i = j; i < n; ++i) r[i + ld * j] = r[j + ld * i];
+        x[j] = r[j + ld * j];
+        wa[j] = qtb[j];
+    }
+    for (int j = 0; j < n; ++j) {
+        int l = ipvt[j];
+        if (diag[l] != 0.0) {
+            for (int k = j; k < n; ++k) sdiag[k] = 0.0;
+            sdiag[j] = diag[l];
+            double qtbpj = 0.0;
+            for (int k = j; k < n; ++k) {
+                if (sdiag[k] == 0.0) continue;
+                double rkk = r[k + ld * k];
+                double c, s;
+                if (fabs(rkk) >= fabs(sdiag[k])) {
+                    double t = sdiag[k] / rkk;
+                    c = 0.5 / sqrt(0.25 + 0.25 * (t * t));
+                    s = c * t;
+                } else {
+                    double ct = rkk / sdiag[k];
+                    s = 0.5 / sqrt(0.25 + 0.25 * (ct * ct));
+                    c = s * ct;
+                }
+                r[k + ld * k] = c * rkk + s * sdiag[k];
+                double temp = c * wa[k] + s * qtbpj;
+                qtbpj = -s * wa[k] + c * qtbpj;
+                wa[k] = temp;
+                for (int i = k + 1; i < n; ++i) {
+                    double rik = r[i + ld * k];
+                    temp = c * rik + s * sdiag[i];
+                    sdiag[i] = -s * rik + c * sdiag[i];
+                    r[i + ld * k] = temp;
+                }
+            }
+        }
+        sdiag[j] = r[j + ld * j];
+        r[j + ld * j] = x[j];
+    }
+    int nsing = n;
+    for (int j = 0; j < n; ++j) {
+        if (sdiag[j] == 0.0 && nsing == n) nsing = j;
+        if (nsing < n) wa[j] = 0.0;
+    }
+    for (int k = 0; k < nsing; ++k) {
+        int j = nsing - 1 - k;
+        double sum = 0.0;
+        for (int i = j + 1; i < nsing; ++i) sum += r[i + ld * j] * wa[i];
+        wa[j] = (wa[j] - sum) / sdiag[j];
+    }
+    for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
+}
+
+// MINPACK lmpar.
+PFX_HD inline void lmpar_seq(int n, double* r, const int* ipvt, const double* diag,
+                             const double* qtb, double delta, double& par, double* x,
+                             double* sdiag, double* wa1, double* wa2) {
+    const int ld = NPMAX;
+    const double p1 = 0.1, p001 = 0.001;
+    int nsing = n;
+    for (int j = 0; j < n; ++j) {
+        wa1[j] = qtb[j];
+        if (r[j + ld * j] == 0.0 && nsing == n) nsing = j;
+        if (nsing < n) wa1[j] = 0.0;
+    }
+    for (int k = 0; k < nsing; ++k) {
+        int j = nsing - 1 - k;
+        wa1[j] = wa1[j] / r[j + ld * j];
+        double temp = wa1[j];
+        for (int i = 0; i < j; ++i) wa1[i] -= r[i + ld * j] * temp;
+    }
+    for (int j = 0; j < n; ++j) x[ipvt[j]] = wa1[j];
+
+    int iter = 0;
+    for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
+    double dxnorm = enorm_seq(n, wa2);
+    double fp = dxnorm - delta;
+    if (fp <= p1 * delta) {
+        par = 0.0;
+        return;
+    }
+    double parl = 0.0;
+    if (nsing >= n) {
+        for (int j = 0; j < n; ++j) {
+            int l = ipvt[j];
+            wa1[j] = diag[l] * (wa2[l] / dxnorm);
+        }
+        for (int j = 0; j < n; ++j) {
+            double sum = 0.0;
+            for (int i = 0; i < j; ++i) sum += r[i + ld * j] * wa1[i];
+            wa1[j] = (wa1[j] - sum) / r[j + ld * j];
+        }
+        double temp = enorm_seq(n, wa1);
+        parl = ((fp / delta) / temp) / temp;
+    }
+    for (int j = 0; j < n; ++j) {
+        double sum = 0.0;
+        for (int i = 0; i <= j; ++i) sum += r[i + ld * j] * qtb[i];
+        wa1[j] = sum / diag[ipvt[j]];
+    }
+    double gnorm = enorm_seq(n, wa1);
+    double paru = gnorm / delta;
+    if (paru == 0.0) paru = LM_DWARF / fmin(delta, p1);
+    par = fmax(par, parl);
+    par = fmin(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
+    for (;;) {
+        ++iter;
+        if (par == 0.0) par = fmax(LM_DWARF, p001 * paru);
+        double temp = sqrt(par);
+        for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
+        qrsolv_seq(n, r, ipvt, wa1, qtb, x, sdiag, wa2);
+        for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
+        dxnorm = enorm_seq(n, wa2);
+        temp = fp;
+        fp = dxnorm - delta;
+        if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        for (int j = 0; j < n; ++j) {
+            int l = ipvt[j];
+            wa1[j] = diag[l] * (wa2[l] / dxnorm);
+        }
+        for (int j = 0; j < n; ++j) {
+            wa1[j] = wa1[j] / sdiag[j];
+            double t = wa1[j];
+            for (int i = j + 1; i < n; ++i) wa1[i] -= r[i + ld * j] * t;
+        }
+        temp = enorm_seq(n, wa1);
+        double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) parl = fmax(parl, par);
+        if (fp < 0.0) paru = fmin(paru, par);
+        par = fmax(parl, par + parc);
+    }
+}
+
+template <int NP>
+PFX_HD inline double vget(const double (&a)[NP], int idx) {
+    double v = a[0];
+#pragma unroll
+    for (int k = 1; k < NP; ++k)
+        if (k == idx) v = a[k];
+    return v;
+}
+template <int NP>
+PFX_HD inline void vset(double (&a)[NP], int idx, double v) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+        if (k == idx) a[k] = v;
+}
+template <int NP>
+PFX_HD inline int iget(const int (&a)[NP], int idx) {
+    int v = a[0];
+#pragma unroll
+    for (int k = 1; k < NP; ++k)
+        if (k == idx) v = a[k];
+    return v;
+}
+template <int NP>
+PFX_HD inline void iset(int (&a)[NP], int idx, int v) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+        if (k == idx) a[k] = v;
+}
+
+// Large per-fit work vectors (shared memory, or global scratch for oversized histograms).
+struct LmVec {
+    double* fvec;  // [m]
+    double* wa4;   // [m]
+    double* fjac;  // [NP][ld], column j at fjac + j*ld
+    int ld;
+};
+
+// Returns MINPACK's info (scipy's ier).  x: start on entry, solution on exit (replicated in
+// every lane).  Model::eval(g, p, out, m) writes the residual rows owned by the calling lane.
+template <int NP, class G, class Model>
+PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], const LmVec& v,
+                        LmShared& s, int& nfev_out) {
+    const double p1 = 0.1, p5 = 0.5, p25 = 0.25, p75 = 0.75, p0001 = 1e-4;
+    const double ftol = LM_TOL, xtol = LM_TOL, gtol = 0.0, factor = 100.0;
+    const double epsmch = LM_EPSMCH;
+    const int maxfev = 200 * (NP + 1);
+    const double eps = 1.4901161193847656e-08;  // sqrt(max(epsfcn, epsmch)), epsfcn = eps
+    double* fvec = v.fvec;
+    double* wa4 = v.wa4;
+    const int ld = v.ld;
+    int info = 0;
+    int nfev = 0;
+
+    f.eval(g, x, fvec, m);
+    nfev = 1;
+    double fnorm = sqrt(rows_sumsq(g, fvec, 0, m));
+    double par = 0.0;
+    int iter = 1;
+    double diag[NP], qtf[NP], acnorm[NP], rdiag[NP], wa[NP], xnew[NP], p[NP];
+    int ipvt[NP];
+    double xnorm = 0.0, delta = 0.0, gnorm = 0.0;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) diag[j] = 0.0;
+
+    for (;;) {
+        // ---- fdjac2: forward-difference Jacobian ------------------------------------------
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            double temp = x[j];
+            double h = eps * fabs(temp);
+            if (h == 0.0) h = eps;
+            x[j] = temp + h;
+            f.eval(g, x, wa4, m);
+            x[j] = temp;
+            double* col = v.fjac + j * ld;
+            for (int i = g.lane(); i < m; i += G::W) col[i] = (wa4[i] - fvec[i]) / h;
+        }
+        nfev += NP;
+
+        // ---- qrfac with column pivoting ---------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            acnorm[j] = sqrt(rows_sumsq(g, v.fjac + j * ld, 0, m));
+            rdiag[j] = acnorm[j];
+            wa[j] = rdiag[j];
+            ipvt[j] = j;
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            if (j < m) {
+                int kmax = j;
+                double best = rdiag[j];
+#pragma unroll
+                for (int k = j + 1; k < NP; ++k)
+                    if (rdiag[k] > best) {
+                        best = rdiag[k];
+                        kmax = k;
+                    }
+                double* cj = v.fjac + j * ld;
+                if (kmax != j) {
+                    double* ck = v.fjac + kmax * ld;
+                    for (int i = g.lane(); i < m; i += G::W) {
+                        double t = cj[i];
+                        cj[i] = ck[i];
+                        ck[i] = t;
+                    }
+                    vset<NP>(rdiag, kmax, rdiag[j]);
+                    vset<NP>(wa, kmax, wa[j]);
+                    int t = ipvt[j];
+                    ipvt[j] = iget<NP>(ipvt, kmax);
+                    iset<NP>(ipvt, kmax, t);
+                }
+                double ajnorm = sqrt(rows_sumsq(g, cj, j, m));
+                if (ajnorm != 0.0) {
+                    g.sync();
+                    if (cj[j] < 0.0) ajnorm = -ajnorm;
+                    g.sync();
+                    for (int i = g.lane(); i < m; i += G::W)
+                        if (i >= j) {
+                            double t = cj[i] / ajnorm;
+                            if (i == j) t += 1.0;
+                            cj[i] = t;
+                        }
+                    g.sync();
+                    const double ajj = cj[j];
+#pragma unroll
+                    for (int k = j + 1; k < NP; ++k) {
+                        double* ck = v.fjac + k * ld;
+                        double sum = rows_dot(g, cj, ck, j, m);
+                        double temp = sum / ajj;
+                        for (int i = g.lane(); i < m; i += G::W)
+                            if (i >= j) ck[i] -= temp * cj[i];
+                    }
+                    g.sync();
+#pragma unroll
+                    for (int k = j + 1; k < NP; ++k) {
+                        if (rdiag[k] != 0.0) {
+                            const double* ck = v.fjac + k * ld;
+                            double temp = ck[j] / rdiag[k];
+                            rdiag[k] *= sqrt(fmax(0.0, 1.0 - temp * temp));
+                            double q = rdiag[k] / wa[k];
+                            if (0.05 * (q * q) <= epsmch) {
+                                rdiag[k] = sqrt(rows_sumsq(g, ck, j + 1, m));
+                                wa[k] = rdiag[k];
+                            }
+                        }
+                    }
+                }
+                rdiag[j] = -ajnorm;
+            }
+        }
+
+        if (iter == 1) {
+            double sq = 0.0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                diag[j] = acnorm[j];
+                if (acnorm[j] == 0.0) diag[j] = 1.0;
+                double t = diag[j] * x[j];
+                sq += t * t;
+            }
+            xnorm = sqrt(sq);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+
+        // ---- (Q^T fvec)[0..n) ---------------------------------------------------------------
+        for (int i = g.lane(); i < m; i += G::W) wa4[i] = fvec[i];
+        g.sync();
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            if (j < m) {
+                const double* cj = v.fjac + j * ld;
+                const double ajj = cj[j];
+                if (ajj != 0.0) {
+                    double sum = rows_dot(g, cj, wa4, j, m);
+                    double temp = -sum / ajj;
+                    for (int i = g.lane(); i < m; i += G::W)
+                        if (i >= j) wa4[i] += cj[i] * temp;
+                }
+                g.sync();
+                qtf[j] = wa4[j];
+            } else {
+                qtf[j] = 0.0;
+            }
+        }
+
+        // ---- norm of the scaled gradient ----------------------------------------------------
+        gnorm = 0.0;
+        if (fnorm != 0.0) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                int l = ipvt[j];
+                double al = vget<NP>(acnorm, l);
+                if (al != 0.0) {
+                    const double* cj = v.fjac + j * ld;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) {
+                        if (i < j) sum += cj[i] * (qtf[i] / fnorm);
+                    }
+                    sum += rdiag[j] * (qtf[j] / fnorm);
+                    gnorm = fmax(gnorm, fabs(sum / al));   // fmax: a NaN never replaces gnorm
+                }
+            }
+        }
+        if (gnorm <= gtol) info = 4;
+        if (info != 0) break;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) diag[j] = fmax(diag[j], acnorm[j]);
+
+        // leader: publish R, permutation, Q^T f and the scaling for the n x n sub-problem
+        if (g.leader()) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const double* cj = v.fjac + j * ld;
+                for (int i = 0; i < j; ++i) s.r[i + NPMAX * j] = cj[i];
+                s.r[j + NPMAX * j] = rdiag[j];
+                s.ipvt[j] = ipvt[j];
+                s.qtf[j] = qtf[j];
+                s.diag[j] = diag[j];
+            }
+        }
+        g.sync();
+
+        // ---- inner loop ---------------------------------------------------------------------
+        for (;;) {
+            if (g.leader()) {
+                double lpar = par;
+                lmpar_seq(NP, s.r, s.ipvt, s.diag, s.qtf, delta, lpar, s.step, s.sdiag, s.wa1, s.wa2);
+                s.bc[0] = lpar;
+                // || R P^T p ||
+                for (int j = 0; j < NP; ++j) s.wa1[j] = 0.0;
+                for (int j = 0; j < NP; ++j) {
+                    double temp = -s.step[s.ipvt[j]];
+                    for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + NPMAX * j] * temp;
+                }
+                s.bc[1] = enorm_seq(NP, s.wa1);
+            }
+            g.sync();
+            par = s.bc[0];
+            const double rpnorm = s.bc[1];
+            double sq = 0.0;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                p[j] = -s.step[j];
+                xnew[j] = x[j] + p[j];
+                double t = diag[j] * p[j];
+                sq += t * t;
+            }
+            g.sync();
+            const double pnorm = sqrt(sq);
+            if (iter == 1) delta = fmin(delta, pnorm);
+
+            f.eval(g, xnew, wa4, m);
+            ++nfev;
+            const double fnorm1 = sqrt(rows_sumsq(g, wa4, 0, m));
+
+            double actred = -1.0;
+            if (p1 * fnorm1 < fnorm) {
+                double t = fnorm1 / fnorm;
+                actred = 1.0 - t * t;
+            }
+            const double temp1 = rpnorm / fnorm;
+            const double temp2 = (sqrt(par) * pnorm) / fnorm;
+            const double prered = temp1 * temp1 + temp2 * temp2 / p5;
+            const double dirder = -(temp1 * temp1 + temp2 * temp2);
+            double ratio = 0.0;
+            if (prered != 0.0) ratio = actred / prered;
+
+            if (ratio <= p25) {
+                double temp = p5;
+                if (actred >= 0.0) temp = p5;
+                if (actred < 0.0) temp = p5 * dirder / (dirder + p5 * actred);
+                if (p1 * fnorm1 >= fnorm || temp < p1) temp = p1;
+                delta = temp * fmin(delta, pnorm / p1);
+                par = par / temp;
+            } else if (par == 0.0 || ratio >= p75) {
+                delta = pnorm / p5;
+                par = p5 * par;
+            }
+
+            if (ratio >= p0001) {
+                double sq2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    x[j] = xnew[j];
+                    double t = diag[j] * x[j];
+                    sq2 += t * t;
+                }
+                for (int i = g.lane(); i < m; i += G::W) fvec[i] = wa4[i];
+                xnorm = sqrt(sq2);
+                fnorm = fnorm1;
+                ++iter;
+            }
+
+            const bool c1 = fabs(actred) <= ftol && prered <= ftol && p5 * ratio <= 1.0;
+            if (c1) info = 1;
+            if (delta <= xtol * xnorm) info = 2;
+            if (c1 && info == 2) info = 3;
+            if (info != 0) break;
+            if (nfev >= maxfev) info = 5;
+            if (fabs(actred) <= epsmch && prered <= epsmch && p5 * ratio <= 1.0) info = 6;
+            if (delta <= epsmch * xnorm) info = 7;
+            if (gnorm <= epsmch) info = 8;
+            if (info != 0) break;
+            if (ratio >= p0001) break;   // successful step: new Jacobian
+        }
+        if (info != 0) break;
+    }
+    g.sync();
+    nfev_out = nfev;
+    return info;
+}
+
+}  // namespace pfx

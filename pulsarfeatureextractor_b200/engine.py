@@ -1,0 +1,205 @@
+"""
+Batch engine: Python host side of libpfx.  PyTorch is used only for device / pinned buffers
+and streams; every score is computed by the CUDA kernels behind the C ABI (include/pfx.h).
+
+    eng = Engine(device=0)
+    out = eng.score_host(profile, subbands, dmcurve, dmstat, params, features="all")
+    out.features   [N, 30] float64   Bates 1..22 then the 8 Lyon statistics
+    out.status     [N] int32         which reference exception would have fired (0 = row is valid)
+    out.ier        [N, 18] int8      MINPACK info per least-squares call site
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_NP_DTYPE = {np.dtype(np.uint8): _lib.PFX_U8, np.dtype(np.float32): _lib.PFX_F32,
+             np.dtype(np.float64): _lib.PFX_F64}
+_FEATURES = {"bates": _lib.PFX_FEAT_BATES, "lyon": _lib.PFX_FEAT_LYON, "all": _lib.PFX_FEAT_ALL}
+
+
+class PfxError(RuntimeError):
+    pass
+
+
+class Scores(object):
+    __slots__ = ("features", "status", "ier")
+
+    def __init__(self, features, status, ier):
+        self.features = features
+        self.status = status
+        self.ier = ier
+
+    def ok(self):
+        """Boolean mask of candidates whose row the reference would have written."""
+        if self.status is None:
+            return np.ones(len(self.features), dtype=bool)
+        st = self.status.cpu().numpy() if hasattr(self.status, "cpu") else self.status
+        return (st & _lib.ST_FAIL_MASK) == 0
+
+
+def _code(dt):
+    import torch
+    if isinstance(dt, torch.dtype):
+        return {torch.uint8: _lib.PFX_U8, torch.float32: _lib.PFX_F32, torch.float64: _lib.PFX_F64}[dt]
+    return _NP_DTYPE[np.dtype(dt)]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise PfxError("no CUDA device: pulsarfeatureextractor_b200 has no CPU path")
+        self._lib = _lib.load()
+        self.device = int(device)
+        self._torch = torch
+        h = ctypes.c_void_p()
+        rc = self._lib.pfx_create(self.device, ctypes.byref(h))
+        if rc != 0 or not h:
+            raise PfxError("pfx_create(device=%d) failed with %d" % (self.device, rc))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pfx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PfxError("libpfx error %d: %s" % (rc, self._lib.pfx_last_error(self._h).decode()))
+
+    def device_info(self):
+        sm, smem, scratch = ctypes.c_int(), ctypes.c_int(), ctypes.c_size_t()
+        self._check(self._lib.pfx_device_info(self._h, ctypes.byref(sm), ctypes.byref(smem), ctypes.byref(scratch)))
+        return {"sm_count": sm.value, "smem_per_block": smem.value, "scratch_bytes": scratch.value}
+
+    def last_timing(self):
+        t = _lib.Timing()
+        self._check(self._lib.pfx_last_timing(self._h, ctypes.byref(t)))
+        return {k: getattr(t, k) for k, _ in _lib.Timing._fields_}
+
+    # -------------------------------------------------------------------------------------
+    @staticmethod
+    def make_shape(profile, subbands=None, dmcurve=None, dmstat=None, family=_lib.PFX_FAMILY_PHCX):
+        s = _lib.Shape()
+        s.nbin = profile.shape[1]
+        s.dtype = _code(profile.dtype)
+        s.nsub = subbands.shape[1] if subbands is not None else 0
+        s.n_dm = dmcurve.shape[1] if dmcurve is not None else 0
+        s.dm_dtype = _code(dmcurve.dtype) if dmcurve is not None else 0
+        s.n_dmstat = dmstat.shape[1] if dmstat is not None else 0
+        s.dmstat_dtype = _code(dmstat.dtype) if dmstat is not None else 0
+        s.family = family
+        return s
+
+    def _stream(self):
+        return ctypes.c_void_p(self._torch.cuda.current_stream(self.device).cuda_stream)
+
+    def score_device(self, profile, subbands=None, dmcurve=None, dmstat=None, params=None,
+                     features="all", family=_lib.PFX_FAMILY_PHCX, out=None, want_ier=True):
+        """All inputs are CUDA tensors on ``self.device`` (contiguous).  Asynchronous on the
+        current torch stream; returns device tensors."""
+        torch = self._torch
+        fbits = _FEATURES[features] if isinstance(features, str) else int(features)
+        n = profile.shape[0]
+        ncol = (22 if fbits & 1 else 0) + (8 if fbits & 2 else 0)
+        dev = profile.device
+        if out is None:
+            feat = torch.empty((n, ncol), dtype=torch.float64, device=dev)
+            status = torch.zeros((n,), dtype=torch.int32, device=dev)
+            ier = torch.zeros((n, _lib.PFX_NIER), dtype=torch.int8, device=dev) if (want_ier and fbits & 1) else None
+        else:
+            feat, status, ier = out.features, out.status, out.ier
+        for t in (profile, subbands, dmcurve, dmstat, params):
+            if t is not None and not t.is_contiguous():
+                raise PfxError("inputs must be contiguous")
+        shape = self.make_shape(profile, subbands, dmcurve, dmstat, family)
+        rc = self._lib.pfx_score_dev(self._h, ctypes.byref(shape), n, fbits, _ptr(profile), _ptr(subbands),
+                                     _ptr(dmcurve), _ptr(dmstat), _ptr(params), _ptr(feat), feat.shape[1],
+                                     _ptr(ier), _ptr(status), self._stream())
+        self._check(rc)
+        return Scores(feat, status, ier)
+
+    def score_host(self, profile, subbands=None, dmcurve=None, dmstat=None, params=None,
+                   features="all", family=_lib.PFX_FAMILY_PHCX, out=None, chunk=0, want_ier=True):
+        """Inputs are host arrays (numpy, or pinned torch CPU tensors for asynchronous copies).
+        Streams chunks H2D, scores them and copies the rows back; returns numpy arrays (or the
+        tensors passed in ``out``)."""
+        fbits = _FEATURES[features] if isinstance(features, str) else int(features)
+        n = profile.shape[0]
+        ncol = (22 if fbits & 1 else 0) + (8 if fbits & 2 else 0)
+        if out is None:
+            feat = np.empty((n, ncol), dtype=np.float64)
+            status = np.zeros((n,), dtype=np.int32)
+            ier = np.zeros((n, _lib.PFX_NIER), dtype=np.int8) if (want_ier and fbits & 1) else None
+        else:
+            feat, status, ier = out.features, out.status, out.ier
+        shape = self.make_shape(profile, subbands, dmcurve, dmstat, family)
+        rc = self._lib.pfx_score_host(self._h, ctypes.byref(shape), n, fbits, _ptr(profile), _ptr(subbands),
+                                      _ptr(dmcurve), _ptr(dmstat), _ptr(params), _ptr(feat), feat.shape[1],
+                                      _ptr(ier), _ptr(status), int(chunk))
+        self._check(rc)
+        return Scores(feat, status, ier)
+
+    # ---- one entry per operator-API method (ProfileOperationsInterface.py:69-130) ---------
+    def _group(self, fn, n, ncol_needed, args, want_ier=True):
+        torch = self._torch
+        dev = torch.device("cuda", self.device)
+        feat = torch.full((n, 22), float("nan"), dtype=torch.float64, device=dev)
+        status = torch.zeros((n,), dtype=torch.int32, device=dev)
+        ier = torch.zeros((n, _lib.PFX_NIER), dtype=torch.int8, device=dev)
+        return feat, status, ier
+
+    def sinusoid(self, profile):
+        feat, status, ier = self._group(None, profile.shape[0], 4, None)
+        shape = self.make_shape(profile)
+        self._check(self._lib.pfx_sinusoid_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
+                                               _ptr(feat), 22, _ptr(ier), _ptr(status), self._stream()))
+        return Scores(feat[:, 0:4], status, ier)
+
+    def gaussian(self, profile):
+        feat, status, ier = self._group(None, profile.shape[0], 11, None)
+        shape = self.make_shape(profile)
+        self._check(self._lib.pfx_gaussian_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
+                                               _ptr(feat), 22, _ptr(ier), _ptr(status), self._stream()))
+        return Scores(feat[:, 4:11], status, ier)
+
+    def dmfit(self, profile, dmcurve, params, family=_lib.PFX_FAMILY_PHCX):
+        feat, status, ier = self._group(None, profile.shape[0], 19, None)
+        shape = self.make_shape(profile, None, dmcurve, None, family)
+        self._check(self._lib.pfx_dmfit_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
+                                            _ptr(dmcurve), _ptr(params), _ptr(feat), 22, _ptr(ier), _ptr(status),
+                                            self._stream()))
+        return Scores(feat[:, 11:19], status, ier)
+
+    def subband(self, profile, subbands, params):
+        feat, status, ier = self._group(None, profile.shape[0], 22, None)
+        shape = self.make_shape(profile, subbands)
+        self._check(self._lib.pfx_subband_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
+                                              _ptr(subbands), _ptr(params), _ptr(feat), 22, _ptr(status),
+                                              self._stream()))
+        return Scores(feat[:, 19:22], status, None)
+
+    def lyon8(self, profile, dmstat):
+        torch = self._torch
+        n = profile.shape[0]
+        feat = torch.empty((n, 8), dtype=torch.float64, device=profile.device)
+        shape = self.make_shape(profile, None, None, dmstat)
+        self._check(self._lib.pfx_lyon8_dev(self._h, ctypes.byref(shape), n, _ptr(profile), _ptr(dmstat),
+                                            _ptr(feat), 8, self._stream()))
+        return Scores(feat, None, None)

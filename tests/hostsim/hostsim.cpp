@@ -1,0 +1,98 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the scoring routines of pulsarfeatureextractor_b200/csrc (the same templates the CUDA
+// kernels instantiate with 32-lane groups) for the host with a one-lane group, so the kernel
+// LOGIC (MINPACK port, histogram, peak stripping, status bits ...) can be checked against the
+// oracle on machines without a GPU.  It is built by tests/hostsim/build.sh into
+// tests/hostsim/_hostsim.so and loaded only by tests/test_hostsim_logic.py.  The product
+// package never loads it: pulsarfeatureextractor_b200 has no CPU path.
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../pulsarfeatureextractor_b200/csrc/pfx_driver.cuh"
+
+using namespace pfx;
+typedef Group<1> G1;
+
+extern "C" {
+
+int hs_sinusoid(const void* profile, int dtype, int m, double* feat, int8_t* ier) {
+    std::vector<double> ws(sin_work_doubles(m) + 16);
+    G1 g;
+    sinusoid_candidate(g, ws.data(), profile, dtype, 0, m, feat, ier);
+    return 0;
+}
+
+unsigned hs_gaussian(const void* profile, int dtype, int m, int cap_smem, int cap_global,
+                     double* feat, int8_t* ier) {
+    std::vector<double> ws(hist_work_doubles(m, cap_smem) + 16);
+    std::vector<double> gs(hist_scratch_doubles(cap_global) + 16);
+    G1 g;
+    double pow_m = pow((double)m, -0.3333333), pow_m1 = pow((double)(m - 1), -0.3333333);
+    double ph_expect = NAN;
+    unsigned st = hist_candidate(g, ws.data(), cap_smem, cap_global > 0 ? gs.data() : nullptr, cap_global,
+                                 profile, dtype, 0, m, pow_m, pow_m1, feat, ier, &ph_expect);
+    if (st & PFX_ST_FAIL_MASK) return st;
+    std::vector<double> ws2(gauss_work_doubles(m) + 16);
+    st |= gauss_candidate(g, ws2.data(), profile, dtype, 0, m, ph_expect, feat, ier);
+    return st;
+}
+
+unsigned hs_dmfit(const void* dmcurve, int dm_dtype, int n_dm, int family, const double* prm,
+                  double* feat, int8_t* ier) {
+    std::vector<double> ws(dm_work_doubles(n_dm) + 16);
+    G1 g;
+    return dmfit_candidate(g, ws.data(), dmcurve, dm_dtype, 0, n_dm, family, prm, feat, ier);
+}
+
+unsigned hs_subband(const void* profile, const void* subbands, int dtype, int nbin, int nsub,
+                    double width, double* feat) {
+    std::vector<double> ws(sub_work_doubles(nbin, nsub) + 16);
+    G1 g;
+    return subband_candidate(g, ws.data(), profile, subbands, dtype, 0, nbin, nsub, width, feat);
+}
+
+void hs_lyon4(const void* data, int dtype, int len, double* out) {
+    G1 g;
+    lyon4_row(g, data, dtype, 0, len, out);
+}
+
+}  // extern "C"
+
+// ---- generic LM with a caller-supplied residual (Python callback) -------------------------
+// Lets tests run the SAME numpy residual through scipy.optimize.leastsq and through this port.
+typedef void (*hs_resid_cb)(const double* p, double* out);
+template <int NP>
+struct CallbackModel {
+    hs_resid_cb cb;
+    template <class G>
+    void eval(const G&, const double (&p)[NP], double* out, int) const { cb(p, out); }
+};
+template <int NP>
+static int run_cb(int m, double* x, hs_resid_cb cb, int* nfev) {
+    std::vector<double> buf((NP + 2) * (size_t)m + 16);
+    LmShared s;
+    LmVec v;
+    v.fvec = buf.data();
+    v.wa4 = buf.data() + m;
+    v.fjac = buf.data() + 2 * (size_t)m;
+    v.ld = m;
+    CallbackModel<NP> f;
+    f.cb = cb;
+    double p[NP];
+    for (int i = 0; i < NP; ++i) p[i] = x[i];
+    G1 g;
+    int info = lmdif<NP>(g, f, m, p, v, s, *nfev);
+    for (int i = 0; i < NP; ++i) x[i] = p[i];
+    return info;
+}
+extern "C" int hs_lmdif_cb(int n, int m, double* x, hs_resid_cb cb, int* nfev) {
+    switch (n) {
+        case 2: return run_cb<2>(m, x, cb, nfev);
+        case 3: return run_cb<3>(m, x, cb, nfev);
+        case 4: return run_cb<4>(m, x, cb, nfev);
+        case 8: return run_cb<8>(m, x, cb, nfev);
+    }
+    return -100;
+}
