@@ -51,7 +51,7 @@ FAST_CORR = False
 # "Perturbed twin" (SURVEY.md section 8c tolerances): the same oracle with the residual expressions
 # re-associated (algebraically identical, a few ulp different).  oracle-vs-twin scatter is the
 # noise floor any independent implementation is judged against on ill-conditioned fits.
-TWIN = False
+TWIN = False      # False, 1 (first twin) or 2 (second twin)
 
 # --- per-candidate status bits (mirrored in include/pfx.h) --------------------------------
 ST_HIST_ZERO_BINS = 1 << 0    # numpy.histogram(bins=0) -> ValueError        (PO:657,678)
@@ -246,6 +246,8 @@ def fit_sine(y, maxima, log=None):
 
     def resid(p, x, y, amp, bg):
         f, phi = p
+        if TWIN == 2:
+            return y - (abs(amp) * np.sin(2 * np.pi * (f * x) + phi) + abs(bg))
         if TWIN:
             return (y - abs(bg)) - abs(amp) * np.sin(phi + (2 * np.pi * x) * f)
         return y - (abs(amp) * np.sin(2 * np.pi * f * x + phi) + abs(bg))
@@ -269,6 +271,9 @@ def fit_sine_sqr(y, maxima, log=None):
 
     def resid(p, x, y, amp, bg):
         f, phi = p
+        if TWIN == 2:
+            sn = np.sin(2 * np.pi * (f * x) + phi)
+            return y - abs(amp) * (sn * sn) + abs(bg)
         if TWIN:
             sn = np.sin(phi + (2 * np.pi * x) * f)
             return (y + abs(bg)) - abs(amp) * (sn * sn)
@@ -338,6 +343,8 @@ def _histogram(data, nbins):
 
 def _gexp(x, mu, sigma):
     """exp(-((x-mu)/sigma)^2 / 2) as the reference writes it, or re-associated for the twin."""
+    if TWIN == 2:
+        return np.exp(-((x - mu) ** 2) / (2 * sigma * sigma))
     if TWIN:
         return np.exp(-0.5 * ((x - mu) * (1.0 / sigma)) ** 2)
     return np.exp((-((x - mu) / sigma) ** 2) / 2)
@@ -712,6 +719,9 @@ def dm_fittings_phcx(curve_y, curve_x, length_all, snr, dm, period_ms, width, dm
 
         def model(x, p):
             amp, prop, shift = p
+            if TWIN == 2:
+                weff = np.sqrt(wint + pow(prop * (kdm * abs((dm + shift) - x) * df) / pow(f, 3), 2))
+                return amp * (np.sqrt(period_ms - weff) / np.sqrt(weff))
             if TWIN:
                 weff = np.sqrt(wint + pow((prop * (kdm * df / pow(f, 3))) * abs((dm + shift) - x), 2))
                 return amp * np.sqrt(period_ms / weff - 1.0)

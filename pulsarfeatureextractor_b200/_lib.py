@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpfx.so")
+LIB_PATH = os.environ.get("PFX_LIB") or os.path.join(_HERE, "libpfx.so")
 
 PFX_U8, PFX_F32, PFX_F64 = 0, 1, 2
 PFX_FAMILY_PHCX, PFX_FAMILY_PFD = 0, 1

@@ -10,6 +10,19 @@
 
 using namespace pfx;
 
+#if defined(PFX_PROFILE)
+__device__ unsigned long long pfx_prof[16];
+extern "C" int pfx_prof_dump(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, pfx_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(pfx_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 int pfx::set_err(pfx_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
         va_list ap;

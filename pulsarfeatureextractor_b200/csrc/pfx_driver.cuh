@@ -82,26 +82,16 @@ PFX_HD inline unsigned hist_candidate(const G& g, double* ws, int cap_smem, doub
     double* q = h.srt + next_pow2(m);
     load_row(g, profile, dtype, cand, m, h.y);
     g.sync();
-    auto carve = [&](double* base, int cap) {
-        h.hx = base;
-        h.hy = base + cap;
-        h.cnt = (int*)(base + 2 * cap);
-        h.v.fvec = base + 3 * cap;
-        h.v.wa4 = base + 4 * cap;
-        h.v.fjac = base + 5 * cap;
-        h.v.ld = cap;
-        h.cap = cap;
-    };
-    carve(q, cap_smem);
+    h.hx = q;
+    h.hy = q + cap_smem;
+    h.cnt = (int*)(q + 2 * cap_smem);
+    h.v.fvec = q + 3 * cap_smem;
+    h.v.wa4 = q + 4 * cap_smem;
+    h.v.fjac = q + 5 * cap_smem;
+    h.v.ld = cap_smem;
+    h.cap = cap_smem;
     h.ph_expect = NAN;
-    unsigned st = hist_scores(g, h, m, pow_m, pow_m1, dtype == PFX_U8, feat, ier);
-    if ((st & PFX_ST_HIST_OVERFLOW) && gscratch != nullptr && cap_global > cap_smem) {
-        // oversized histogram: redo the stage with the group's global scratch slot
-        st &= ~PFX_ST_HIST_OVERFLOW;
-        g.sync();
-        carve(gscratch, cap_global);
-        st |= hist_scores(g, h, m, pow_m, pow_m1, dtype == PFX_U8, feat, ier);
-    }
+    unsigned st = hist_scores(g, h, m, pow_m, pow_m1, dtype == PFX_U8, gscratch, cap_global, feat, ier);
     g.sync();
     *ph_expect = h.ph_expect;
     return st;

@@ -18,9 +18,11 @@
 #if defined(__CUDACC__)
 #define PFX_HD __host__ __device__
 #define PFX_D __device__
+#define PFX_NOINLINE __noinline__
 #else
 #define PFX_HD
 #define PFX_D
+#define PFX_NOINLINE __attribute__((noinline))
 #endif
 
 #if defined(__CUDA_ARCH__)

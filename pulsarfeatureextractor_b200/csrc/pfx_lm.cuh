@@ -12,6 +12,24 @@
 
 #include "pfx_group.cuh"
 
+// Optional phase timers (development builds with -DPFX_PROFILE): cycles spent per LM phase,
+// accumulated by the group leader into pfx_prof[] and dumped by pfx_prof_dump().
+#if defined(PFX_PROFILE) && defined(__CUDA_ARCH__)
+extern __device__ unsigned long long pfx_prof[16];
+#define PFX_T0() long long t_prof_ = clock64()
+#define PFX_TACC(slot)                                                        \
+    do {                                                                      \
+        long long t_now_ = clock64();                                         \
+        if (g.leader()) atomicAdd(&pfx_prof[slot], (unsigned long long)(t_now_ - t_prof_)); \
+        t_prof_ = t_now_;                                                     \
+    } while (0)
+#define PFX_TCOUNT(slot) do { if (g.leader()) atomicAdd(&pfx_prof[slot], 1ULL); } while (0)
+#else
+#define PFX_T0() do {} while (0)
+#define PFX_TACC(slot) do {} while (0)
+#define PFX_TCOUNT(slot) do {} while (0)
+#endif
+
 namespace pfx {
 
 constexpr int NPMAX = 8;
@@ -40,7 +58,7 @@ PFX_HD inline double enorm_seq(int n, const double* x) {
 }
 
 // MINPACK qrsolv on the n x n system, r column major with leading dimension NPMAX.
-PFX_HD inline void qrsolv_seq(int n, double* r, const int* ipvt, const double* diag,
+PFX_HD PFX_NOINLINE inline void qrsolv_seq(int n, double* r, const int* ipvt, const double* diag,
                               const double* qtb, double* x, double* sdiag, double* wa) {
     const int ld = NPMAX;
     for (int j = 0; j < n; ++j) {
@@ -97,7 +115,7 @@ PFX_HD inline void qrsolv_seq(int n, double* r, const int* ipvt, const double* d
 }
 
 // MINPACK lmpar.
-PFX_HD inline void lmpar_seq(int n, double* r, const int* ipvt, const double* diag,
+PFX_HD PFX_NOINLINE inline void lmpar_seq(int n, double* r, const int* ipvt, const double* diag,
                              const double* qtb, double delta, double& par, double* x,
                              double* sdiag, double* wa1, double* wa2) {
     const int ld = NPMAX;
@@ -214,6 +232,14 @@ struct LmVec {
     int ld;
 };
 
+// Residual evaluation is kept out of line: lmdif calls it from three places and the models
+// carry exp / sin, so inlining would triple the hot code (instruction-cache misses dominated
+// the first version of these kernels).
+template <int NP, class G, class Model>
+PFX_HD PFX_NOINLINE void lm_eval(const G& g, const Model& f, const double (&p)[NP], double* out, int m) {
+    f.eval(g, p, out, m);
+}
+
 // Returns MINPACK's info (scipy's ier).  x: start on entry, solution on exit (replicated in
 // every lane).  Model::eval(g, p, out, m) writes the residual rows owned by the calling lane.
 template <int NP, class G, class Model>
@@ -230,9 +256,12 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
     int info = 0;
     int nfev = 0;
 
-    f.eval(g, x, fvec, m);
+    PFX_T0();
+    PFX_TCOUNT(8);
+    lm_eval<NP>(g, f, x, fvec, m);
     nfev = 1;
     double fnorm = sqrt(rows_sumsq(g, fvec, 0, m));
+    PFX_TACC(0);
     double par = 0.0;
     int iter = 1;
     double diag[NP], qtf[NP], acnorm[NP], rdiag[NP], wa[NP], xnew[NP], p[NP];
@@ -243,92 +272,101 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
 
     for (;;) {
         // ---- fdjac2: forward-difference Jacobian ------------------------------------------
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < NP; ++j) {
-            double temp = x[j];
+            double temp = vget<NP>(x, j);
             double h = eps * fabs(temp);
             if (h == 0.0) h = eps;
-            x[j] = temp + h;
-            f.eval(g, x, wa4, m);
-            x[j] = temp;
+            vset<NP>(x, j, temp + h);
+            lm_eval<NP>(g, f, x, wa4, m);
+            vset<NP>(x, j, temp);
             double* col = v.fjac + j * ld;
             for (int i = g.lane(); i < m; i += G::W) col[i] = (wa4[i] - fvec[i]) / h;
         }
         nfev += NP;
+        PFX_TACC(1);
+        PFX_TCOUNT(9);
 
         // ---- qrfac with column pivoting ---------------------------------------------------
-#pragma unroll
+        // (loops are deliberately not unrolled; the small vectors live in registers and are
+        // indexed with select chains)
+#pragma unroll 1
         for (int j = 0; j < NP; ++j) {
-            acnorm[j] = sqrt(rows_sumsq(g, v.fjac + j * ld, 0, m));
-            rdiag[j] = acnorm[j];
-            wa[j] = rdiag[j];
-            ipvt[j] = j;
+            double a = sqrt(rows_sumsq(g, v.fjac + j * ld, 0, m));
+            vset<NP>(acnorm, j, a);
+            vset<NP>(rdiag, j, a);
+            vset<NP>(wa, j, a);
+            iset<NP>(ipvt, j, j);
         }
-#pragma unroll
-        for (int j = 0; j < NP; ++j) {
-            if (j < m) {
-                int kmax = j;
-                double best = rdiag[j];
-#pragma unroll
-                for (int k = j + 1; k < NP; ++k)
-                    if (rdiag[k] > best) {
-                        best = rdiag[k];
-                        kmax = k;
-                    }
-                double* cj = v.fjac + j * ld;
-                if (kmax != j) {
-                    double* ck = v.fjac + kmax * ld;
-                    for (int i = g.lane(); i < m; i += G::W) {
-                        double t = cj[i];
-                        cj[i] = ck[i];
-                        ck[i] = t;
-                    }
-                    vset<NP>(rdiag, kmax, rdiag[j]);
-                    vset<NP>(wa, kmax, wa[j]);
-                    int t = ipvt[j];
-                    ipvt[j] = iget<NP>(ipvt, kmax);
-                    iset<NP>(ipvt, kmax, t);
+        const int minmn = (m < NP) ? m : NP;
+#pragma unroll 1
+        for (int j = 0; j < minmn; ++j) {
+            int kmax = j;
+            double best = vget<NP>(rdiag, j);
+#pragma unroll 1
+            for (int k = j + 1; k < NP; ++k) {
+                double rk = vget<NP>(rdiag, k);
+                if (rk > best) {
+                    best = rk;
+                    kmax = k;
                 }
-                double ajnorm = sqrt(rows_sumsq(g, cj, j, m));
-                if (ajnorm != 0.0) {
-                    g.sync();
-                    if (cj[j] < 0.0) ajnorm = -ajnorm;
-                    g.sync();
-                    for (int i = g.lane(); i < m; i += G::W)
-                        if (i >= j) {
-                            double t = cj[i] / ajnorm;
-                            if (i == j) t += 1.0;
-                            cj[i] = t;
-                        }
-                    g.sync();
-                    const double ajj = cj[j];
-#pragma unroll
-                    for (int k = j + 1; k < NP; ++k) {
-                        double* ck = v.fjac + k * ld;
-                        double sum = rows_dot(g, cj, ck, j, m);
-                        double temp = sum / ajj;
-                        for (int i = g.lane(); i < m; i += G::W)
-                            if (i >= j) ck[i] -= temp * cj[i];
-                    }
-                    g.sync();
-#pragma unroll
-                    for (int k = j + 1; k < NP; ++k) {
-                        if (rdiag[k] != 0.0) {
-                            const double* ck = v.fjac + k * ld;
-                            double temp = ck[j] / rdiag[k];
-                            rdiag[k] *= sqrt(fmax(0.0, 1.0 - temp * temp));
-                            double q = rdiag[k] / wa[k];
-                            if (0.05 * (q * q) <= epsmch) {
-                                rdiag[k] = sqrt(rows_sumsq(g, ck, j + 1, m));
-                                wa[k] = rdiag[k];
-                            }
-                        }
-                    }
-                }
-                rdiag[j] = -ajnorm;
             }
+            double* cj = v.fjac + j * ld;
+            if (kmax != j) {
+                double* ck = v.fjac + kmax * ld;
+                for (int i = g.lane(); i < m; i += G::W) {
+                    double t = cj[i];
+                    cj[i] = ck[i];
+                    ck[i] = t;
+                }
+                vset<NP>(rdiag, kmax, vget<NP>(rdiag, j));
+                vset<NP>(wa, kmax, vget<NP>(wa, j));
+                int t = iget<NP>(ipvt, j);
+                iset<NP>(ipvt, j, iget<NP>(ipvt, kmax));
+                iset<NP>(ipvt, kmax, t);
+            }
+            double ajnorm = sqrt(rows_sumsq(g, cj, j, m));
+            if (ajnorm != 0.0) {
+                g.sync();
+                if (cj[j] < 0.0) ajnorm = -ajnorm;
+                g.sync();
+                for (int i = g.lane(); i < m; i += G::W)
+                    if (i >= j) {
+                        double t = cj[i] / ajnorm;
+                        if (i == j) t += 1.0;
+                        cj[i] = t;
+                    }
+                g.sync();
+                const double ajj = cj[j];
+#pragma unroll 1
+                for (int k = j + 1; k < NP; ++k) {
+                    double* ck = v.fjac + k * ld;
+                    double sum = rows_dot(g, cj, ck, j, m);
+                    double temp = sum / ajj;
+                    for (int i = g.lane(); i < m; i += G::W)
+                        if (i >= j) ck[i] -= temp * cj[i];
+                }
+                g.sync();
+#pragma unroll 1
+                for (int k = j + 1; k < NP; ++k) {
+                    double rk = vget<NP>(rdiag, k);
+                    if (rk != 0.0) {
+                        const double* ck = v.fjac + k * ld;
+                        double temp = ck[j] / rk;
+                        rk *= sqrt(fmax(0.0, 1.0 - temp * temp));
+                        double q = rk / vget<NP>(wa, k);
+                        if (0.05 * (q * q) <= epsmch) {
+                            rk = sqrt(rows_sumsq(g, ck, j + 1, m));
+                            vset<NP>(wa, k, rk);
+                        }
+                        vset<NP>(rdiag, k, rk);
+                    }
+                }
+            }
+            vset<NP>(rdiag, j, -ajnorm);
         }
 
+        PFX_TACC(2);
         if (iter == 1) {
             double sq = 0.0;
 #pragma unroll
@@ -346,8 +384,9 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
         // ---- (Q^T fvec)[0..n) ---------------------------------------------------------------
         for (int i = g.lane(); i < m; i += G::W) wa4[i] = fvec[i];
         g.sync();
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < NP; ++j) {
+            double qj = 0.0;
             if (j < m) {
                 const double* cj = v.fjac + j * ld;
                 const double ajj = cj[j];
@@ -358,27 +397,25 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
                         if (i >= j) wa4[i] += cj[i] * temp;
                 }
                 g.sync();
-                qtf[j] = wa4[j];
-            } else {
-                qtf[j] = 0.0;
+                qj = wa4[j];
             }
+            vset<NP>(qtf, j, qj);
         }
 
+        PFX_TACC(3);
         // ---- norm of the scaled gradient ----------------------------------------------------
         gnorm = 0.0;
         if (fnorm != 0.0) {
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < NP; ++j) {
-                int l = ipvt[j];
+                int l = iget<NP>(ipvt, j);
                 double al = vget<NP>(acnorm, l);
                 if (al != 0.0) {
                     const double* cj = v.fjac + j * ld;
                     double sum = 0.0;
-#pragma unroll
-                    for (int i = 0; i < NP; ++i) {
-                        if (i < j) sum += cj[i] * (qtf[i] / fnorm);
-                    }
-                    sum += rdiag[j] * (qtf[j] / fnorm);
+#pragma unroll 1
+                    for (int i = 0; i < j; ++i) sum += cj[i] * (vget<NP>(qtf, i) / fnorm);
+                    sum += vget<NP>(rdiag, j) * (vget<NP>(qtf, j) / fnorm);
                     gnorm = fmax(gnorm, fabs(sum / al));   // fmax: a NaN never replaces gnorm
                 }
             }
@@ -390,20 +427,22 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
 
         // leader: publish R, permutation, Q^T f and the scaling for the n x n sub-problem
         if (g.leader()) {
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < NP; ++j) {
                 const double* cj = v.fjac + j * ld;
                 for (int i = 0; i < j; ++i) s.r[i + NPMAX * j] = cj[i];
-                s.r[j + NPMAX * j] = rdiag[j];
-                s.ipvt[j] = ipvt[j];
-                s.qtf[j] = qtf[j];
-                s.diag[j] = diag[j];
+                s.r[j + NPMAX * j] = vget<NP>(rdiag, j);
+                s.ipvt[j] = iget<NP>(ipvt, j);
+                s.qtf[j] = vget<NP>(qtf, j);
+                s.diag[j] = vget<NP>(diag, j);
             }
         }
         g.sync();
 
+        PFX_TACC(4);
         // ---- inner loop ---------------------------------------------------------------------
         for (;;) {
+            PFX_TCOUNT(10);
             if (g.leader()) {
                 double lpar = par;
                 lmpar_seq(NP, s.r, s.ipvt, s.diag, s.qtf, delta, lpar, s.step, s.sdiag, s.wa1, s.wa2);
@@ -428,12 +467,14 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
                 sq += t * t;
             }
             g.sync();
+            PFX_TACC(5);
             const double pnorm = sqrt(sq);
             if (iter == 1) delta = fmin(delta, pnorm);
 
-            f.eval(g, xnew, wa4, m);
+            lm_eval<NP>(g, f, xnew, wa4, m);
             ++nfev;
             const double fnorm1 = sqrt(rows_sumsq(g, wa4, 0, m));
+            PFX_TACC(6);
 
             double actred = -1.0;
             if (p1 * fnorm1 < fnorm) {
@@ -483,6 +524,7 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
             if (delta <= epsmch * xnorm) info = 7;
             if (gnorm <= epsmch) info = 8;
             if (info != 0) break;
+            PFX_TACC(7);
             if (ratio >= p0001) break;   // successful step: new Jacobian
         }
         if (info != 0) break;

@@ -104,6 +104,8 @@ struct Gauss4AbsModel {
     PFX_HD double at(const double (&p)[4], double xv) const {
         return PFX_ADD(PFX_MUL(fabs(p[2]), gauss_core(xv, p[1], p[0])), fabs(p[3]));
     }
+    // curve on the full bin grid x = 0..m-1 (PO:1391, 1413-1414)
+    PFX_HD double fit(const double (&p)[4], int i) const { return at(p, (double)i); }
     template <class G>
     PFX_HD void eval(const G& g, const double (&p)[4], double* out, int m) const {
         for (int i = g.lane(); i < m; i += G::W) out[i] = PFX_SUB(y[i], at(p, x[i]));
@@ -136,6 +138,7 @@ struct DmPhcxModel {
         double weff = sqrt(PFX_ADD(wint, PFX_MUL(q, q)));
         return PFX_MUL(amp, sqrt(PFX_DIV(PFX_SUB(period, weff), weff)));
     }
+    PFX_HD double fit(const double (&p)[3], int i) const { return curve(p[0], p[1], p[2], x[i]); }
     template <class G>
     PFX_HD void eval(const G& g, const double (&p)[3], double* out, int m) const {
         for (int i = g.lane(); i < m; i += G::W) out[i] = PFX_SUB(y[i], curve(p[0], p[1], p[2], x[i]));
@@ -160,6 +163,23 @@ struct DmPfdModel {
             out[i] = PFX_SUB(y[i], curve(p[0], p[1], p[2], p[3], x[i]));
     }
 };
+
+// Evaluate the fitted curve on every row, out of line (one copy per model; see lm_eval).
+template <int NP, class G, class Model>
+PFX_HD PFX_NOINLINE void fit_rows(const G& g, const Model& f, const double (&p)[NP], double* out, int m) {
+    for (int i = g.lane(); i < m; i += G::W) out[i] = f.fit(p, i);
+}
+
+// sum over own rows of (y - fit)^2, joined over the group
+template <class G>
+PFX_HD inline double chisq_rows(const G& g, const double* y, const double* fit, int m) {
+    double c = 0.0;
+    for (int i = g.lane(); i < m; i += G::W) {
+        double d = y[i] - fit[i];
+        c = PFX_FMA(d, d, c);
+    }
+    return g.sum(c);
+}
 
 // =============================================================================================
 // scores 1-4                                                                   PO:190-587
@@ -231,12 +251,8 @@ PFX_HD inline void sinusoid_scores(const G& g, const SinWork& w, int m, double* 
         int nfev;
         int info = lmdif<2>(g, f, m, p, w.v, *w.s, nfev);
         if (ier && g.leader()) ier[PFX_FIT_SINE] = (int8_t)info;
-        double c = 0.0;
-        for (int i = g.lane(); i < m; i += G::W) {
-            double d = y[i] - f.fit(p, i);
-            c = PFX_FMA(d, d, c);
-        }
-        chi1 = g.sum(c) / (double)m;
+        fit_rows<2>(g, f, p, w.v.wa4, m);
+        chi1 = chisq_rows(g, y, w.v.wa4, m) / (double)m;
     }
     // score 2, PO:495-587
     {
@@ -252,12 +268,8 @@ PFX_HD inline void sinusoid_scores(const G& g, const SinWork& w, int m, double* 
         int nfev;
         int info = lmdif<2>(g, f, m, p, w.v, *w.s, nfev);
         if (ier && g.leader()) ier[PFX_FIT_SINESQ] = (int8_t)info;
-        double c = 0.0;
-        for (int i = g.lane(); i < m; i += G::W) {
-            double d = y[i] - f.fit(p, i);
-            c = PFX_FMA(d, d, c);
-        }
-        chi2 = g.sum(c) / (double)m;
+        fit_rows<2>(g, f, p, w.v.wa4, m);
+        chi2 = chisq_rows(g, y, w.v.wa4, m) / (double)m;
     }
     if (g.leader()) {
         feat[0] = chi1 / (double)maxima;   // maxima == 0 -> inf / nan, as numpy does (PO:373-374)
@@ -319,7 +331,7 @@ PFX_HD inline double percentile_sorted(const double* srt, int n, double per) {
 // POI:138-166 on data d[0..n); returns nbins (may be 0 or huge).  pow_n = pow(n, -0.3333333)
 // evaluated on the host with the C library (what Python's pow does).
 template <class G>
-PFX_HD inline long long fd_bins(const G& g, const double* d, int n, double* srt, double pow_n,
+PFX_HD PFX_NOINLINE long long fd_bins(const G& g, const double* d, int n, double* srt, double pow_n,
                                bool int_data, double& dmin, double& dmax) {
     int n2 = 1;
     while (n2 < n) n2 <<= 1;
@@ -346,7 +358,7 @@ PFX_HD inline long long fd_bins(const G& g, const double* d, int n, double* srt,
 // numpy.histogram(d, nb) uniform-bin path (numpy/lib/_histograms_impl.py:814-873); fills
 // hx[0..nb) with the left edges and hy[0..nb) with the counts.
 template <class G>
-PFX_HD inline void np_histogram(const G& g, const double* d, int n, int nb, double first, double last,
+PFX_HD PFX_NOINLINE void np_histogram(const G& g, const double* d, int n, int nb, double first, double last,
                                 double* hx, double* hy, int* cnt) {
     if (first == last) {
         first -= 0.5;
@@ -385,7 +397,7 @@ PFX_HD inline void np_histogram(const G& g, const double* d, int n, int nb, doub
 // PO:774-983.  On entry hx/hy hold nb bins; they are zero-padded to 3 points when shorter.
 // Returns status bits; p = (sigma, mu, max) of the last fit done.
 template <class G>
-PFX_HD inline unsigned fit_gaussian_hist(const G& g, HistWork& w, int nb, double (&p)[3],
+PFX_HD PFX_NOINLINE unsigned fit_gaussian_hist(const G& g, HistWork& w, int nb, double (&p)[3],
                                         int8_t* ier, int slot, int count_slot) {
     double* hx = w.hx;
     double* hy = w.hy;
@@ -421,12 +433,8 @@ PFX_HD inline unsigned fit_gaussian_hist(const G& g, HistWork& w, int nb, double
         int info = lmdif<3>(g, f, mfit, p, w.v, *w.s, nfev);
         ++nfits;
         if (ier && g.leader()) ier[slot] = (int8_t)info;
-        double c = 0.0;
-        for (int i = g.lane(); i < n0; i += G::W) {
-            double d = hy[i] - f.fit(p, i);
-            c = PFX_FMA(d, d, c);
-        }
-        const double chisq = g.sum(c) / (double)mfit;
+        fit_rows<3>(g, f, p, w.v.wa4, n0);
+        const double chisq = chisq_rows(g, hy, w.v.wa4, n0) / (double)mfit;
         if ((chisq > meansq * (double)n0) && (p[0] < 0.2 * (double)n0)) {
             ++counter;
             // temp = delete(temp, first_max): counts with [first_max, first_max+counter) removed
@@ -470,25 +478,40 @@ PFX_HD inline unsigned fit_gaussian_hist(const G& g, HistWork& w, int nb, double
 }
 
 // scores 5, 6, 7 and the profile-histogram expectation needed by scores 8-11.
+// `w` arrives carved for shared memory (capacity w.cap); when a histogram has more bins than
+// that, the histogram and fit vectors are re-pointed at the group's global scratch slot
+// (gscratch, capacity cap_global) -- candidates are flagged, never truncated.
 template <class G>
 PFX_HD inline unsigned hist_scores(const G& g, HistWork& w, int m, double pow_m, double pow_m1,
-                                   bool int_data, double* feat, int8_t* ier) {
+                                   bool int_data, double* gscratch, int cap_global, double* feat,
+                                   int8_t* ier) {
     const double* y = w.y;
     unsigned st = 0;
     double dmin, dmax;
     // profile bins (POI:138-166 on the profile)
     long long nbp = fd_bins(g, y, m, w.srt, pow_m, int_data, dmin, dmax);
     const double pmin = dmin, pmax = dmax;
-    // derivative dy[i] = y[i] - y[i+1] (POI:170-186), built in the fvec area of the work vectors
-    double* dy = w.v.fjac;   // free until the first fit; needs m-1 <= cap*3
+    // derivative dy[i] = y[i] - y[i+1] (POI:170-186), staged in the shared-memory Jacobian area
+    double* dy = w.v.fjac;
     for (int i = g.lane(); i < m - 1; i += G::W) dy[i] = y[i] - y[i + 1];
     g.sync();
     long long nbd = fd_bins(g, dy, m - 1, w.srt, pow_m1, int_data, dmin, dmax);
     if (nbd < 1 || nbp < 1) return st | PFX_ST_HIST_ZERO_BINS;
-    if (nbd > w.cap || nbp > w.cap) return st | PFX_ST_HIST_OVERFLOW;
+    const long long nbmax = nbd > nbp ? nbd : nbp;
+    if (nbmax > w.cap) {
+        if (gscratch == nullptr || nbmax > cap_global) return st | PFX_ST_HIST_OVERFLOW;
+        w.hx = gscratch;
+        w.hy = gscratch + cap_global;
+        w.cnt = (int*)(gscratch + 2 * cap_global);
+        w.v.fvec = gscratch + 3 * cap_global;
+        w.v.wa4 = gscratch + 4 * cap_global;
+        w.v.fjac = gscratch + 5 * cap_global;
+        w.v.ld = cap_global;
+        w.cap = cap_global;
+    }
 
-    // derivative histogram + fit (PO:657-661).  dy lives in fjac, which lmdif overwrites, so the
-    // histogram is finished first.
+    // derivative histogram + fit (PO:657-661); the histogram is finished before the fit
+    // overwrites the staging area
     np_histogram(g, dy, m - 1, (int)nbd, dmin, dmax, w.hx, w.hy, w.cnt);
     double pd[3];
     st |= fit_gaussian_hist(g, w, (int)nbd, pd, ier, PFX_FIT_DYHIST, PFX_FIT_DYHIST_COUNT);
@@ -632,14 +655,8 @@ PFX_HD inline unsigned gauss_scores(const G& g, GaussWork& w, int m, double ph_e
         int info = lmdif<4>(g, f, m, p, w.v, *w.s, nfev);
         if (ier && g.leader()) ier[PFX_FIT_T1] = (int8_t)info;
         t1_fwhm = fabs(FWHM_K * p[0]);
-        double c = 0.0;
-        for (int i = g.lane(); i < m; i += G::W) {
-            double fi = f.fit(p, i);
-            w.t1fit[i] = fi;
-            double d = w.yr[i] - fi;
-            c = PFX_FMA(d, d, c);
-        }
-        t1_chi = g.sum(c) / (double)m;
+        fit_rows<4>(g, f, p, w.t1fit, m);
+        t1_chi = chisq_rows(g, w.yr, w.t1fit, m) / (double)m;
     }
     g.sync();
     if (g.leader()) {
@@ -708,9 +725,10 @@ PFX_HD inline unsigned gauss_scores(const G& g, GaussWork& w, int m, double ph_e
         const double nfwhm = fabs(FWHM_K * p[0]);
         const double lo = p[2] - (1.5 * nfwhm) / 2.0;
         const double hi = p[2] + (1.5 * nfwhm) / 2.0;
+        fit_rows<4>(g, f4, p, w.v.wa4, m);
         for (int i = g.lane(); i < m; i += G::W) {
             double xv = (double)i;
-            double ev = f4.at(p, xv);
+            double ev = w.v.wa4[i];
             double yv = yr[i];
             double nv;
             if (ev <= yv) nv = PFX_ADD(PFX_SUB(yv, ev), p[3]);
@@ -740,16 +758,17 @@ PFX_HD inline unsigned gauss_scores(const G& g, GaussWork& w, int m, double ph_e
     const double fwhm2 = fabs(FWHM_K * q[4]);
     double c = 0.0, cc = 0.0;
     const double bgmix = PFX_MUL(PFX_ADD(p1[3], p2[3]), 0.5);
+    fit_rows<8>(g, f8, q, w.ny, m);          // final fit
+    fit_rows<4>(g, f4, p1, w.v.wa4, m);      // fit1
+    fit_rows<4>(g, f4, p2, w.v.fvec, m);     // fit2
     for (int i = g.lane(); i < m; i += G::W) {
-        double fi = f8.fit(q, i);
-        w.ny[i] = fi;   // final fit
+        double fi = w.ny[i];
         if (fi >= 1.0) {
             double d = yr[i] - fi;
             c += (d * d) / (double)m;
         }
         // combifit = fit1 + fit2 - bg1 - bg2 + (bg1 + bg2)/2   (PO:1413-1415)
-        double xv = (double)i;
-        double cf = PFX_ADD(PFX_SUB(PFX_SUB(PFX_ADD(f4.at(p1, xv), f4.at(p2, xv)), p1[3]), p2[3]), bgmix);
+        double cf = PFX_ADD(PFX_SUB(PFX_SUB(PFX_ADD(w.v.wa4[i], w.v.fvec[i]), p1[3]), p2[3]), bgmix);
         w.nx[i] = cf;
         if (cf >= 1.0) {
             double d = yr[i] - cf;
@@ -855,8 +874,9 @@ PFX_HD inline unsigned dm_scores(const G& g, DmWork& w, int n_dm, int family, co
         prop = p[1];
         shift = p[2];
         double c = 0.0;
+        fit_rows<3>(g, f, p, w.v.wa4, n_dm);
         for (int i = g.lane(); i < n_dm; i += G::W) {
-            double fit = f.curve(p[0], p[1], p[2], w.x[i]);
+            double fit = w.v.wa4[i];
             if (fit >= 1.0) {
                 double d = w.y[i] - w.theo[i];
                 c = PFX_FMA(d, d, c);

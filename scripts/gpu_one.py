@@ -1,0 +1,21 @@
+"""Development helper: run one scoring call (for ncu).  usage: gpu_one.py <n> <all|gauss|lyon>"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from pulsarfeatureextractor_b200 import synth
+from pulsarfeatureextractor_b200.engine import Engine
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+what = sys.argv[2] if len(sys.argv) > 2 else "all"
+b = synth.generate(2, 0, n)
+eng = Engine(0); dev = torch.device("cuda", 0)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+prof, sub, dm, ds, par = t(b.profile), t(b.subbands), t(b.dmcurve), t(b.dmstat), t(b.params)
+if what == "gauss":
+    eng.gaussian(prof)
+elif what == "lyon":
+    eng.lyon8(prof, ds)
+else:
+    eng.score_device(prof, sub, dm, ds, par, features="all")
+torch.cuda.synchronize()
+print("done", eng.last_timing())

@@ -1,0 +1,219 @@
+"""
+CPU check of the KERNEL LOGIC: the scoring templates of pulsarfeatureextractor_b200/csrc compiled
+for the host with a one-lane group (tests/hostsim, test infrastructure only) against the oracle.
+
+* the MINPACK port (lmdif / lmpar / qrsolv / qrfac / fdjac2 of csrc/pfx_lm.cuh) is driven with the
+  SAME numpy residual callbacks as scipy.optimize.leastsq: identical ier on every fit, identical
+  nfev on >= 97 %;
+* deterministic scores (3, 4, 12-16, 19-22, Lyon-8) agree with the oracle to 1e-9, score 3 exactly;
+* status bits (which reference exception fires) agree on every candidate, edge cases included;
+* least-squares derived scores sit on the oracle's own noise floor (oracle vs its re-associated
+  twin), checked through quantiles.
+"""
+import ctypes
+import os
+import subprocess
+import warnings
+
+import numpy as np
+import pytest
+from scipy.optimize import leastsq
+
+import pfx_oracle as O
+from pulsarfeatureextractor_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "hostsim", "_hostsim.so")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    src = [os.path.join(HERE, "hostsim", "hostsim.cpp")] + \
+          [os.path.join(HERE, "..", "pulsarfeatureextractor_b200", "csrc", f)
+           for f in ("pfx_group.cuh", "pfx_lm.cuh", "pfx_scores.cuh", "pfx_driver.cuh")]
+    if (not os.path.isfile(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
+        subprocess.check_call(["sh", os.path.join(HERE, "hostsim", "build.sh")])
+    lib = ctypes.CDLL(SO)
+    for f in ("hs_gaussian", "hs_dmfit", "hs_subband"):
+        getattr(lib, f).restype = ctypes.c_uint
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def host_bates(lib, prof, sub, dmc, prm):
+    feat = np.full(22, np.nan)
+    ier = np.zeros(18, np.int8)
+    st = 0
+    lib.hs_sinusoid(P(prof), 0, prof.size, P(feat), P(ier))
+    st |= lib.hs_gaussian(P(prof), 0, prof.size, 192, 4096, P(feat), P(ier))
+    st |= lib.hs_dmfit(P(dmc), 0, dmc.size, 0, P(prm), P(feat), P(ier))
+    st |= lib.hs_subband(P(prof), P(sub), 0, prof.size, sub.shape[0], ctypes.c_double(prm[3]), P(feat))
+    return feat, ier, st
+
+
+CB = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double))
+
+
+def port_leastsq(lib, resid, p0, m):
+    n = len(p0)
+    x = np.array(p0, dtype=np.float64)
+
+    def cb(pp, out):
+        p = np.ctypeslib.as_array(pp, (n,)).copy()
+        with np.errstate(all="ignore"):
+            np.ctypeslib.as_array(out, (m,))[:] = resid(p)
+
+    nfev = ctypes.c_int(0)
+    info = lib.hs_lmdif_cb(n, m, x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), CB(cb), ctypes.byref(nfev))
+    return x, info, nfev.value
+
+
+def test_minpack_port_matches_scipy_on_identical_residuals(hs):
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(5)
+    xx = np.arange(128)
+    same_ier = same_nfev = total = 0
+    for t in range(60):
+        kind = t % 4
+        if kind == 0:
+            prof = rng.normal(0, 1, 128)
+        elif kind == 1:
+            prof = rng.uniform(5, 50) * np.exp(-0.5 * ((xx - rng.uniform(0, 128)) / rng.uniform(1, 12)) ** 2) + rng.normal(0, 1, 128)
+        elif kind == 2:
+            prof = (rng.uniform(5, 50) * np.exp(-0.5 * ((xx - rng.uniform(0, 128)) / rng.uniform(1, 12)) ** 2) +
+                    rng.uniform(5, 50) * np.exp(-0.5 * ((xx - rng.uniform(0, 128)) / rng.uniform(1, 12)) ** 2) + rng.normal(0, 1, 128))
+        else:
+            prof = rng.uniform(2, 10) * np.sin(2 * np.pi * rng.integers(1, 5) * xx / 128 + rng.uniform(0, 6)) + rng.normal(0, 1, 128)
+        y = np.round((prof - prof.min()) / (prof.max() - prof.min()) * 255)
+        amp = (y.max() - y.min()) / 2
+        fits = [
+            (lambda p: y - (abs(p[2]) * np.exp((-((xx - p[1]) / abs(p[0])) ** 2) / 2) + p[3]),
+             [np.std(y), float(np.argmax(y)), y.max(), 1.0]),
+            (lambda p: y - (amp * np.sin(2 * np.pi * p[0] * xx + p[1]) + amp), [2 / 127., -1 / (4 * 2 / 127.)]),
+            (lambda p: y - ((abs(p[2]) * np.exp((-((xx - p[1]) / abs(p[0])) ** 2) / 2)) +
+                            (abs(p[6]) * np.exp((-((xx - p[5]) / abs(p[4])) ** 2) / 2)) + (abs(p[3]) + abs(p[7])) / 2),
+             [5., float(np.argmax(y)), y.max(), 10., 8., float((np.argmax(y) + 40) % 128), y.max() / 2, 10.]),
+            (lambda p: y[:40] - (abs(p[2]) * np.exp((-((xx[:40] * 3.0 - p[1]) / p[0]) ** 2) / 2)),
+             [np.std(y[:40]), float(np.argmax(y[:40]) * 3.0), y[:40].max()]),
+        ]
+        for res, p0 in fits:
+            m = len(res(np.array(p0)))
+            with np.errstate(all="ignore"):
+                xs, _c, info, _m, ier = leastsq(res, p0, full_output=True)
+            xm, im, nf = port_leastsq(hs, res, p0, m)
+            total += 1
+            same_ier += int(ier == im)
+            same_nfev += int(info["nfev"] == nf)
+    assert same_ier == total
+    assert same_nfev >= 0.97 * total
+
+
+def test_nan_residuals_return_start_with_ier4(hs):
+    # NaN residuals -> x0 unchanged, ier 4, nfev n+1
+    res = lambda p: np.full(16, np.nan)
+    x, info, nfev = port_leastsq(hs, res, [1.0, 2.0, 3.0], 16)
+    assert info == 4 and nfev == 4 and list(x) == [1.0, 2.0, 3.0]
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xs, _c, inf, _m, ier = leastsq(res, [1.0, 2.0, 3.0], full_output=True)
+    assert ier == 4 and inf["nfev"] == 4
+
+
+@pytest.fixture(scope="module")
+def scored(hs):
+    warnings.simplefilter("ignore")
+    b = synth.generate(31, 0, 4096)
+    pick = list(range(96)) + [int(i) for k in range(synth.N_EDGE_KINDS) for i in np.nonzero(b.edge == k)[0][:2]]
+    rows = []
+    for i in pick:
+        prof = np.ascontiguousarray(b.profile[i])
+        sub = np.ascontiguousarray(b.subbands[i])
+        dmc = np.ascontiguousarray(b.dmcurve[i])
+        prm = np.ascontiguousarray(b.params[i])
+        r = O.bates22_phcx(prof.astype(np.int64), sub.astype(np.int64), dmc.astype(np.int64), prm)
+        tws = []
+        for level in (1, 2):
+            O.TWIN = level
+            try:
+                tws.append(O.bates22_phcx(prof.astype(np.int64), sub.astype(np.int64), dmc.astype(np.int64), prm))
+            finally:
+                O.TWIN = False
+        feat, ier, st = host_bates(hs, prof, sub, dmc, prm)
+        rows.append((i, r, tws, feat, ier, st, int(b.edge[i])))
+    return rows
+
+
+def _rel(a, c):
+    with np.errstate(all="ignore"):
+        e = np.abs(a - c) / np.maximum(np.abs(a), 1e-12)
+    e[(a == c) | (np.isnan(a) & np.isnan(c))] = 0
+    e[np.isnan(e)] = np.inf
+    return e
+
+
+def test_status_bits_match_oracle(scored):
+    for i, r, tws, feat, ier, st, edge in scored:
+        assert (r.status & O.ST_FAIL_MASK != 0) == (st & O.ST_FAIL_MASK != 0), (i, edge, hex(r.status), hex(st))
+        assert (r.status & O.ST_DG_SENTINEL) == (st & O.ST_DG_SENTINEL), (i, edge)
+        if st & O.ST_FAIL_MASK:
+            # same first failing group: the bits a group sets are the ones the oracle reports
+            assert (r.status & O.ST_FAIL_MASK) & st, (i, edge, hex(r.status), hex(st))
+
+
+def test_deterministic_scores(scored):
+    det = [2, 3, 11, 12, 13, 14, 15, 18, 19, 20, 21]          # 0-based columns
+    for i, r, tws, feat, ier, st, edge in scored:
+        ok = ~np.isnan(r.features)
+        if ok[2]:
+            assert feat[2] == r.features[2], (i, "score 3 must be bit-exact")
+        e = _rel(r.features, feat)
+        for k in det:
+            if ok[k]:
+                assert e[k] <= 1e-9, (i, k + 1, r.features[k], feat[k])
+
+
+def test_fit_scores_on_the_oracle_noise_floor(scored):
+    """Least-squares derived scores.  Many of the reference's fits are ill conditioned and react
+    chaotically to ulp-level changes, so the yardstick is the oracle's own
+    scatter under algebraically neutral re-association ("twins"):
+      Tier W  candidates on which twin 1 reproduces the oracle to 1e-8.  On them the port must
+              reproduce the oracle to 1e-6 at least as often as twin 2 does, minus 10 points
+              (the port differs from the oracle in more places than a twin does: libm exp/sin
+              instead of numpy's SIMD kernels, summation order of std/mean, nine chained fits).
+      all     the port's error quantiles stay within a factor of the twins'.
+      ier     agreement with the oracle's convergence flags no worse than the twins', minus 10 points."""
+    lm_cols = [0, 1, 4, 5, 6, 7, 8, 9, 10, 16, 17]
+    good = [(r, tws, feat, ier) for _i, r, tws, feat, ier, st, _e in scored if not (r.status & O.ST_FAIL_MASK)]
+    e_host = np.array([_rel(r.features, feat) for r, tws, feat, ier in good])
+    e_tw1 = np.array([_rel(r.features, tws[0].features) for r, tws, feat, ier in good])
+    e_tw2 = np.array([_rel(r.features, tws[1].features) for r, tws, feat, ier in good])
+    for k in lm_cols:
+        w = e_tw1[:, k] <= 1e-8
+        assert w.sum() >= 20
+        f_host = np.mean(e_host[w, k] <= 1e-6)
+        f_tw2 = np.mean(e_tw2[w, k] <= 1e-6)
+        assert f_host >= f_tw2 - 0.10, (k + 1, f_host, f_tw2, int(w.sum()))
+        for q in (0.5, 0.9):
+            hq = np.quantile(e_host[:, k], q)
+            tq = max(np.quantile(e_tw1[:, k], q), np.quantile(e_tw2[:, k], q))
+            assert hq <= max(20 * tq, 1e-7), (k + 1, q, hq, tq)
+    ier_host = np.mean([np.array_equal(ier[:16], r.ier[:16]) for r, tws, feat, ier in good])
+    ier_twin = np.mean([np.array_equal(tws[0].ier[:16], r.ier[:16]) for r, tws, feat, ier in good])
+    assert ier_host >= ier_twin - 0.10, (ier_host, ier_twin)
+
+
+def test_lyon_rows(hs):
+    rng = np.random.default_rng(2)
+    for dt, code in ((np.uint8, 0), (np.float32, 1), (np.float64, 2)):
+        x = np.ascontiguousarray(rng.integers(0, 256, 200).astype(dt))
+        out = np.zeros(4)
+        hs.hs_lyon4(P(x), code, x.size, P(out))
+        ref = np.array(O.lyon4(x))
+        assert np.allclose(out, ref, rtol=1e-10, atol=1e-12)
+    c = np.full(64, 9, dtype=np.uint8)
+    out = np.zeros(4)
+    hs.hs_lyon4(P(c), 0, 64, P(out))
+    assert out[0] == 9 and out[1] == 0 and np.isnan(out[2]) and np.isnan(out[3])
