@@ -251,8 +251,12 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(times[0]), float(times[1])
     ok = int(((out_host.status.numpy() & 0x3df) == 0).sum())
-    same = bool(torch.equal(torch.nan_to_num(out_dev.features.cpu(), nan=-1.0),
-                            torch.nan_to_num(out_host.features, nan=-1.0)))
+    fd, fh = out_dev.features.cpu(), out_host.features
+    diff = ~((fd == fh) | (torch.isnan(fd) & torch.isnan(fh)))
+    same = not bool(diff.any())
+    if not same and rank == 0:
+        sys.stderr.write("host/device rows differ: %d, columns %s\n" % (int(diff.any(1).sum()),
+                         (torch.nonzero(diff.any(0)).flatten() + 1).tolist()))
 
     if rank == 0:
         peak, peak_kind = read_peaks()

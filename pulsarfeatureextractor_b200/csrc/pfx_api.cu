@@ -65,6 +65,7 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->counters);
     if (ctx->hist_scratch) cudaFree(ctx->hist_scratch);
+    if (ctx->carry) cudaFree(ctx->carry);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         cudaStreamDestroy(ctx->streams[i]);

@@ -33,6 +33,8 @@ struct pfx_ctx {
     int counter_slot;
     double* hist_scratch;
     size_t hist_scratch_bytes;
+    void* carry;              // per-candidate records passed between the two Gaussian kernels
+    size_t carry_bytes;
     cudaEvent_t ev[pfx::N_EVENTS];
     bool ev_valid;
     int last_launches;

@@ -1,0 +1,513 @@
+// pfx_lane_gauss.cuh -- scores 8-11 with one lane per candidate (see pfx_lane_lm.cuh for why).
+//
+// A candidate goes through ten least-squares fits (ProfileOperations.py:724-768,1061-1483):
+//   stage 0      Gaussian + background on the background-subtracted, rotated profile  (PO:1194-1264)
+//   stage 1..8   the eight 4-parameter rounds of the double-Gaussian procedure        (PO:1358-1405)
+//   final        the 8-parameter fit and the choice between it and the "combi" curve  (PO:1407-1483)
+// Stages 0..8 all fit |max| exp(-((x-mu)/s)^2/2) + b with four parameters, so one kernel runs them
+// as a per-lane state machine: every trip of the kernel loop is "one Jacobian pass and one trial
+// point" for all 32 lanes of a warp, whatever stage or candidate each lane is in.  The final fit
+// has eight parameters and runs in a second kernel; the few numbers it needs travel through a
+// small per-candidate record in global memory (GaussCarry).
+//
+// Per-lane working data: dat[m] (float64 data vector of the current fit) and xs[m] (uint16 bin
+// numbers) in shared memory, strided so that the lanes of a warp never collide on a bank.
+#pragma once
+
+#include "pfx_driver.cuh"
+#include "pfx_lane_lm.cuh"
+
+namespace pfx {
+
+struct LaneBuf {
+    double* dat;           // element i of this lane at dat[i * stride]
+    unsigned short* xs;    // element i of this lane at xs[i * stride]
+    int stride;
+    PFX_HD double& d(int i) const { return dat[(size_t)i * stride]; }
+    PFX_HD unsigned short& x(int i) const { return xs[(size_t)i * stride]; }
+};
+
+// what the final-fit kernel needs from the rounds kernel
+struct GaussCarry {
+    double p_t1[4];
+    double p1[4];
+    double p2[4];
+    double minbg, sd, t1_fwhm;
+    int skip;      // 1: candidate finished in the rounds kernel (failure or sentinel)
+    int pad;
+};
+
+enum { GP_IDLE = 0, GP_SETUP = 1, GP_JAC = 2, GP_TRIAL = 3, GP_FIN = 4 };
+
+// rows of the 4-parameter family: value = |p2| exp(-((x-p1)/s)^2/2) + b,
+// s = |p0| or p0, b = p3 or |p3|
+struct G4Flags {
+    bool abs_sigma, abs_bg;
+};
+
+PFX_HD inline double g4_value(const double (&p)[4], G4Flags fl, double xv) {
+    const double sg = fl.abs_sigma ? fabs(p[0]) : p[0];
+    const double bg = fl.abs_bg ? fabs(p[3]) : p[3];
+    return PFX_ADD(PFX_MUL(fabs(p[2]), gauss_core(xv, p[1], sg)), bg);
+}
+
+struct GaussLane {
+    // candidate
+    const void* profile;
+    int dtype;
+    long long cand;
+    int m, cut;
+    double ph_expect, mean, sd, minbg;
+    // state
+    int phase, stage, nrows;
+    G4Flags fl;
+    LaneLM<4> lm;
+    double p_t1[4], p1[4], p2[4];
+    double t1_fwhm, t1_chi;
+    unsigned status;
+    int8_t ier[10];      // slots PFX_FIT_T1 .. PFX_FIT_DG_ROUND0+7 (index = slot - PFX_FIT_T1)
+    bool finished, sentinel;
+
+    PFX_HD double yrot(int i) const {
+        int src = i + cut;
+        if (src >= m) src -= m;
+        return load_elem(profile, dtype, cand * (long long)m + src);
+    }
+
+    PFX_HD void start(const void* prof, int dt, long long c, int m_, double ph) {
+        profile = prof;
+        dtype = dt;
+        cand = c;
+        m = m_;
+        cut = m_ / 2;
+        ph_expect = ph;
+        stage = 0;
+        phase = GP_SETUP;
+        status = 0;
+        finished = false;
+        sentinel = false;
+        for (int k = 0; k < 10; ++k) ier[k] = 0;
+        t1_fwhm = NAN;
+        t1_chi = NAN;
+    }
+
+    // mean / std / argmax / builtin-max of dat[0..n)
+    PFX_HD void stats(const LaneBuf& b, int n, double& mu, double& sdev, int& amax, double& vmax, double& bmax) const {
+        double s = 0.0;
+        amax = 0;
+        vmax = b.d(0);
+        bmax = b.d(0);
+        for (int i = 0; i < n; ++i) {
+            const double v = b.d(i);
+            s += v;
+            if (i > 0) {
+                if (argmax_better(v, i, vmax, amax)) {
+                    vmax = v;
+                    amax = i;
+                }
+                if (v > bmax) bmax = v;      // builtin max: sequential '>'
+            }
+        }
+        mu = s / (double)n;
+        double q = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double dlt = b.d(i) - mu;
+            q = PFX_FMA(dlt, dlt, q);
+        }
+        sdev = sqrt(q / (double)n);
+    }
+
+    PFX_HD void setup(const LaneBuf& b) {
+        double x0[4];
+        if (stage == 0) {
+            // profile statistics and the T1 data vector (PO:724-739, 1098-1110)
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) {
+                const double v = yrot(i);
+                b.d(i) = v;
+                b.x(i) = (unsigned short)i;
+                s += v;
+            }
+            mean = s / (double)m;
+            double q = 0.0;
+            for (int i = 0; i < m; ++i) {
+                const double dlt = b.d(i) - mean;
+                q = PFX_FMA(dlt, dlt, q);
+            }
+            sd = sqrt(q / (double)m);
+            minbg = (mean < ph_expect) ? mean : ph_expect;     // builtin min(ph_expect, mean)
+            if (minbg > 0.0) {
+                for (int i = 0; i < m; ++i) {
+                    double v = PFX_ADD(PFX_SUB(b.d(i), minbg), sd);
+                    if (v < 0.0) v = 0.0;
+                    b.d(i) = v;
+                }
+            }
+            double mu, sdev, vmax, bmax;
+            int amax;
+            stats(b, m, mu, sdev, amax, vmax, bmax);
+            x0[0] = sdev;
+            x0[1] = (double)amax;
+            x0[2] = vmax;
+            x0[3] = 1.0;
+            fl.abs_sigma = true;
+            fl.abs_bg = false;
+            nrows = m;
+        } else if (stage == 1) {
+            // rotated raw profile, peak stripping (PO:1305-1354)
+            int amax = 0;
+            double vmax = 0.0;
+            for (int i = 0; i < m; ++i) {
+                const double v = yrot(i);
+                b.d(i) = v;
+                if (i == 0 || argmax_better(v, i, vmax, amax)) {
+                    vmax = v;
+                    amax = i;
+                }
+            }
+            const int nlen = strip_peak(b, amax);
+            if (nlen < 0) {                 // IndexError -> 1e6 sentinels (PO:762-764)
+                sentinel = true;
+                status |= PFX_ST_DG_SENTINEL;
+                finished = true;
+                phase = GP_IDLE;
+                return;
+            }
+            if (nlen == 0) {
+                status |= PFX_ST_EMPTY_SEQUENCE;
+                finished = true;
+                phase = GP_IDLE;
+                return;
+            }
+            for (int k = 0; k < nlen; ++k) b.d(k) = b.d(b.x(k));   // x(k) >= k, so no overwrite hazard
+            double mu, sdev, bmax;
+            int am2;
+            stats(b, nlen, mu, sdev, am2, vmax, bmax);
+            x0[0] = sdev;
+            x0[1] = (double)b.x(am2);
+            x0[2] = bmax;
+            x0[3] = mu;
+            nrows = nlen;
+            for (int k = nlen; k < 4; ++k) {     // PO:1373-1377 zero padding
+                b.d(k) = 0.0;
+                b.x(k) = 0;
+                nrows = 4;
+            }
+            fl.abs_sigma = false;
+            fl.abs_bg = true;
+        } else {
+            // rounds 2..8: data were rebuilt by the previous round's finish()
+            double mu, sdev, vmax, bmax;
+            int amax;
+            stats(b, m, mu, sdev, amax, vmax, bmax);
+            x0[0] = sdev;
+            x0[1] = (double)b.x(amax);
+            x0[2] = bmax;
+            x0[3] = mu;
+            nrows = m;
+            fl.abs_sigma = false;
+            fl.abs_bg = true;
+        }
+        lm.init(x0);
+        phase = GP_JAC;
+    }
+
+    // PO:1305-1354 on the index list kept in xs; returns the survivor count or -1 (IndexError)
+    PFX_HD int strip_peak(const LaneBuf& b, int pos) const {
+        const int n = m;
+        int len = n;
+        for (int i = 0; i < n; ++i) b.x(i) = (unsigned short)i;
+#define PFX_DEL(k_)                                                  \
+    do {                                                             \
+        int k = (k_);                                                \
+        if (k < -len || k >= len) return -1;                         \
+        if (k < 0) k += len;                                         \
+        for (int q_ = k; q_ < len - 1; ++q_) b.x(q_) = b.x(q_ + 1);  \
+        --len;                                                       \
+    } while (0)
+        PFX_DEL(pos);
+        int tol = 0;
+        const int limit = 5;
+        for (int i = 1; i < n; ++i) {
+            if ((pos - i) > 0 && (pos + i) < n) {
+                const double yl = b.d(pos - i), yl1 = b.d(pos - i + 1), yr_ = b.d(pos + i), yr1 = b.d(pos + i - 1);
+                if ((yl < yl1) && (yr_ < yr1)) {
+                    PFX_DEL(pos - i);
+                    PFX_DEL(pos - i);
+                } else if ((yl >= yl1) || ((yr_ >= yr1) && (tol < limit))) {
+                    PFX_DEL(pos - i);
+                    PFX_DEL(pos - i);
+                    ++tol;
+                } else {
+                    break;
+                }
+            } else if ((pos - i) < 0) {
+                if (pos + i >= n) return -1;
+                const double yr_ = b.d(pos + i), yr1 = b.d(pos + i - 1);
+                if (yr_ < yr1) {
+                    PFX_DEL(pos - i + 1);
+                } else if ((yr_ >= yr1) && (tol < limit)) {
+                    PFX_DEL(pos - i + 1);
+                    ++tol;
+                } else {
+                    break;
+                }
+            } else if ((pos + i) > n) {
+                const double yl = b.d(pos - i), yl1 = b.d(pos - i + 1);
+                if (yl < yl1) {
+                    PFX_DEL(pos - i + 1);
+                } else if ((yl >= yl1) && (tol < limit)) {
+                    PFX_DEL(pos - i);
+                    ++tol;
+                } else {
+                    break;
+                }
+            }
+        }
+#undef PFX_DEL
+        return len;
+    }
+
+    // one Jacobian pass: three exponentials per row (the max and background columns reuse the
+    // base exponential, which gives bit-identical values to re-evaluating the model)
+    PFX_HD void jac_pass(const LaneBuf& b) {
+        lm.jac_begin();
+        const double* x = lm.x;
+        const double* h = lm.h;
+        const double sg = fl.abs_sigma ? fabs(x[0]) : x[0];
+        const double sgh = fl.abs_sigma ? fabs(x[0] + h[0]) : (x[0] + h[0]);
+        const double mu = x[1], muh = x[1] + h[1];
+        const double amx = fabs(x[2]), amxh = fabs(x[2] + h[2]);
+        const double bg = fl.abs_bg ? fabs(x[3]) : x[3];
+        const double bgh = fl.abs_bg ? fabs(x[3] + h[3]) : (x[3] + h[3]);
+        for (int i = 0; i < nrows; ++i) {
+            const double xv = (double)b.x(i), yv = b.d(i);
+            const double e0 = gauss_core(xv, mu, sg);
+            const double e1 = gauss_core(xv, mu, sgh);
+            const double e2 = gauss_core(xv, muh, sg);
+            const double base = PFX_MUL(amx, e0);
+            const double f0 = PFX_SUB(yv, PFX_ADD(base, bg));
+            double a[4];
+            a[0] = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e1), bg)) - f0) / h[0];
+            a[1] = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e2), bg)) - f0) / h[1];
+            a[2] = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) / h[2];
+            a[3] = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) / h[3];
+            lm.jac_row(a, f0);
+        }
+        const int r = lm.jac_end(nrows);
+        phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+    }
+
+    PFX_HD void trial_pass(const LaneBuf& b) {
+        lm.trial_begin();
+        double s = 0.0;
+        for (int i = 0; i < nrows; ++i) {
+            const double f = PFX_SUB(b.d(i), g4_value(lm.xnew, fl, (double)b.x(i)));
+            s = PFX_FMA(f, f, s);
+        }
+        const int r = lm.trial_end(sqrt(s));
+        phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+    }
+
+    PFX_HD void finish(const LaneBuf& b) {
+        double p[4] = {lm.x[0], lm.x[1], lm.x[2], lm.x[3]};
+        ier[stage] = (int8_t)lm.info;
+        if (stage == 0) {
+            for (int k = 0; k < 4; ++k) p_t1[k] = p[k];
+            t1_fwhm = fabs(FWHM_K * p[0]);
+            double c = 0.0;
+            for (int i = 0; i < m; ++i) {
+                const double dlt = b.d(i) - g4_value(p, fl, (double)i);
+                c = PFX_FMA(dlt, dlt, c);
+            }
+            t1_chi = c / (double)m;
+        } else {
+            // rebuild the data for the next round over the full profile (PO:1388-1399)
+            const double nfwhm = fabs(FWHM_K * p[0]);
+            const double lo = p[2] - (1.5 * nfwhm) / 2.0;
+            const double hi = p[2] + (1.5 * nfwhm) / 2.0;
+            for (int i = 0; i < m && stage < 8; ++i) {
+                const double xv = (double)i;
+                const double ev = g4_value(p, fl, xv);
+                const double yv = yrot(i);
+                double nv;
+                if (ev <= yv) nv = PFX_ADD(PFX_SUB(yv, ev), p[3]);
+                else if ((ev > yv) && (xv > lo) && (xv < hi)) nv = p[3];
+                else nv = yv;
+                b.d(i) = nv;
+                b.x(i) = (unsigned short)i;
+            }
+            if (stage == 7)
+                for (int k = 0; k < 4; ++k) p2[k] = p[k];
+            if (stage == 8)
+                for (int k = 0; k < 4; ++k) p1[k] = p[k];
+        }
+        ++stage;
+        if (stage > 8) {
+            finished = true;
+            phase = GP_IDLE;
+        } else {
+            phase = GP_SETUP;
+        }
+    }
+
+    // one trip of the kernel loop
+    PFX_HD void step(const LaneBuf& b) {
+        if (phase == GP_SETUP) setup(b);
+        if (phase == GP_JAC) jac_pass(b);
+        if (phase == GP_TRIAL) trial_pass(b);
+        if (phase == GP_FIN) finish(b);
+    }
+};
+
+// ---- final 8-parameter fit -----------------------------------------------------------------
+struct Gauss8Lane {
+    const void* profile;
+    int dtype;
+    long long cand;
+    int m, cut, phase;
+    LaneLM<8> lm;
+    GaussCarry carry;
+    double s10, s11;
+    int8_t ier;
+    bool finished;
+
+    PFX_HD void start(const void* prof, int dt, long long c, int m_, const GaussCarry& cy, const LaneBuf& b) {
+        profile = prof;
+        dtype = dt;
+        cand = c;
+        m = m_;
+        cut = m_ / 2;
+        carry = cy;
+        finished = false;
+        for (int i = 0; i < m; ++i) {
+            int src = i + cut;
+            if (src >= m) src -= m;
+            b.d(i) = load_elem(profile, dtype, cand * (long long)m + src);
+        }
+        double x0[8];
+        for (int k = 0; k < 4; ++k) {
+            x0[k] = cy.p1[k];
+            x0[4 + k] = cy.p2[k];
+        }
+        lm.init(x0);
+        phase = GP_JAC;
+    }
+
+    PFX_HD static double value(const double* p, double xv) {
+        const double a = PFX_MUL(fabs(p[2]), gauss_core(xv, p[1], fabs(p[0])));
+        const double c = PFX_MUL(fabs(p[6]), gauss_core(xv, p[5], fabs(p[4])));
+        const double bg = PFX_MUL(PFX_ADD(fabs(p[3]), fabs(p[7])), 0.5);
+        return PFX_ADD(PFX_ADD(a, c), bg);
+    }
+
+    PFX_HD void jac_pass(const LaneBuf& b) {
+        lm.jac_begin();
+        const double* x = lm.x;
+        const double* h = lm.h;
+        const double s1 = fabs(x[0]), s1h = fabs(x[0] + h[0]), m1 = x[1], m1h = x[1] + h[1];
+        const double a1 = fabs(x[2]), a1h = fabs(x[2] + h[2]);
+        const double s2 = fabs(x[4]), s2h = fabs(x[4] + h[4]), m2 = x[5], m2h = x[5] + h[5];
+        const double a2 = fabs(x[6]), a2h = fabs(x[6] + h[6]);
+        const double bg = PFX_MUL(PFX_ADD(fabs(x[3]), fabs(x[7])), 0.5);
+        const double bg3 = PFX_MUL(PFX_ADD(fabs(x[3] + h[3]), fabs(x[7])), 0.5);
+        const double bg7 = PFX_MUL(PFX_ADD(fabs(x[3]), fabs(x[7] + h[7])), 0.5);
+        for (int i = 0; i < m; ++i) {
+            const double xv = (double)i, yv = b.d(i);
+            const double e1 = gauss_core(xv, m1, s1), e2 = gauss_core(xv, m2, s2);
+            const double g1 = PFX_MUL(a1, e1), g2 = PFX_MUL(a2, e2);
+            const double f0 = PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg));
+            double a[8];
+            a[0] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1, gauss_core(xv, m1, s1h)), g2), bg)) - f0) / h[0];
+            a[1] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1, gauss_core(xv, m1h, s1)), g2), bg)) - f0) / h[1];
+            a[2] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1h, e1), g2), bg)) - f0) / h[2];
+            a[3] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg3)) - f0) / h[3];
+            a[4] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2, gauss_core(xv, m2, s2h))), bg)) - f0) / h[4];
+            a[5] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2, gauss_core(xv, m2h, s2))), bg)) - f0) / h[5];
+            a[6] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2h, e2)), bg)) - f0) / h[6];
+            a[7] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg7)) - f0) / h[7];
+            lm.jac_row(a, f0);
+        }
+        const int r = lm.jac_end(m);
+        phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+    }
+
+    PFX_HD void trial_pass(const LaneBuf& b) {
+        lm.trial_begin();
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double f = PFX_SUB(b.d(i), value(lm.xnew, (double)i));
+            s = PFX_FMA(f, f, s);
+        }
+        const int r = lm.trial_end(sqrt(s));
+        phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+    }
+
+    // PO:1407-1428 and PO:747-761
+    PFX_HD void finish(const LaneBuf& b) {
+        ier = (int8_t)lm.info;
+        const double* q = lm.x;
+        const double fwhm1 = fabs(FWHM_K * q[0]), fwhm2 = fabs(FWHM_K * q[4]);
+        const G4Flags rf = {false, true};
+        const G4Flags tf = {true, false};
+        const double bgmix = PFX_MUL(PFX_ADD(carry.p1[3], carry.p2[3]), 0.5);
+        double c = 0.0, cc = 0.0;
+        // pass 1: both chi-squares
+        for (int i = 0; i < m; ++i) {
+            const double xv = (double)i, yv = b.d(i);
+            const double fi = value(q, xv);
+            if (fi >= 1.0) {
+                const double dlt = yv - fi;
+                c += (dlt * dlt) / (double)m;
+            }
+            const double cf = PFX_ADD(PFX_SUB(PFX_SUB(PFX_ADD(g4_value(carry.p1, rf, xv), g4_value(carry.p2, rf, xv)),
+                                                      carry.p1[3]), carry.p2[3]), bgmix);
+            if (cf >= 1.0) {
+                const double dlt = yv - cf;
+                cc += (dlt * dlt) / (double)m;
+            }
+        }
+        const bool use_final = (c <= cc);
+        double fw_a, fw_b, dg_chi;
+        if (use_final) {
+            fw_a = fwhm1;
+            fw_b = fwhm2;
+            dg_chi = c;
+        } else {
+            fw_a = fabs(FWHM_K * carry.p2[0]);
+            fw_b = fabs(FWHM_K * carry.p1[0]);
+            dg_chi = cc;
+        }
+        // pass 2 and 3: std of (chosen fit) - (T1 fit + minbg - std)   (PO:755-756)
+        double ds = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double xv = (double)i;
+            const double dg = use_final ? value(q, xv)
+                                        : PFX_ADD(PFX_SUB(PFX_SUB(PFX_ADD(g4_value(carry.p1, rf, xv), g4_value(carry.p2, rf, xv)),
+                                                                  carry.p1[3]), carry.p2[3]), bgmix);
+            const double dlt = dg - PFX_SUB(PFX_ADD(g4_value(carry.p_t1, tf, xv), carry.minbg), carry.sd);
+            b.d(i) = dlt;       // the data vector is no longer needed
+            ds += dlt;
+        }
+        const double dmean = ds / (double)m;
+        double dv = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double dlt = b.d(i) - dmean;
+            dv = PFX_FMA(dlt, dlt, dv);
+        }
+        const double dstd = fabs(sqrt(dv / (double)m));
+        if (dstd < 3.0) s10 = carry.t1_fwhm;
+        else s10 = (fw_b < fw_a) ? fw_b : fw_a;
+        s11 = dg_chi;
+        finished = true;
+        phase = GP_IDLE;
+    }
+
+    PFX_HD void step(const LaneBuf& b) {
+        if (phase == GP_JAC) jac_pass(b);
+        if (phase == GP_TRIAL) trial_pass(b);
+        if (phase == GP_FIN) finish(b);
+    }
+};
+
+}  // namespace pfx

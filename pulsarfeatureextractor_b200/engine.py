@@ -143,6 +143,12 @@ class Engine(object):
         fbits = _FEATURES[features] if isinstance(features, str) else int(features)
         n = profile.shape[0]
         ncol = (22 if fbits & 1 else 0) + (8 if fbits & 2 else 0)
+        for a in (profile, subbands, dmcurve, dmstat, params):
+            if a is None:
+                continue
+            ok = a.is_contiguous() if hasattr(a, "is_contiguous") else a.flags.c_contiguous
+            if not ok:
+                raise PfxError("inputs must be C-contiguous")
         if out is None:
             feat = np.empty((n, ncol), dtype=np.float64)
             status = np.zeros((n,), dtype=np.int32)

@@ -199,7 +199,9 @@ def _chunk(config_id, chunk_index, count, nbin, nsub, n_dm, n_dmstat, want_subba
     params[:, PARAM_DM_START] = dm_start
     params[:, PARAM_DM_END] = dm_end
     params[:, PARAM_DM_LEN_ALL] = 128 * n_dm
-    return Batch(profile, subbands, dmcurve, dmstat, params, klass, edge)
+    c = np.ascontiguousarray
+    return Batch(c(profile), None if subbands is None else c(subbands), None if dmcurve is None else c(dmcurve),
+                 None if dmstat is None else c(dmstat), c(params), klass, edge)
 
 
 def generate(config_id, start, count, nbin=128, nsub=16, n_dm=256, n_dmstat=256,

@@ -96,3 +96,103 @@ extern "C" int hs_lmdif_cb(int n, int m, double* x, hs_resid_cb cb, int* nfev) {
     }
     return -100;
 }
+
+// ---- lane-per-fit LM (streaming QR) with a caller-supplied residual ---------------------------
+#include "../../pulsarfeatureextractor_b200/csrc/pfx_lane_lm.cuh"
+template <int NP>
+static int run_lane_cb(int m, double* x, hs_resid_cb cb, int* nfev) {
+    std::vector<double> f0(m), fj((size_t)NP * m), f1(m);
+    double x0[NP];
+    for (int i = 0; i < NP; ++i) x0[i] = x[i];
+    LaneLM<NP> lm;
+    lm.init(x0);
+    int phase = LANE_JAC;
+    while (phase != LANE_DONE) {
+        if (phase == LANE_JAC) {
+            lm.jac_begin();
+            cb(lm.x, f0.data());
+            for (int j = 0; j < NP; ++j) {
+                double p[NP];
+                for (int k = 0; k < NP; ++k) p[k] = lm.x[k];
+                p[j] = lm.x[j] + lm.h[j];
+                cb(p, fj.data() + (size_t)j * m);
+            }
+            for (int i = 0; i < m; ++i) {
+                double a[NP];
+                for (int j = 0; j < NP; ++j) a[j] = (fj[(size_t)j * m + i] - f0[i]) / lm.h[j];
+                lm.jac_row(a, f0[i]);
+            }
+            phase = lm.jac_end(m);
+        } else {
+            lm.trial_begin();
+            cb(lm.xnew, f1.data());
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += f1[i] * f1[i];
+            phase = lm.trial_end(sqrt(s));
+        }
+    }
+    for (int i = 0; i < NP; ++i) x[i] = lm.x[i];
+    *nfev = lm.nfev;
+    return lm.info;
+}
+extern "C" int hs_lanelm_cb(int n, int m, double* x, hs_resid_cb cb, int* nfev) {
+    switch (n) {
+        case 2: return run_lane_cb<2>(m, x, cb, nfev);
+        case 3: return run_lane_cb<3>(m, x, cb, nfev);
+        case 4: return run_lane_cb<4>(m, x, cb, nfev);
+        case 8: return run_lane_cb<8>(m, x, cb, nfev);
+    }
+    return -100;
+}
+
+// ---- lane-per-candidate scores 8-11 (pfx_lane_gauss.cuh) ----------------------------------------
+#include "../../pulsarfeatureextractor_b200/csrc/pfx_lane_gauss.cuh"
+extern "C" unsigned hs_gauss_lane(const void* profile, int dtype, int m, double ph_expect, double* feat,
+                                  int8_t* ier) {
+    std::vector<double> dat(m + 8);
+    std::vector<unsigned short> xs(m + 8);
+    LaneBuf b;
+    b.dat = dat.data();
+    b.xs = xs.data();
+    b.stride = 1;
+    GaussLane g;
+    g.start(profile, dtype, 0, m, ph_expect);
+    while (g.phase != GP_IDLE) g.step(b);
+    for (int k = 0; k < 9; ++k) ier[PFX_FIT_T1 + k] = g.ier[k];
+    feat[7] = g.t1_fwhm;
+    feat[8] = g.t1_chi;
+    if (g.sentinel) {
+        feat[9] = 1000000.0;
+        feat[10] = 1000000.0;
+        return g.status;
+    }
+    if (g.status & PFX_ST_FAIL_MASK) return g.status;
+    GaussCarry cy;
+    for (int k = 0; k < 4; ++k) {
+        cy.p_t1[k] = g.p_t1[k];
+        cy.p1[k] = g.p1[k];
+        cy.p2[k] = g.p2[k];
+    }
+    cy.minbg = g.minbg;
+    cy.sd = g.sd;
+    cy.t1_fwhm = g.t1_fwhm;
+    cy.skip = 0;
+    Gauss8Lane f;
+    f.start(profile, dtype, 0, m, cy, b);
+    while (f.phase != GP_IDLE) f.step(b);
+    ier[PFX_FIT_DG_FINAL] = f.ier;
+    feat[9] = f.s10;
+    feat[10] = f.s11;
+    return g.status;
+}
+
+// scores 5-7 only (histogram stage); returns status, *ph_expect = mu of the profile-histogram fit
+extern "C" unsigned hs_hist(const void* profile, int dtype, int m, int cap_smem, int cap_global,
+                            double* feat, int8_t* ier, double* ph_expect) {
+    std::vector<double> ws(hist_work_doubles(m, cap_smem) + 16);
+    std::vector<double> gs(hist_scratch_doubles(cap_global) + 16);
+    G1 g;
+    double pow_m = pow((double)m, -0.3333333), pow_m1 = pow((double)(m - 1), -0.3333333);
+    return hist_candidate(g, ws.data(), cap_smem, cap_global > 0 ? gs.data() : nullptr, cap_global,
+                          profile, dtype, 0, m, pow_m, pow_m1, feat, ier, ph_expect);
+}
