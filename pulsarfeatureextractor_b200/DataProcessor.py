@@ -1,0 +1,240 @@
+"""
+DataProcessor -- directory walk, batch submission and the output writers of the reference
+(DataProcessor.py:51-995), with the per-candidate loop replaced by batches on the GPU.
+
+Kept from the reference: file patterns (DataProcessor.py:67-70), os.walk + fnmatch order, the
+CSV / ARFF / .dat row formats (DataProcessor.py:305-325,405-447), the 'nan' and 'inf' -> '0'
+substitution over the whole line, ARFF headers (DataProcessor.py:329-401), the per-candidate
+failure handling (row omitted, path appended to CandidateErrorLog.txt, DataProcessor.py:517-523),
+the counters printed at the end, rows buffered and appended once (DataProcessor.py:590-594).
+Numbers are written with Python 2's str(float) = '%.12g' (SURVEY.md 8c D3); pass py2_format=False for
+repr().
+"""
+import datetime
+import fnmatch
+import os
+import sys
+
+import numpy as np
+
+from . import _lib, phcx_io
+from .Candidate import Candidate
+
+
+def fmt_float(v, py2=True):
+    v = float(v)
+    if not py2:
+        return repr(v)
+    if v != v:
+        return "nan"
+    if v in (float("inf"), float("-inf")):
+        return "inf" if v > 0 else "-inf"
+    s = "%.12g" % v
+    if "." not in s and "e" not in s:
+        s += ".0"
+    return s
+
+
+class DataProcessor(object):
+    def __init__(self, debugFlag=False, engine=None, batch=4096, features=None, py2_format=True,
+                 error_log="CandidateErrorLog.txt"):
+        self.debug = debugFlag
+        self.phcxRegex = "*.phcx.gz"
+        self.superbRegex = "*.phcx"
+        self.pfdRegex = "*.pfd"
+        self.scoreStore = []
+        self.candidateErrorLog = error_log
+        self.engine = engine
+        self.batch = int(batch)
+        self.features = features          # None: what the reference mode implies
+        self.py2 = py2_format
+        self.pfd = self.phcx = self.superb = False
+        if not os.path.isfile(self.candidateErrorLog):
+            self.appendToFile(self.candidateErrorLog, "")
+
+    # ---- Utilities.py:60-115 -------------------------------------------------------------------
+    @staticmethod
+    def appendToFile(path, text):
+        with open(path, "a") as fh:
+            fh.write(str(text))
+
+    @staticmethod
+    def fileExists(path):
+        return os.path.isfile(path)
+
+    def _engine(self):
+        if self.engine is None:
+            from .engine import Engine
+            self.engine = Engine(0)
+        return self.engine
+
+    # ---- row formats ----------------------------------------------------------------------------
+    def storeScore(self, candidate, scores, outPath=None):
+        entry = candidate + "," + ",".join(fmt_float(s, self.py2) for s in scores)
+        self.scoreStore.append(entry.replace("nan", "0").replace("inf", "0"))
+
+    def storeScoreARFF(self, candidate, scores, outPath=None):
+        entry = ",".join(fmt_float(s, self.py2) for s in scores) + ",?%" + candidate
+        self.scoreStore.append(entry.replace("nan", "0").replace("inf", "0"))
+
+    def outputScores(self, scores, outputFile):
+        with open(outputFile + ".dat", "w") as fh:
+            fh.write(",".join(fmt_float(s, self.py2) for s in scores).replace("nan", "0").replace("inf", "0"))
+
+    def prepareARFFFile(self, path, genProfileData, n_scores=22):
+        header = "@relation PulsarCandidates_" + datetime.datetime.now().isoformat() + "\n"
+        attributes = n_scores + 1
+        if genProfileData and self.superb:
+            attributes = 65
+        elif genProfileData and self.phcx:
+            attributes = 129
+        for n in range(1, attributes):
+            header += "@attribute Score" + str(n) + " numeric\n"
+        header += "@attribute class {0,1}\n@data\n"
+        self.appendToFile(path, header)
+
+    def prepareDMProfileARFFFile(self, path):
+        header = "@relation PulsarCandidates_" + datetime.datetime.now().isoformat() + "\n"
+        for name in ("Profile_mean", "Profile_stdev", "Profile_skewness", "Profile_kurtosis",
+                     "DM_mean", "DM_stdev", "DM_skewness", "DM_kurtosis"):
+            header += "@attribute " + name + " numeric\n"
+        header += "@attribute class {0,1}\n@data\n"
+        self.appendToFile(path, header)
+
+    # ---- candidate discovery (DataProcessor.py:491-497) --------------------------------------------
+    def find(self, directory, fileTypeRegexes, processSingleCandidate):
+        if processSingleCandidate:
+            return [directory]
+        if directory == "":
+            directory = os.path.dirname(os.path.realpath(__file__))
+            print("User has not provided a search directory - searching local directory")
+        found = []
+        for filetype in fileTypeRegexes:
+            for root, _sub, filenames in os.walk(directory):
+                for filename in fnmatch.filter(filenames, filetype):
+                    found.append(os.path.join(root, filename))
+        return found
+
+    # ---- the batched core ------------------------------------------------------------------------
+    def _score_files(self, paths, features):
+        """Yields (path, scores or None) in input order.  None = the reference would have raised."""
+        eng = self._engine()
+        for lo in range(0, len(paths), self.batch):
+            chunk = paths[lo:lo + self.batch]
+            cands, keep = [], []
+            results = [None] * len(chunk)
+            for k, p in enumerate(chunk):
+                try:
+                    c = Candidate(p, p)
+                    cands.append(c.load())
+                    keep.append(k)
+                except Exception as e:      # noqa: BLE001 - mirrors DataProcessor.py:517
+                    print("Error reading profile data :\n\t", type(e).__name__, e)
+            # group by array shapes so every group is one SoA batch
+            groups = {}
+            for k, c in zip(keep, cands):
+                key = (c.profile.size, c.subbands.shape, c.dmcurve.size, c.dmstat.size)
+                groups.setdefault(key, []).append((k, c))
+            for _key, items in groups.items():
+                prof = np.ascontiguousarray(np.stack([c.profile for _k, c in items]))
+                sub = np.ascontiguousarray(np.stack([c.subbands for _k, c in items]))
+                dmc = np.ascontiguousarray(np.stack([c.dmcurve for _k, c in items]))
+                dms = np.ascontiguousarray(np.stack([c.dmstat for _k, c in items]))
+                par = np.ascontiguousarray(np.stack([c.params for _k, c in items]))
+                out = eng.score_host(prof, sub, dmc, dms, par, features=features)
+                ok = out.ok() if features != "lyon" else np.ones(len(items), dtype=bool)
+                for j, (k, _c) in enumerate(items):
+                    results[k] = out.features[j] if ok[j] else None
+            for p, r in zip(chunk, results):
+                yield p, r
+
+    def _run(self, directory, fileTypeRegexes, outPath, arff, features, processSingleCandidate, separate=False):
+        start = datetime.datetime.now()
+        paths = self.find(directory, fileTypeRegexes, processSingleCandidate)
+        successes = failures = 0
+        for cand, scores in self._score_files(paths, features):
+            if scores is None:
+                print(cand, " did not have scores generated.")
+                self.appendToFile(self.candidateErrorLog, cand + "\n")
+                failures += 1
+                continue
+            if separate:
+                self.outputScores(scores, cand)
+            elif arff:
+                self.storeScoreARFF(cand, scores, outPath)
+            else:
+                self.storeScore(cand, scores, outPath)
+            successes += 1
+        end = datetime.datetime.now()
+        if not separate:
+            self.appendToFile(outPath, "".join(s + "\n" for s in self.scoreStore))
+            self.scoreStore = []
+        print("\nCandidates processed:\t", len(paths))
+        print("Successes:\t", successes)
+        print("Failures:\t", failures)
+        print("Execution time: ", str(end - start))
+        return successes, failures
+
+    # ---- public methods, names as in the reference ---------------------------------------------------
+    def processCollectively(self, directory, verbose, fileTypeRegexes, outPath, arff, genProfileData,
+                            processSingleCandidate):
+        feats = self.features or "bates"
+        if arff:
+            self.prepareARFFFile(outPath, genProfileData, {"bates": 22, "lyon": 8, "all": 30}[feats])
+        if genProfileData:
+            return self._run_profile(directory, fileTypeRegexes, outPath, arff, processSingleCandidate)
+        return self._run(directory, fileTypeRegexes, outPath, arff, feats, processSingleCandidate)
+
+    def _run_profile(self, directory, fileTypeRegexes, outPath, arff, processSingleCandidate):
+        paths = self.find(directory, fileTypeRegexes, processSingleCandidate)
+        ok = bad = 0
+        for p in paths:
+            try:
+                scores = Candidate(p, p).calculateProfileScores()
+                (self.storeScoreARFF if arff else self.storeScore)(p, scores, outPath)
+                ok += 1
+            except Exception:       # noqa: BLE001
+                self.appendToFile(self.candidateErrorLog, p + "\n")
+                bad += 1
+        self.appendToFile(outPath, "".join(s + "\n" for s in self.scoreStore))
+        self.scoreStore = []
+        return ok, bad
+
+    def processSeparately(self, directory, verbose, fileTypeRegexes, processSingleCandidate):
+        return self._run(directory, fileTypeRegexes, None, False, self.features or "bates",
+                         processSingleCandidate, separate=True)
+
+    def dmprof(self, directory, verbose, fileTypeRegexes, outPath, arff, processSingleCandidate):
+        if arff:
+            self.prepareDMProfileARFFFile(outPath)
+        return self._run(directory, fileTypeRegexes, outPath, arff, "lyon", processSingleCandidate)
+
+    def processPHCXCollectively(self, directory, verbose, outPath, arff, genProfileData, processSingleCandidate):
+        self.phcx = True
+        return self.processCollectively(directory, verbose, [self.phcxRegex], outPath, arff, genProfileData,
+                                        processSingleCandidate)
+
+    def processPHCXSeparately(self, directory, verbose, processSingleCandidate):
+        self.phcx = True
+        return self.processSeparately(directory, verbose, [self.phcxRegex], processSingleCandidate)
+
+    def processSUPERBCollectively(self, directory, verbose, outPath, arff, genProfileData, processSingleCandidate):
+        self.superb = True
+        return self.processCollectively(directory, verbose, [self.superbRegex], outPath, arff, genProfileData,
+                                        processSingleCandidate)
+
+    def dmprofPHCX(self, directory, verbose, outPath, arff, processSingleCandidate):
+        return self.dmprof(directory, verbose, [self.phcxRegex], outPath, arff, processSingleCandidate)
+
+    def dmprofSUPERB(self, directory, verbose, outPath, arff, processSingleCandidate):
+        return self.dmprof(directory, verbose, [self.superbRegex], outPath, arff, processSingleCandidate)
+
+    def _pfd_unsupported(self, *a, **k):
+        sys.stderr.write("PFD candidates: the .pfd reader/dedispersion stage is not part of this build "
+                         "(SURVEY.md 8f2); PFD-shaped arrays can be scored through Engine.score_host "
+                         "with family=PFX_FAMILY_PFD.\n")
+        return 0, 0
+
+    processPFDCollectively = processPFDSeparately = dmprofPFD = _pfd_unsupported
+    processPFDAndPHCXCollectively = processPHCXCollectively
+    processPFDAndPHCXSeparately = processPHCXSeparately

@@ -16,19 +16,26 @@ using namespace pfx;
 
 namespace {
 
-__device__ __forceinline__ LaneBuf lane_buf(double* smem, int m) {
+// shared memory of a block of T lanes: ws[nws][T] float64 | dat[m][T] float64 | xs[m][T] uint16
+__device__ __forceinline__ LaneBuf lane_buf(double* smem, int m, int nws) {
     LaneBuf b;
     b.stride = blockDim.x;
-    b.dat = smem + threadIdx.x;
-    b.xs = (unsigned short*)(smem + (size_t)m * blockDim.x) + threadIdx.x;
+    b.dat = smem + (size_t)nws * blockDim.x + threadIdx.x;
+    b.xs = (unsigned short*)(smem + (size_t)(nws + m) * blockDim.x) + threadIdx.x;
     return b;
+}
+__device__ __forceinline__ LaneWs lane_ws(double* smem, int n) {
+    LaneWs w;
+    w.carve(smem + threadIdx.x, blockDim.x, n);
+    return w;
 }
 
 __global__ void __launch_bounds__(128, 1)
 k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
                int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry) {
     extern __shared__ double smem[];
-    const LaneBuf b = lane_buf(smem, m);
+    const LaneBuf b = lane_buf(smem, m, lane_ws_doubles(4));
+    const LaneWs ws = lane_ws(smem, 4);
     GaussLane g;
     g.phase = GP_IDLE;
     g.finished = false;
@@ -83,7 +90,7 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
             }
         }
         if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
-        g.step(b);
+        g.step(b, ws);
     }
 }
 
@@ -91,7 +98,8 @@ __global__ void __launch_bounds__(128, 1)
 k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
               int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry) {
     extern __shared__ double smem[];
-    const LaneBuf b = lane_buf(smem, m);
+    const LaneBuf b = lane_buf(smem, m, lane_ws_doubles(8));
+    const LaneWs ws = lane_ws(smem, 8);
     Gauss8Lane g;
     g.phase = GP_IDLE;
     g.cand = -1;
@@ -115,22 +123,22 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
             }
         }
         if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
-        g.step(b);
+        g.step(b, ws);
     }
 }
 
 }  // namespace
 
-static int lane_block(pfx_ctx* ctx, int m, int* threads, size_t* smem) {
-    // per lane: m float64 + m uint16
-    const size_t per_lane = (size_t)m * 10;
+static int lane_block(pfx_ctx* ctx, int m, int np, int* threads, size_t* smem) {
+    // per lane: LM workspace + m float64 + m uint16
+    const size_t per_lane = (size_t)m * 10 + (size_t)lane_ws_doubles(np) * 8;
     int t = 128;
     const size_t budget = (size_t)ctx->smem_optin - 1024;
     while (t > 32 && per_lane * t > budget) t -= 32;
     if (per_lane * t > budget)
         return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin=%d needs %zu bytes of shared memory per lane", m, per_lane);
     *threads = t;
-    *smem = ((size_t)m * 8 * t + (size_t)m * 2 * t + 15) / 16 * 16;
+    *smem = (per_lane * t + 15) / 16 * 16;
     return PFX_OK;
 }
 
@@ -140,7 +148,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     if (m < 8 || m > 65535) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin out of range");
     int threads;
     size_t smem;
-    int rc = lane_block(ctx, m, &threads, &smem);
+    int rc = lane_block(ctx, m, 4, &threads, &smem);
     if (rc) return rc;
     // carry records
     const size_t need = (size_t)n * sizeof(GaussCarry);
@@ -165,6 +173,8 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     k_gauss_rounds<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                  take_counter(ctx, ck, st), carry);
     PFX_CUDA(ctx, cudaGetLastError());
+    rc = lane_block(ctx, m, 8, &threads, &smem);
+    if (rc) return rc;
     rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
     if (rc) return rc;
     if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);

@@ -270,7 +270,7 @@ struct GaussLane {
 
     // one Jacobian pass: three exponentials per row (the max and background columns reuse the
     // base exponential, which gives bit-identical values to re-evaluating the model)
-    PFX_HD void jac_pass(const LaneBuf& b) {
+    PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
         lm.jac_begin();
         const double* x = lm.x;
         const double* h = lm.h;
@@ -294,12 +294,12 @@ struct GaussLane {
             a[3] = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) / h[3];
             lm.jac_row(a, f0);
         }
-        const int r = lm.jac_end(nrows);
+        const int r = lm.jac_end(ws, nrows);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
 
-    PFX_HD void trial_pass(const LaneBuf& b) {
-        lm.trial_begin();
+    PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
+        lm.trial_begin(ws);
         double s = 0.0;
         for (int i = 0; i < nrows; ++i) {
             const double f = PFX_SUB(b.d(i), g4_value(lm.xnew, fl, (double)b.x(i)));
@@ -352,10 +352,10 @@ struct GaussLane {
     }
 
     // one trip of the kernel loop
-    PFX_HD void step(const LaneBuf& b) {
+    PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {
         if (phase == GP_SETUP) setup(b);
-        if (phase == GP_JAC) jac_pass(b);
-        if (phase == GP_TRIAL) trial_pass(b);
+        if (phase == GP_JAC) jac_pass(b, ws);
+        if (phase == GP_TRIAL) trial_pass(b, ws);
         if (phase == GP_FIN) finish(b);
     }
 };
@@ -401,7 +401,7 @@ struct Gauss8Lane {
         return PFX_ADD(PFX_ADD(a, c), bg);
     }
 
-    PFX_HD void jac_pass(const LaneBuf& b) {
+    PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
         lm.jac_begin();
         const double* x = lm.x;
         const double* h = lm.h;
@@ -428,12 +428,12 @@ struct Gauss8Lane {
             a[7] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg7)) - f0) / h[7];
             lm.jac_row(a, f0);
         }
-        const int r = lm.jac_end(m);
+        const int r = lm.jac_end(ws, m);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
 
-    PFX_HD void trial_pass(const LaneBuf& b) {
-        lm.trial_begin();
+    PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
+        lm.trial_begin(ws);
         double s = 0.0;
         for (int i = 0; i < m; ++i) {
             const double f = PFX_SUB(b.d(i), value(lm.xnew, (double)i));
@@ -503,9 +503,9 @@ struct Gauss8Lane {
         phase = GP_IDLE;
     }
 
-    PFX_HD void step(const LaneBuf& b) {
-        if (phase == GP_JAC) jac_pass(b);
-        if (phase == GP_TRIAL) trial_pass(b);
+    PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {
+        if (phase == GP_JAC) jac_pass(b, ws);
+        if (phase == GP_TRIAL) trial_pass(b, ws);
         if (phase == GP_FIN) finish(b);
     }
 };

@@ -29,8 +29,8 @@ namespace pfx {
 // MINPACK qrfac (pivoting) on an n x n matrix a (column major, leading dimension NPMAX), applied
 // to the triangular factor accumulated by the row rotations.  acnorm/rdiag/wa are preset by the
 // caller to the streamed column norms of the full Jacobian.
-PFX_HD PFX_NOINLINE inline void qrfac_small(int n, double* a, int* ipvt, double* rdiag, double* wa) {
-    const int ld = NPMAX;
+template <class RV, class IV>
+PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag, double* wa) {
     for (int j = 0; j < n; ++j) ipvt[j] = j;
     for (int j = 0; j < n; ++j) {
         int kmax = j;
@@ -79,6 +79,27 @@ PFX_HD PFX_NOINLINE inline void qrfac_small(int n, double* a, int* ipvt, double*
 
 enum LanePhase { LANE_JAC = 0, LANE_TRIAL = 1, LANE_DONE = 2 };
 
+// per-lane workspace of the n x n sub-problem: r (n x n, column major), six n-vectors, ipvt
+PFX_HD inline int lane_ws_doubles(int n) { return n * n + 6 * n + (n + 1) / 2; }
+struct LaneWs {
+    SPtr<double> r, diag, qtf, step, sdiag, wa1, wa2;
+    SPtr<int> ipvt;
+    // base points at this lane's first element; consecutive elements are `stride` doubles apart
+    PFX_HD void carve(double* base, int stride, int n) {
+        auto at = [&](int k) { SPtr<double> v; v.p = base + (size_t)k * stride; v.stride = stride; return v; };
+        r = at(0);
+        diag = at(n * n);
+        qtf = at(n * n + n);
+        step = at(n * n + 2 * n);
+        sdiag = at(n * n + 3 * n);
+        wa1 = at(n * n + 4 * n);
+        wa2 = at(n * n + 5 * n);
+        // ints are packed two per double slot, still strided per lane
+        ipvt.p = (int*)(base + (size_t)(n * n + 6 * n) * stride);
+        ipvt.stride = 2 * stride;
+    }
+};
+
 template <int N>
 struct LaneLM {
     // persistent over the whole solve
@@ -91,8 +112,8 @@ struct LaneLM {
     double q[N];
     double acn2[N];
     double f2;
-    // n x n sub-problem (local memory, dynamically indexed)
-    LmShared s;
+    // n x n sub-problem: dynamically indexed small vectors in the lane's strided workspace
+    // (shared memory on the device), see LaneWs
     double acnorm[N];
     // trial point
     double xnew[N];
@@ -162,7 +183,7 @@ struct LaneLM {
     }
 
     // returns LANE_TRIAL, or LANE_DONE with info set
-    PFX_HD int jac_end(int m) {
+    PFX_HD int jac_end(const LaneWs& s, int m) {
         nfev += N;
         if (iter == 1) fnorm = sqrt(f2);
         double rdiag[N], wa[N];
@@ -173,14 +194,12 @@ struct LaneLM {
             wa[j] = acnorm[j];
         }
         // unpack the triangular factor; rows beyond m do not exist (m >= N is guaranteed upstream)
+#pragma unroll
         for (int j = 0; j < N; ++j)
-            for (int i = 0; i < N; ++i) s.r[i + NPMAX * j] = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int j = i; j < N; ++j) s.r[i + NPMAX * j] = R[ridx(i, j)];
+            for (int i = 0; i < N; ++i) s.r[i + N * j] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
         (void)m;
-        qrfac_small(N, s.r, s.ipvt, rdiag, wa);
+        qrfac_small(N, N, s.r, s.ipvt, rdiag, wa);
         if (iter == 1) {
             double sq = 0.0;
 #pragma unroll
@@ -199,14 +218,14 @@ struct LaneLM {
 #pragma unroll
         for (int j = 0; j < N; ++j) w4[j] = q[j];
         for (int j = 0; j < N; ++j) {
-            const double ajj = s.r[j + NPMAX * j];
+            const double ajj = s.r[j + N * j];
             if (ajj != 0.0) {
                 double sum = 0.0;
-                for (int i = j; i < N; ++i) sum += s.r[i + NPMAX * j] * w4[i];
+                for (int i = j; i < N; ++i) sum += s.r[i + N * j] * w4[i];
                 double temp = -sum / ajj;
-                for (int i = j; i < N; ++i) w4[i] += s.r[i + NPMAX * j] * temp;
+                for (int i = j; i < N; ++i) w4[i] += s.r[i + N * j] * temp;
             }
-            s.r[j + NPMAX * j] = rdiag[j];
+            s.r[j + N * j] = rdiag[j];
             s.qtf[j] = w4[j];
         }
         gnorm = 0.0;
@@ -216,7 +235,7 @@ struct LaneLM {
                 const double al = acnorm[l];
                 if (al != 0.0) {
                     double sum = 0.0;
-                    for (int i = 0; i <= j; ++i) sum += s.r[i + NPMAX * j] * (s.qtf[i] / fnorm);
+                    for (int i = 0; i <= j; ++i) sum += s.r[i + N * j] * (s.qtf[i] / fnorm);
                     gnorm = fmax(gnorm, fabs(sum / al));
                 }
             }
@@ -233,12 +252,12 @@ struct LaneLM {
         return LANE_TRIAL;
     }
 
-    PFX_HD void trial_begin() {
-        lmpar_seq(N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.sdiag, s.wa1, s.wa2);
+    PFX_HD void trial_begin(const LaneWs& s) {
+        lmpar_seq(N, N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.sdiag, s.wa1, s.wa2);
         for (int j = 0; j < N; ++j) s.wa1[j] = 0.0;
         for (int j = 0; j < N; ++j) {
             double temp = -s.step[s.ipvt[j]];
-            for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + NPMAX * j] * temp;
+            for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + N * j] * temp;
         }
         rpnorm = enorm_seq(N, s.wa1);
         double sq = 0.0;

@@ -51,16 +51,26 @@ struct LmShared {
     int pad[NPMAX];
 };
 
-PFX_HD inline double enorm_seq(int n, const double* x) {
+// Strided view: element k of a small per-lane vector lives at p[k * stride].  With stride = block
+// size and the lane index folded into p, the 32 lanes of a warp touch 32 consecutive words, i.e.
+// shared-memory accesses of the lane-per-fit kernels are bank-conflict free.
+template <class T>
+struct SPtr {
+    T* p;
+    int stride;
+    PFX_HD T& operator[](int k) const { return p[(size_t)k * stride]; }
+};
+
+template <class V>
+PFX_HD inline double enorm_seq(int n, V x) {
     double s = 0.0;
     for (int i = 0; i < n; ++i) s += x[i] * x[i];
     return sqrt(s);
 }
 
 // MINPACK qrsolv on the n x n system, r column major with leading dimension NPMAX.
-PFX_HD PFX_NOINLINE inline void qrsolv_seq(int n, double* r, const int* ipvt, const double* diag,
-                              const double* qtb, double* x, double* sdiag, double* wa) {
-    const int ld = NPMAX;
+template <class RV, class IV>
+PFX_HD PFX_NOINLINE void qrsolv_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, RV x, RV sdiag, RV wa) {
     for (int j = 0; j < n; ++j) {
         for (int i = j; i < n; ++i) r[i + ld * j] = r[j + ld * i];
         x[j] = r[j + ld * j];
@@ -115,10 +125,9 @@ PFX_HD PFX_NOINLINE inline void qrsolv_seq(int n, double* r, const int* ipvt, co
 }
 
 // MINPACK lmpar.
-PFX_HD PFX_NOINLINE inline void lmpar_seq(int n, double* r, const int* ipvt, const double* diag,
-                             const double* qtb, double delta, double& par, double* x,
-                             double* sdiag, double* wa1, double* wa2) {
-    const int ld = NPMAX;
+template <class RV, class IV>
+PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, double delta, double& par,
+                                   RV x, RV sdiag, RV wa1, RV wa2) {
     const double p1 = 0.1, p001 = 0.001;
     int nsing = n;
     for (int j = 0; j < n; ++j) {
@@ -172,7 +181,7 @@ PFX_HD PFX_NOINLINE inline void lmpar_seq(int n, double* r, const int* ipvt, con
         if (par == 0.0) par = fmax(LM_DWARF, p001 * paru);
         double temp = sqrt(par);
         for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
-        qrsolv_seq(n, r, ipvt, wa1, qtb, x, sdiag, wa2);
+        qrsolv_seq(n, ld, r, ipvt, wa1, qtb, x, sdiag, wa2);
         for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
         dxnorm = enorm_seq(n, wa2);
         temp = fp;
@@ -445,7 +454,7 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
             PFX_TCOUNT(10);
             if (g.leader()) {
                 double lpar = par;
-                lmpar_seq(NP, s.r, s.ipvt, s.diag, s.qtf, delta, lpar, s.step, s.sdiag, s.wa1, s.wa2);
+                lmpar_seq<double*, int*>(NP, NPMAX, s.r, s.ipvt, s.diag, s.qtf, delta, lpar, s.step, s.sdiag, s.wa1, s.wa2);
                 s.bc[0] = lpar;
                 // || R P^T p ||
                 for (int j = 0; j < NP; ++j) s.wa1[j] = 0.0;
@@ -453,7 +462,7 @@ PFX_HD inline int lmdif(const G& g, const Model& f, int m, double (&x)[NP], cons
                     double temp = -s.step[s.ipvt[j]];
                     for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + NPMAX * j] * temp;
                 }
-                s.bc[1] = enorm_seq(NP, s.wa1);
+                s.bc[1] = enorm_seq<double*>(NP, s.wa1);
             }
             g.sync();
             par = s.bc[0];

@@ -106,6 +106,9 @@ static int run_lane_cb(int m, double* x, hs_resid_cb cb, int* nfev) {
     for (int i = 0; i < NP; ++i) x0[i] = x[i];
     LaneLM<NP> lm;
     lm.init(x0);
+    std::vector<double> wsbuf(lane_ws_doubles(NP) + 8);
+    LaneWs ws;
+    ws.carve(wsbuf.data(), 1, NP);
     int phase = LANE_JAC;
     while (phase != LANE_DONE) {
         if (phase == LANE_JAC) {
@@ -122,9 +125,9 @@ static int run_lane_cb(int m, double* x, hs_resid_cb cb, int* nfev) {
                 for (int j = 0; j < NP; ++j) a[j] = (fj[(size_t)j * m + i] - f0[i]) / lm.h[j];
                 lm.jac_row(a, f0[i]);
             }
-            phase = lm.jac_end(m);
+            phase = lm.jac_end(ws, m);
         } else {
-            lm.trial_begin();
+            lm.trial_begin(ws);
             cb(lm.xnew, f1.data());
             double s = 0.0;
             for (int i = 0; i < m; ++i) s += f1[i] * f1[i];
@@ -155,9 +158,12 @@ extern "C" unsigned hs_gauss_lane(const void* profile, int dtype, int m, double 
     b.dat = dat.data();
     b.xs = xs.data();
     b.stride = 1;
+    std::vector<double> wsbuf(lane_ws_doubles(8) + 8);
+    LaneWs ws;
+    ws.carve(wsbuf.data(), 1, 4);
     GaussLane g;
     g.start(profile, dtype, 0, m, ph_expect);
-    while (g.phase != GP_IDLE) g.step(b);
+    while (g.phase != GP_IDLE) g.step(b, ws);
     for (int k = 0; k < 9; ++k) ier[PFX_FIT_T1 + k] = g.ier[k];
     feat[7] = g.t1_fwhm;
     feat[8] = g.t1_chi;
@@ -178,8 +184,9 @@ extern "C" unsigned hs_gauss_lane(const void* profile, int dtype, int m, double 
     cy.t1_fwhm = g.t1_fwhm;
     cy.skip = 0;
     Gauss8Lane f;
+    ws.carve(wsbuf.data(), 1, 8);
     f.start(profile, dtype, 0, m, cy, b);
-    while (f.phase != GP_IDLE) f.step(b);
+    while (f.phase != GP_IDLE) f.step(b, ws);
     ier[PFX_FIT_DG_FINAL] = f.ier;
     feat[9] = f.s10;
     feat[10] = f.s11;
