@@ -190,7 +190,10 @@ int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t fea
                    const void* dmstat, const double* params,
                    double* feat, int64_t feat_ld, int8_t* ier, int32_t* status, int64_t chunk);
 
-/* Timings of the most recent pfx_score_dev / pfx_score_host call on this context (synchronises). */
+/* Stage timing.  By default pfx_score_dev overlaps independent score groups on a side stream.
+ * With stage timing on, the groups run back to back on the caller's stream with a CUDA event
+ * between them, and pfx_last_timing (which synchronises) returns their durations. */
+int pfx_set_stage_timing(pfx_ctx* ctx, int on);
 int pfx_last_timing(pfx_ctx* ctx, pfx_timing* out);
 
 #ifdef __cplusplus

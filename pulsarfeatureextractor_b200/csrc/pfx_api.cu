@@ -10,18 +10,6 @@
 
 using namespace pfx;
 
-#if defined(PFX_PROFILE)
-__device__ unsigned long long pfx_prof[16];
-extern "C" int pfx_prof_dump(unsigned long long* out, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, pfx_prof, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(pfx_prof, z, sizeof(z));
-    }
-    return 0;
-}
-#endif
 
 int pfx::set_err(pfx_ctx* ctx, int code, const char* fmt, ...) {
     if (ctx) {
@@ -54,7 +42,12 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     }
     ctx->scratch_bytes = sizeof(u64) * COUNTER_SLOTS * COUNTERS_PER_SLOT;
     for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
-    for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
+    }
     *out = ctx;
     return PFX_OK;
 }
@@ -66,9 +59,14 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     cudaFree(ctx->counters);
     if (ctx->hist_scratch) cudaFree(ctx->hist_scratch);
     if (ctx->carry) cudaFree(ctx->carry);
+    for (int i = 0; i < 4; ++i)
+        if (ctx->lane_buf[i]) cudaFree(ctx->lane_buf[i]);
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         cudaStreamDestroy(ctx->streams[i]);
+        cudaStreamDestroy(ctx->side[i]);
+        cudaEventDestroy(ctx->fork_ev[i]);
+        cudaEventDestroy(ctx->join_ev[i]);
     }
     for (int i = 0; i < N_EVENTS; ++i) cudaEventDestroy(ctx->ev[i]);
     free(ctx);
@@ -193,22 +191,44 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
         rc = launch_fill_nan(ctx, feat, n, feat_ld, PFX_NBATES, st);
         if (rc) return rc;
         ++launches;
-        rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, 0);
+        // The histogram -> Gaussian chain is the long pole and ends in a tail of slow candidates;
+        // scores 1-4, 12-19 and 20-22 do not depend on it and run on a side stream next to it.
+        // (Timed calls keep everything on one stream so that the per-stage events mean something.)
+        cudaStream_t sd = st;
+        const int par = ctx->counter_slot & 1;
+        if (!timed) {
+            sd = ctx->side[par];
+            PFX_CUDA(ctx, cudaEventRecord(ctx->fork_ev[par], st));
+            PFX_CUDA(ctx, cudaStreamWaitEvent(sd, ctx->fork_ev[par], 0));
+        }
+        if (!timed) {
+            rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+            if (rc) return rc;
+            rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
+            if (rc) return rc;
+        }
+        rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd, 0);
+        if (rc) return rc;
+        if (timed) {
+            cudaEventRecord(ctx->ev[e++], st);
+            rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
+            rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
+        }
+        rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, 3);
         if (rc) return rc;
         if (timed) cudaEventRecord(ctx->ev[e++], st);
-        rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+        rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, 4);
         if (rc) return rc;
         if (timed) cudaEventRecord(ctx->ev[e++], st);
-        rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
-        if (rc) return rc;
-        if (timed) cudaEventRecord(ctx->ev[e++], st);
-        rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, st, 3);
-        if (rc) return rc;
-        if (timed) cudaEventRecord(ctx->ev[e++], st);
-        rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, st, 4);
-        if (rc) return rc;
-        if (timed) cudaEventRecord(ctx->ev[e++], st);
-        launches += 5;
+        if (!timed) {
+            PFX_CUDA(ctx, cudaEventRecord(ctx->join_ev[par], sd));
+            PFX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join_ev[par], 0));
+        }
+        launches += 6;
     }
     ctx->last_launches = launches;
     if (timed) ctx->ev_valid = bates;
@@ -224,7 +244,13 @@ extern "C" int pfx_score_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, ui
     if (n == 0) return PFX_OK;
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
     return score_dev_impl(ctx, shape, n, features, profile, subbands, dmcurve, dmstat, params, feat, feat_ld,
-                          ier, status, (cudaStream_t)stream, true);
+                          ier, status, (cudaStream_t)stream, ctx->stage_timing != 0);
+}
+
+extern "C" int pfx_set_stage_timing(pfx_ctx* ctx, int on) {
+    if (!ctx) return PFX_ERR_INVALID;
+    ctx->stage_timing = on;
+    return PFX_OK;
 }
 
 extern "C" int pfx_last_timing(pfx_ctx* ctx, pfx_timing* out) {

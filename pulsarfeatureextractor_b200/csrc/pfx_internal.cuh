@@ -35,8 +35,14 @@ struct pfx_ctx {
     size_t hist_scratch_bytes;
     void* carry;              // per-candidate records passed between the two Gaussian kernels
     size_t carry_bytes;
+    void* lane_buf[4];        // per-lane data vectors of the lane-per-candidate kernels
+    size_t lane_bytes[4];
     cudaEvent_t ev[pfx::N_EVENTS];
+    // fork/join: the independent score groups of one call run on a side stream
+    cudaStream_t side[2];
+    cudaEvent_t fork_ev[2], join_ev[2];
     bool ev_valid;
+    int stage_timing;         // 1: serialise the stages of pfx_score_dev and time each (pfx_last_timing)
     int last_launches;
     // host-path staging
     cudaStream_t streams[2];

@@ -14,14 +14,32 @@
 
 using namespace pfx;
 
+#if defined(PFX_PROFILE)
+// development build (make prof): cycles per section of the lane state machine
+static __device__ unsigned long long pfx_prof[16];
+extern "C" int pfx_prof_dump(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, pfx_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(pfx_prof, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
 namespace {
 
-// shared memory of a block of T lanes: ws[nws][T] float64 | dat[m][T] float64 | xs[m][T] uint16
-__device__ __forceinline__ LaneBuf lane_buf(double* smem, int m, int nws) {
+// Per-lane data vector and bin numbers live in a global scratch area laid out [row][lane] over all
+// lanes of the grid, so a warp reads 32 consecutive float64 per row (coalesced, L1/L2 resident);
+// the small n x n workspace is in shared memory, [element][lane of the block].
+__device__ __forceinline__ LaneBuf lane_buf(double* gdat, unsigned short* gxs) {
     LaneBuf b;
-    b.stride = blockDim.x;
-    b.dat = smem + (size_t)nws * blockDim.x + threadIdx.x;
-    b.xs = (unsigned short*)(smem + (size_t)(nws + m) * blockDim.x) + threadIdx.x;
+    const size_t lanes = (size_t)gridDim.x * blockDim.x;
+    const size_t lane = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    b.stride = (int)lanes;
+    b.dat = gdat + lane;
+    b.xs = gxs + lane;
     return b;
 }
 __device__ __forceinline__ LaneWs lane_ws(double* smem, int n) {
@@ -30,11 +48,12 @@ __device__ __forceinline__ LaneWs lane_ws(double* smem, int n) {
     return w;
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
-               int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry) {
+               int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
+               unsigned short* gxs) {
     extern __shared__ double smem[];
-    const LaneBuf b = lane_buf(smem, m, lane_ws_doubles(4));
+    const LaneBuf b = lane_buf(gdat, gxs);
     const LaneWs ws = lane_ws(smem, 4);
     GaussLane g;
     g.phase = GP_IDLE;
@@ -90,15 +109,29 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
             }
         }
         if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
+#if defined(PFX_PROFILE)
+        {
+            // development build: cycles per section, summed over the lanes that executed it
+            long long t0 = clock64();
+            if (g.phase == GP_SETUP) { g.setup(b); long long t1 = clock64(); atomicAdd(&pfx_prof[0], (u64)(t1 - t0)); atomicAdd(&pfx_prof[8], 1ULL); t0 = t1; }
+            if (g.phase == GP_JAC) { g.jac_pass(b, ws); long long t1 = clock64(); atomicAdd(&pfx_prof[1], (u64)(t1 - t0)); atomicAdd(&pfx_prof[9], 1ULL); t0 = t1; }
+            if (g.phase == GP_TRIAL) { g.trial_pass(b, ws); long long t1 = clock64(); atomicAdd(&pfx_prof[2], (u64)(t1 - t0)); atomicAdd(&pfx_prof[10], 1ULL); t0 = t1; }
+            if (g.phase == GP_FIN) { g.finish(b); long long t1 = clock64(); atomicAdd(&pfx_prof[3], (u64)(t1 - t0)); atomicAdd(&pfx_prof[11], 1ULL); t0 = t1; }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&pfx_prof[12], 1ULL); }
+        }
+#else
         g.step(b, ws);
+#endif
     }
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
-              int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry) {
+              int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat,
+              unsigned short* gxs) {
     extern __shared__ double smem[];
-    const LaneBuf b = lane_buf(smem, m, lane_ws_doubles(8));
+    const LaneBuf b = lane_buf(gdat, gxs);
     const LaneWs ws = lane_ws(smem, 8);
     Gauss8Lane g;
     g.phase = GP_IDLE;
@@ -129,16 +162,25 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
 
 }  // namespace
 
-static int lane_block(pfx_ctx* ctx, int m, int np, int* threads, size_t* smem) {
-    // per lane: LM workspace + m float64 + m uint16
-    const size_t per_lane = (size_t)m * 10 + (size_t)lane_ws_doubles(np) * 8;
-    int t = 128;
-    const size_t budget = (size_t)ctx->smem_optin - 1024;
-    while (t > 32 && per_lane * t > budget) t -= 32;
-    if (per_lane * t > budget)
-        return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin=%d needs %zu bytes of shared memory per lane", m, per_lane);
-    *threads = t;
-    *smem = (per_lane * t + 15) / 16 * 16;
+static const int LANE_THREADS = 128;
+
+// scratch for the per-lane data vectors of one launch: lanes x m x (8 + 2) bytes
+static int lane_scratch(pfx_ctx* ctx, size_t lanes, int m, int slot, double** gdat, unsigned short** gxs) {
+    const size_t need = ((lanes * (size_t)m * 10) + 255) / 256 * 256;
+    if (ctx->lane_bytes[slot] < need) {
+        if (ctx->lane_buf[slot]) {
+            cudaDeviceSynchronize();
+            cudaFree(ctx->lane_buf[slot]);
+            ctx->scratch_bytes -= ctx->lane_bytes[slot];
+            ctx->lane_buf[slot] = nullptr;
+            ctx->lane_bytes[slot] = 0;
+        }
+        PFX_CUDA(ctx, cudaMalloc(&ctx->lane_buf[slot], need));
+        ctx->lane_bytes[slot] = need;
+        ctx->scratch_bytes += need;
+    }
+    *gdat = (double*)ctx->lane_buf[slot];
+    *gxs = (unsigned short*)((char*)ctx->lane_buf[slot] + lanes * (size_t)m * 8);
     return PFX_OK;
 }
 
@@ -146,40 +188,47 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
                       int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
     const int m = s->nbin;
     if (m < 8 || m > 65535) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin out of range");
-    int threads;
-    size_t smem;
-    int rc = lane_block(ctx, m, 4, &threads, &smem);
-    if (rc) return rc;
+    const int threads = LANE_THREADS;
+    const int par = ctx->counter_slot & 1;      // calls in flight alternate between two scratch sets
     // carry records
     const size_t need = (size_t)n * sizeof(GaussCarry);
     if (ctx->carry_bytes < need) {
         if (ctx->carry) {
             cudaDeviceSynchronize();
             cudaFree(ctx->carry);
-            ctx->scratch_bytes -= ctx->carry_bytes;
+            ctx->scratch_bytes -= 2 * ctx->carry_bytes;
             ctx->carry = nullptr;
             ctx->carry_bytes = 0;
         }
-        PFX_CUDA(ctx, cudaMalloc(&ctx->carry, need * 2));      // two halves: calls in flight alternate
+        PFX_CUDA(ctx, cudaMalloc(&ctx->carry, need * 2));
         ctx->carry_bytes = need;
         ctx->scratch_bytes += need * 2;
     }
-    GaussCarry* carry = (GaussCarry*)((char*)ctx->carry + (size_t)(ctx->counter_slot & 1) * ctx->carry_bytes);
-    int grid;
-    rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
-    if (rc) return rc;
-    const long long lanes = (long long)grid * threads;
-    if (lanes > n) grid = (int)((n + threads - 1) / threads);
-    k_gauss_rounds<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
-                                                 take_counter(ctx, ck, st), carry);
-    PFX_CUDA(ctx, cudaGetLastError());
-    rc = lane_block(ctx, m, 8, &threads, &smem);
-    if (rc) return rc;
-    rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
-    if (rc) return rc;
-    if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
-    k_gauss_final<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier,
-                                                take_counter(ctx, ck + 4, st), carry);
-    PFX_CUDA(ctx, cudaGetLastError());
+    GaussCarry* carry = (GaussCarry*)((char*)ctx->carry + (size_t)par * ctx->carry_bytes);
+    double* gdat;
+    unsigned short* gxs;
+    int grid, rc;
+    {
+        const size_t smem = (size_t)lane_ws_doubles(4) * 8 * threads;
+        rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
+        if (rc) return rc;
+        if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
+        rc = lane_scratch(ctx, (size_t)grid * threads, m, par * 2 + 0, &gdat, &gxs);
+        if (rc) return rc;
+        k_gauss_rounds<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
+                                                     take_counter(ctx, ck, st), carry, gdat, gxs);
+        PFX_CUDA(ctx, cudaGetLastError());
+    }
+    {
+        const size_t smem = (size_t)lane_ws_doubles(8) * 8 * threads;
+        rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
+        if (rc) return rc;
+        if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
+        rc = lane_scratch(ctx, (size_t)grid * threads, m, par * 2 + 1, &gdat, &gxs);
+        if (rc) return rc;
+        k_gauss_final<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier,
+                                                    take_counter(ctx, ck + 4, st), carry, gdat, gxs);
+        PFX_CUDA(ctx, cudaGetLastError());
+    }
     return PFX_OK;
 }

@@ -45,10 +45,31 @@ struct G4Flags {
     bool abs_sigma, abs_bg;
 };
 
+// exp(-((x-mu)/sigma)^2 / 2) with the division replaced by a multiplication with 1/sigma
+// (computed once per pass with an IEEE division) and the branch-free exponential: the two
+// deviations from the reference expression are below 2 ulp, the size of the differences between
+// any two exp() implementations.
+PFX_HD inline double gauss_fast(double xv, double mu, double inv_sigma) {
+    const double t = PFX_MUL(PFX_SUB(xv, mu), inv_sigma);
+    return exp_neg(PFX_MUL(-PFX_MUL(t, t), 0.5));
+}
+
+// one evaluation point of the 4-parameter family, prepared once per pass
+struct G4Eval {
+    double mu, inv, amx, bg;
+    PFX_HD void set(const double (&p)[4], G4Flags fl) {
+        mu = p[1];
+        inv = 1.0 / (fl.abs_sigma ? fabs(p[0]) : p[0]);
+        amx = fabs(p[2]);
+        bg = fl.abs_bg ? fabs(p[3]) : p[3];
+    }
+    PFX_HD double value(double xv) const { return PFX_ADD(PFX_MUL(amx, gauss_fast(xv, mu, inv)), bg); }
+};
+
 PFX_HD inline double g4_value(const double (&p)[4], G4Flags fl, double xv) {
-    const double sg = fl.abs_sigma ? fabs(p[0]) : p[0];
-    const double bg = fl.abs_bg ? fabs(p[3]) : p[3];
-    return PFX_ADD(PFX_MUL(fabs(p[2]), gauss_core(xv, p[1], sg)), bg);
+    G4Eval e;
+    e.set(p, fl);
+    return e.value(xv);
 }
 
 struct GaussLane {
@@ -274,25 +295,43 @@ struct GaussLane {
         lm.jac_begin();
         const double* x = lm.x;
         const double* h = lm.h;
-        const double sg = fl.abs_sigma ? fabs(x[0]) : x[0];
-        const double sgh = fl.abs_sigma ? fabs(x[0] + h[0]) : (x[0] + h[0]);
+        const double isg = 1.0 / (fl.abs_sigma ? fabs(x[0]) : x[0]);
+        const double isgh = 1.0 / (fl.abs_sigma ? fabs(x[0] + h[0]) : (x[0] + h[0]));
         const double mu = x[1], muh = x[1] + h[1];
         const double amx = fabs(x[2]), amxh = fabs(x[2] + h[2]);
         const double bg = fl.abs_bg ? fabs(x[3]) : x[3];
         const double bgh = fl.abs_bg ? fabs(x[3] + h[3]) : (x[3] + h[3]);
-        for (int i = 0; i < nrows; ++i) {
-            const double xv = (double)b.x(i), yv = b.d(i);
-            const double e0 = gauss_core(xv, mu, sg);
-            const double e1 = gauss_core(xv, mu, sgh);
-            const double e2 = gauss_core(xv, muh, sg);
-            const double base = PFX_MUL(amx, e0);
-            const double f0 = PFX_SUB(yv, PFX_ADD(base, bg));
-            double a[4];
-            a[0] = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e1), bg)) - f0) / h[0];
-            a[1] = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e2), bg)) - f0) / h[1];
-            a[2] = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) / h[2];
-            a[3] = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) / h[3];
-            lm.jac_row(a, f0);
+        const double ih0 = 1.0 / h[0], ih1 = 1.0 / h[1], ih2 = 1.0 / h[2], ih3 = 1.0 / h[3];
+        // rows are produced two at a time (six independent exponentials in flight) into the staged
+        // block and eliminated eight at a time
+        constexpr int B = LANE_BLOCK_ROWS;
+        for (int i0 = 0; i0 < nrows; i0 += B) {
+            const int rows = (nrows - i0 < B) ? nrows - i0 : B;
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
+                const int i = i0 + r;
+                const double xv = (double)b.x(i), yv = b.d(i);
+                const double e0 = gauss_fast(xv, mu, isg);
+                const double e1 = gauss_fast(xv, mu, isgh);
+                const double e2 = gauss_fast(xv, muh, isg);
+                const double base = PFX_MUL(amx, e0);
+                const double f0 = PFX_SUB(yv, PFX_ADD(base, bg));
+                const double a0 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e1), bg)) - f0) * ih0;
+                const double a1 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e2), bg)) - f0) * ih1;
+                const double a2 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) * ih2;
+                const double a3 = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) * ih3;
+                lm.acn2[0] = PFX_FMA(a0, a0, lm.acn2[0]);
+                lm.acn2[1] = PFX_FMA(a1, a1, lm.acn2[1]);
+                lm.acn2[2] = PFX_FMA(a2, a2, lm.acn2[2]);
+                lm.acn2[3] = PFX_FMA(a3, a3, lm.acn2[3]);
+                lm.f2 = PFX_FMA(f0, f0, lm.f2);
+                ws.blk[r * 5 + 0] = a0;
+                ws.blk[r * 5 + 1] = a1;
+                ws.blk[r * 5 + 2] = a2;
+                ws.blk[r * 5 + 3] = a3;
+                ws.blk[r * 5 + 4] = f0;
+            }
+            lm.jac_block_staged<B>(ws.blk, rows);
         }
         const int r = lm.jac_end(ws, nrows);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
@@ -300,9 +339,12 @@ struct GaussLane {
 
     PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
         lm.trial_begin(ws);
+        G4Eval ev;
+        ev.set(lm.xnew, fl);
         double s = 0.0;
+#pragma unroll 4
         for (int i = 0; i < nrows; ++i) {
-            const double f = PFX_SUB(b.d(i), g4_value(lm.xnew, fl, (double)b.x(i)));
+            const double f = PFX_SUB(b.d(i), ev.value((double)b.x(i)));
             s = PFX_FMA(f, f, s);
         }
         const int r = lm.trial_end(sqrt(s));
@@ -315,9 +357,12 @@ struct GaussLane {
         if (stage == 0) {
             for (int k = 0; k < 4; ++k) p_t1[k] = p[k];
             t1_fwhm = fabs(FWHM_K * p[0]);
+            G4Eval ev;
+            ev.set(p, fl);
             double c = 0.0;
+#pragma unroll 4
             for (int i = 0; i < m; ++i) {
-                const double dlt = b.d(i) - g4_value(p, fl, (double)i);
+                const double dlt = b.d(i) - ev.value((double)i);
                 c = PFX_FMA(dlt, dlt, c);
             }
             t1_chi = c / (double)m;
@@ -326,9 +371,12 @@ struct GaussLane {
             const double nfwhm = fabs(FWHM_K * p[0]);
             const double lo = p[2] - (1.5 * nfwhm) / 2.0;
             const double hi = p[2] + (1.5 * nfwhm) / 2.0;
+            G4Eval fe;
+            fe.set(p, fl);
+#pragma unroll 4
             for (int i = 0; i < m && stage < 8; ++i) {
                 const double xv = (double)i;
-                const double ev = g4_value(p, fl, xv);
+                const double ev = fe.value(xv);
                 const double yv = yrot(i);
                 double nv;
                 if (ev <= yv) nv = PFX_ADD(PFX_SUB(yv, ev), p[3]);
@@ -395,8 +443,8 @@ struct Gauss8Lane {
     }
 
     PFX_HD static double value(const double* p, double xv) {
-        const double a = PFX_MUL(fabs(p[2]), gauss_core(xv, p[1], fabs(p[0])));
-        const double c = PFX_MUL(fabs(p[6]), gauss_core(xv, p[5], fabs(p[4])));
+        const double a = PFX_MUL(fabs(p[2]), gauss_fast(xv, p[1], 1.0 / fabs(p[0])));
+        const double c = PFX_MUL(fabs(p[6]), gauss_fast(xv, p[5], 1.0 / fabs(p[4])));
         const double bg = PFX_MUL(PFX_ADD(fabs(p[3]), fabs(p[7])), 0.5);
         return PFX_ADD(PFX_ADD(a, c), bg);
     }
@@ -405,28 +453,47 @@ struct Gauss8Lane {
         lm.jac_begin();
         const double* x = lm.x;
         const double* h = lm.h;
-        const double s1 = fabs(x[0]), s1h = fabs(x[0] + h[0]), m1 = x[1], m1h = x[1] + h[1];
+        const double s1 = 1.0 / fabs(x[0]), s1h = 1.0 / fabs(x[0] + h[0]), m1 = x[1], m1h = x[1] + h[1];
         const double a1 = fabs(x[2]), a1h = fabs(x[2] + h[2]);
-        const double s2 = fabs(x[4]), s2h = fabs(x[4] + h[4]), m2 = x[5], m2h = x[5] + h[5];
+        const double s2 = 1.0 / fabs(x[4]), s2h = 1.0 / fabs(x[4] + h[4]), m2 = x[5], m2h = x[5] + h[5];
         const double a2 = fabs(x[6]), a2h = fabs(x[6] + h[6]);
         const double bg = PFX_MUL(PFX_ADD(fabs(x[3]), fabs(x[7])), 0.5);
         const double bg3 = PFX_MUL(PFX_ADD(fabs(x[3] + h[3]), fabs(x[7])), 0.5);
         const double bg7 = PFX_MUL(PFX_ADD(fabs(x[3]), fabs(x[7] + h[7])), 0.5);
-        for (int i = 0; i < m; ++i) {
-            const double xv = (double)i, yv = b.d(i);
-            const double e1 = gauss_core(xv, m1, s1), e2 = gauss_core(xv, m2, s2);
-            const double g1 = PFX_MUL(a1, e1), g2 = PFX_MUL(a2, e2);
-            const double f0 = PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg));
-            double a[8];
-            a[0] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1, gauss_core(xv, m1, s1h)), g2), bg)) - f0) / h[0];
-            a[1] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1, gauss_core(xv, m1h, s1)), g2), bg)) - f0) / h[1];
-            a[2] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1h, e1), g2), bg)) - f0) / h[2];
-            a[3] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg3)) - f0) / h[3];
-            a[4] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2, gauss_core(xv, m2, s2h))), bg)) - f0) / h[4];
-            a[5] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2, gauss_core(xv, m2h, s2))), bg)) - f0) / h[5];
-            a[6] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2h, e2)), bg)) - f0) / h[6];
-            a[7] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg7)) - f0) / h[7];
-            lm.jac_row(a, f0);
+        double ih[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ih[k] = 1.0 / h[k];
+#ifndef PFX_G8_BLOCK
+#define PFX_G8_BLOCK 2
+#endif
+        constexpr int B = PFX_G8_BLOCK;
+#pragma unroll 1
+        for (int i0 = 0; i0 < m; i0 += B) {
+            double A[B][8], bv[B];
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                const int i = i0 + r;
+                if (i < m) {
+                    const double xv = (double)i, yv = b.d(i);
+                    const double e1 = gauss_fast(xv, m1, s1), e2 = gauss_fast(xv, m2, s2);
+                    const double g1 = PFX_MUL(a1, e1), g2 = PFX_MUL(a2, e2);
+                    const double f0 = PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg));
+                    A[r][0] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1, gauss_fast(xv, m1, s1h)), g2), bg)) - f0) * ih[0];
+                    A[r][1] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1, gauss_fast(xv, m1h, s1)), g2), bg)) - f0) * ih[1];
+                    A[r][2] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(PFX_MUL(a1h, e1), g2), bg)) - f0) * ih[2];
+                    A[r][3] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg3)) - f0) * ih[3];
+                    A[r][4] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2, gauss_fast(xv, m2, s2h))), bg)) - f0) * ih[4];
+                    A[r][5] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2, gauss_fast(xv, m2h, s2))), bg)) - f0) * ih[5];
+                    A[r][6] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, PFX_MUL(a2h, e2)), bg)) - f0) * ih[6];
+                    A[r][7] = (PFX_SUB(yv, PFX_ADD(PFX_ADD(g1, g2), bg7)) - f0) * ih[7];
+                    bv[r] = f0;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) A[r][k] = 0.0;
+                    bv[r] = 0.0;
+                }
+            }
+            lm.jac_block<B>(A, bv);
         }
         const int r = lm.jac_end(ws, m);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;

@@ -22,6 +22,8 @@
 // rounding level exactly like the tree-ordered sums of the warp version did.
 #pragma once
 
+#include <string.h>
+
 #include "pfx_lm.cuh"
 
 namespace pfx {
@@ -79,10 +81,72 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
 
 enum LanePhase { LANE_JAC = 0, LANE_TRIAL = 1, LANE_DONE = 2 };
 
+// reciprocal / reciprocal square root for the orthogonal transformations (not for the model or
+// for MINPACK's own formulas): a few ulp are irrelevant there and the short dependency chain is
+// what bounds the latency of a Jacobian pass
+PFX_HD inline double fast_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(x);
+#else
+    return 1.0 / x;
+#endif
+}
+// exp(a) for a <= 0 (or NaN), branch free: the lane kernels spend most of their time in
+// exp(-t^2/2), and the branches of the library exp()/division fragment the instruction stream
+// (instruction-fetch stalls were the top stall reason in ncu).  Cody-Waite reduction, degree-13
+// polynomial, two-step scaling so that denormal results come out right.  Measured against glibc
+// on 2e7 arguments in [-760, 0]: max error 1 ulp (scripts/micro/exp_check.cpp).
+PFX_HD inline double exp_neg(double a) {
+    const double L2E = 1.4426950408889634074, LN2_HI = 6.93147180369123816490e-01,
+                 LN2_LO = 1.90821492927058770002e-10;
+    const double ac = (a < -745.5) ? -745.5 : a;
+    const double nf = rint(ac * L2E);
+    double r = fma(-nf, LN2_HI, ac);
+    r = fma(-nf, LN2_LO, r);
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int n = (int)nf;
+    const int n1 = n / 2, n2 = n - n1;
+#if defined(__CUDA_ARCH__)
+    const double s1 = __hiloint2double((n1 + 1023) << 20, 0), s2 = __hiloint2double((n2 + 1023) << 20, 0);
+#else
+    double s1, s2;
+    {
+        unsigned long long b1 = (unsigned long long)(n1 + 1023) << 52, b2 = (unsigned long long)(n2 + 1023) << 52;
+        memcpy(&s1, &b1, 8);
+        memcpy(&s2, &b2, 8);
+    }
+#endif
+    const double res = (p * s1) * s2;
+    return (a != a) ? a : res;
+}
+
+PFX_HD inline double fast_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 // per-lane workspace of the n x n sub-problem: r (n x n, column major), six n-vectors, ipvt
-PFX_HD inline int lane_ws_doubles(int n) { return n * n + 6 * n + (n + 1) / 2; }
+constexpr int LANE_BLOCK_ROWS = 8;
+// r, six vectors, ipvt (one int per float64 slot), and the staged row block of the Jacobian pass
+PFX_HD inline int lane_ws_doubles(int n) { return n * n + 7 * n + LANE_BLOCK_ROWS * (n + 1); }
 struct LaneWs {
-    SPtr<double> r, diag, qtf, step, sdiag, wa1, wa2;
+    SPtr<double> r, diag, qtf, step, sdiag, wa1, wa2, blk;
     SPtr<int> ipvt;
     // base points at this lane's first element; consecutive elements are `stride` doubles apart
     PFX_HD void carve(double* base, int stride, int n) {
@@ -94,9 +158,10 @@ struct LaneWs {
         sdiag = at(n * n + 3 * n);
         wa1 = at(n * n + 4 * n);
         wa2 = at(n * n + 5 * n);
-        // ints are packed two per double slot, still strided per lane
+        // one int per float64 slot (low half), strided like the rest
         ipvt.p = (int*)(base + (size_t)(n * n + 6 * n) * stride);
         ipvt.stride = 2 * stride;
+        blk = at(n * n + 7 * n);
     }
 };
 
@@ -178,6 +243,97 @@ struct LaneLM {
                 const double qj = q[j];
                 q[j] = PFX_FMA(c, qj, sn * b);
                 b = PFX_FMA(c, b, -sn * qj);
+            }
+        }
+    }
+
+    // B rows at once: Householder reflections eliminate the block against the triangular factor.
+    // One sqrt and one division per column per block instead of one rsqrt per column per row,
+    // and the B rows (their exponentials, their dot products) are independent instruction
+    // streams, which is what a single resident warp per scheduler needs to keep the FP64 pipe
+    // busy.  Rows beyond the data are passed as zeros (they change nothing).
+    template <int B>
+    PFX_HD void jac_block(double (&A)[B][N], double (&bv)[B]) {
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+            f2 = PFX_FMA(bv[r], bv[r], f2);
+#pragma unroll
+            for (int j = 0; j < N; ++j) acn2[j] = PFX_FMA(A[r][j], A[r][j], acn2[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double ss = 0.0;
+#pragma unroll
+            for (int r = 0; r < B; ++r) ss = PFX_FMA(A[r][j], A[r][j], ss);
+            if (ss != 0.0) {
+                const double rjj = R[ridx(j, j)];
+                const double nrm = sqrt(PFX_FMA(rjj, rjj, ss));
+                const double alpha = (rjj > 0.0) ? -nrm : nrm;
+                const double v0 = rjj - alpha;
+                const double beta = 1.0 / (nrm * fabs(v0));
+                R[ridx(j, j)] = alpha;
+#pragma unroll
+                for (int k = j + 1; k < N; ++k) {
+                    double d = v0 * R[ridx(j, k)];
+#pragma unroll
+                    for (int r = 0; r < B; ++r) d = PFX_FMA(A[r][j], A[r][k], d);
+                    const double t = beta * d;
+                    R[ridx(j, k)] = PFX_FMA(-t, v0, R[ridx(j, k)]);
+#pragma unroll
+                    for (int r = 0; r < B; ++r) A[r][k] = PFX_FMA(-t, A[r][j], A[r][k]);
+                }
+                double d = v0 * q[j];
+#pragma unroll
+                for (int r = 0; r < B; ++r) d = PFX_FMA(A[r][j], bv[r], d);
+                const double t = beta * d;
+                q[j] = PFX_FMA(-t, v0, q[j]);
+#pragma unroll
+                for (int r = 0; r < B; ++r) bv[r] = PFX_FMA(-t, A[r][j], bv[r]);
+            }
+        }
+    }
+
+    // Same elimination with the block staged in the lane's strided workspace (shared memory):
+    // row r, column k at blk[r * (N + 1) + k], column N holding f.  The rows are produced by a
+    // compact loop (the exponentials are not replicated B times in the instruction stream) and
+    // consumed here column by column.
+    template <int B>
+    PFX_HD void jac_block_staged(const SPtr<double>& blk, int rows) {
+        double c0[B];      // column j of the block
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double ss = 0.0;
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                c0[r] = (r < rows) ? blk[r * (N + 1) + j] : 0.0;
+                ss = PFX_FMA(c0[r], c0[r], ss);
+            }
+            acn2[j] += 0.0;   // (column norms are accumulated by the producer loop)
+            if (ss != 0.0) {
+                const double rjj = R[ridx(j, j)];
+                const double t2 = PFX_FMA(rjj, rjj, ss);
+                const double inv = fast_rsqrt(t2);
+                const double nrm = t2 * inv;
+                const double alpha = (rjj > 0.0) ? -nrm : nrm;
+                const double v0 = rjj - alpha;
+                const double beta = inv * fast_rcp(fabs(v0));
+                R[ridx(j, j)] = alpha;
+#pragma unroll
+                for (int k = j + 1; k <= N; ++k) {
+                    double ck[B];
+                    double d = v0 * ((k < N) ? R[ridx(j, k < N ? k : j)] : q[j]);
+#pragma unroll
+                    for (int r = 0; r < B; ++r) {
+                        ck[r] = (r < rows) ? blk[r * (N + 1) + k] : 0.0;
+                        d = PFX_FMA(c0[r], ck[r], d);
+                    }
+                    const double t = beta * d;
+                    if (k < N) R[ridx(j, k < N ? k : j)] = PFX_FMA(-t, v0, R[ridx(j, k < N ? k : j)]);
+                    else q[j] = PFX_FMA(-t, v0, q[j]);
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        if (r < rows) blk[r * (N + 1) + k] = PFX_FMA(-t, c0[r], ck[r]);
+                }
             }
         }
     }

@@ -14,7 +14,7 @@
 
 // Optional phase timers (development builds with -DPFX_PROFILE): cycles spent per LM phase,
 // accumulated by the group leader into pfx_prof[] and dumped by pfx_prof_dump().
-#if defined(PFX_PROFILE) && defined(__CUDA_ARCH__)
+#if defined(PFX_PROFILE_LM) && defined(__CUDA_ARCH__)
 extern __device__ unsigned long long pfx_prof[16];
 #define PFX_T0() long long t_prof_ = clock64()
 #define PFX_TACC(slot)                                                        \

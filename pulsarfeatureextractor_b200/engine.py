@@ -88,6 +88,10 @@ class Engine(object):
         self._check(self._lib.pfx_device_info(self._h, ctypes.byref(sm), ctypes.byref(smem), ctypes.byref(scratch)))
         return {"sm_count": sm.value, "smem_per_block": smem.value, "scratch_bytes": scratch.value}
 
+    def set_stage_timing(self, on):
+        """Serialise and time the score groups of score_device (see pfx_set_stage_timing)."""
+        self._check(self._lib.pfx_set_stage_timing(self._h, 1 if on else 0))
+
     def last_timing(self):
         t = _lib.Timing()
         self._check(self._lib.pfx_last_timing(self._h, ctypes.byref(t)))
