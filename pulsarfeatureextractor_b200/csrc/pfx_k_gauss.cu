@@ -162,6 +162,77 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
 
 }  // namespace
 
+#if defined(PFX_PROFILE)
+// micro-benchmark: every lane repeats the T1 Jacobian pass / trial pass of its candidate `reps`
+// times (no LM logic), i.e. the row loops under ideal conditions: no divergence, no tail.
+__global__ void __launch_bounds__(128, 2)
+k_micro_rows(const void* __restrict__ profile, int dtype, long long n, int m, int reps, int what,
+             double* gdat, unsigned short* gxs, double* sink) {
+    extern __shared__ double smem[];
+    const LaneBuf b = lane_buf(gdat, gxs);
+    const LaneWs ws = lane_ws(smem, 4);
+    GaussLane g;
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) % n;
+    g.start(profile, dtype, c, m, 100.0);
+    g.setup(b);
+    double acc = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        if (what == 0) {
+            g.jac_pass(b, ws);
+            acc += g.lm.gnorm;
+            g.phase = GP_JAC;
+        } else if (what == 1) {
+            g.lm.trial_begin(ws);
+            G4Eval ev;
+            ev.set(g.lm.xnew, g.fl);
+            double s = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < g.nrows; ++i) {
+                const double f = PFX_SUB(b.d(i), ev.value((double)b.x(i)));
+                s = PFX_FMA(f, f, s);
+            }
+            acc += s;
+        } else {
+            g.lm.trial_begin(ws);
+            acc += g.lm.pnorm;
+        }
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+extern "C" float pfx_micro_rows(const void* profile, int dtype, long long n, int m, int reps, int what, int blocks_per_sm) {
+    int dev, sms;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int threads = 128, grid = sms * blocks_per_sm;
+    const size_t lanes = (size_t)grid * threads;
+    double *gdat, *sink;
+    cudaMalloc(&gdat, lanes * m * 10 + 256);
+    cudaMalloc(&sink, lanes * 8);
+    unsigned short* gxs = (unsigned short*)((char*)gdat + lanes * m * 8);
+    const size_t smem = (size_t)lane_ws_doubles(4) * 8 * threads;
+    cudaFuncSetAttribute(k_micro_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_micro_rows<<<grid, threads, smem>>>(profile, dtype, n, m, 2, what, gdat, gxs, sink);
+    float ms = 1e30f;
+    for (int t = 0; t < 3; ++t) {
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        k_micro_rows<<<grid, threads, smem>>>(profile, dtype, n, m, reps, what, gdat, gxs, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float t_ms = -1;
+        cudaEventElapsedTime(&t_ms, e0, e1);
+        if (t_ms < ms) ms = t_ms;
+    }
+    if (cudaGetLastError() != cudaSuccess) ms = -2;
+    cudaFree(gdat);
+    cudaFree(sink);
+    return ms;
+}
+#endif
+
 static const int LANE_THREADS = 128;
 
 // scratch for the per-lane data vectors of one launch: lanes x m x (8 + 2) bytes

@@ -141,6 +141,213 @@ PFX_HD inline double fast_rsqrt(double x) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident lmpar / qrsolv for small N (fully unrolled, static indexing; the permutation
+// is applied with select chains).  Same algorithm, branches and sign conventions as MINPACK
+// (pfx_lm.cuh: lmpar_seq / qrsolv_seq); the Givens rotations are formed from one reciprocal
+// square root instead of two divisions and a square root, which shortens the dependency chain
+// that bounds the latency of the trust-region solve (measured: the shared-memory version took
+// ~3e5 cycles per call, more than a whole Jacobian pass).
+template <int N>
+struct SmallLM {
+    double r[N][N];      // r[i][j]: upper triangle = R, strictly lower = S^T (qrsolv work)
+    int ipvt[N];
+    double diag[N], qtb[N];
+
+    PFX_HD static double sel(const double (&a)[N], int idx) {
+        double v = a[0];
+#pragma unroll
+        for (int k = 1; k < N; ++k) v = (k == idx) ? a[k] : v;
+        return v;
+    }
+    PFX_HD static void put(double (&a)[N], int idx, double v) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[k] = (k == idx) ? v : a[k];
+    }
+    PFX_HD static double nrm(const double (&a)[N]) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) s += a[k] * a[k];
+        return sqrt(s);
+    }
+
+    // qrsolv: d = diagonal in pivoted order is looked up through ipvt
+    PFX_HD void qrsolv(const double (&d)[N], double (&x)[N], double (&sdiag)[N]) {
+        double wa[N], rd[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int i = j + 1; i < N; ++i) r[i][j] = r[j][i];
+            rd[j] = r[j][j];
+            wa[j] = qtb[j];
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double dl = sel(d, ipvt[j]);
+            if (dl != 0.0) {
+#pragma unroll
+                for (int k = j; k < N; ++k) sdiag[k] = 0.0;
+                sdiag[j] = dl;
+                double qtbpj = 0.0;
+#pragma unroll
+                for (int k = j; k < N; ++k) {
+                    const double sk = sdiag[k];
+                    if (sk != 0.0) {
+                        const double rkk = r[k][k];
+                        const double h2 = PFX_FMA(rkk, rkk, sk * sk);
+                        double c, sn;
+                        if (h2 > 1e-280 && h2 < 1e280) {
+                            const double inv = fast_rsqrt(h2);
+                            if (fabs(rkk) >= fabs(sk)) {          // tan branch: c = |a|/h, s = sign(a) b/h
+                                c = fabs(rkk) * inv;
+                                sn = (rkk < 0.0 ? -sk : sk) * inv;
+                            } else {                               // cotan branch: s = |b|/h, c = sign(b) a/h
+                                sn = fabs(sk) * inv;
+                                c = (sk < 0.0 ? -rkk : rkk) * inv;
+                            }
+                        } else if (fabs(rkk) >= fabs(sk)) {
+                            const double t = sk / rkk;
+                            c = 0.5 / sqrt(0.25 + 0.25 * (t * t));
+                            sn = c * t;
+                        } else {
+                            const double ct = rkk / sk;
+                            sn = 0.5 / sqrt(0.25 + 0.25 * (ct * ct));
+                            c = sn * ct;
+                        }
+                        r[k][k] = c * rkk + sn * sk;
+                        const double temp = c * wa[k] + sn * qtbpj;
+                        qtbpj = -sn * wa[k] + c * qtbpj;
+                        wa[k] = temp;
+#pragma unroll
+                        for (int i = k + 1; i < N; ++i) {
+                            const double rik = r[i][k];
+                            const double t2 = c * rik + sn * sdiag[i];
+                            sdiag[i] = -sn * rik + c * sdiag[i];
+                            r[i][k] = t2;
+                        }
+                    }
+                }
+            }
+            sdiag[j] = r[j][j];
+            r[j][j] = rd[j];
+        }
+        int nsing = N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            if (sdiag[j] == 0.0 && nsing == N) nsing = j;
+            if (nsing < N) wa[j] = 0.0;
+        }
+#pragma unroll
+        for (int kk = 0; kk < N; ++kk) {
+            const int j = N - 1 - kk;
+            if (j < nsing) {
+                double sum = 0.0;
+#pragma unroll
+                for (int i = j + 1; i < N; ++i)
+                    if (i < nsing) sum += r[i][j] * wa[i];
+                wa[j] = (wa[j] - sum) / sdiag[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) put(x, ipvt[j], wa[j]);
+    }
+
+    // lmpar; x = step (un-negated), returns through par
+    PFX_HD void lmpar(double delta, double& par, double (&x)[N], double (&sdiag)[N]) {
+        const double p1 = 0.1, p001 = 0.001;
+        double wa1[N], wa2[N];
+        int nsing = N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            wa1[j] = qtb[j];
+            if (r[j][j] == 0.0 && nsing == N) nsing = j;
+            if (nsing < N) wa1[j] = 0.0;
+        }
+#pragma unroll
+        for (int kk = 0; kk < N; ++kk) {
+            const int j = N - 1 - kk;
+            if (j < nsing) {
+                wa1[j] = wa1[j] / r[j][j];
+                const double temp = wa1[j];
+#pragma unroll
+                for (int i = 0; i < j; ++i) wa1[i] -= r[i][j] * temp;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) put(x, ipvt[j], wa1[j]);
+        int iter = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
+        double dxnorm = nrm(wa2);
+        double fp = dxnorm - delta;
+        if (fp <= p1 * delta) {
+            par = 0.0;
+            return;
+        }
+        double parl = 0.0;
+        if (nsing >= N) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const int l = ipvt[j];
+                wa1[j] = sel(diag, l) * (sel(wa2, l) / dxnorm);
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double sum = 0.0;
+#pragma unroll
+                for (int i = 0; i < j; ++i) sum += r[i][j] * wa1[i];
+                wa1[j] = (wa1[j] - sum) / r[j][j];
+            }
+            const double temp = nrm(wa1);
+            parl = ((fp / delta) / temp) / temp;
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i <= j; ++i) sum += r[i][j] * qtb[i];
+            wa1[j] = sum / sel(diag, ipvt[j]);
+        }
+        const double gnorm = nrm(wa1);
+        double paru = gnorm / delta;
+        if (paru == 0.0) paru = LM_DWARF / fmin(delta, p1);
+        par = fmax(par, parl);
+        par = fmin(par, paru);
+        if (par == 0.0) par = gnorm / dxnorm;
+        for (;;) {
+            ++iter;
+            if (par == 0.0) par = fmax(LM_DWARF, p001 * paru);
+            double temp = sqrt(par);
+#pragma unroll
+            for (int j = 0; j < N; ++j) wa1[j] = temp * diag[j];
+            qrsolv(wa1, x, sdiag);
+#pragma unroll
+            for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
+            dxnorm = nrm(wa2);
+            temp = fp;
+            fp = dxnorm - delta;
+            if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const int l = ipvt[j];
+                wa1[j] = sel(diag, l) * (sel(wa2, l) / dxnorm);
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                wa1[j] = wa1[j] / sdiag[j];
+                const double t = wa1[j];
+#pragma unroll
+                for (int i = j + 1; i < N; ++i) wa1[i] -= r[i][j] * t;
+            }
+            temp = nrm(wa1);
+            const double parc = ((fp / delta) / temp) / temp;
+            if (fp > 0.0) parl = fmax(parl, par);
+            if (fp < 0.0) paru = fmin(paru, par);
+            par = fmax(parl, par + parc);
+        }
+    }
+};
+
 // per-lane workspace of the n x n sub-problem: r (n x n, column major), six n-vectors, ipvt
 constexpr int LANE_BLOCK_ROWS = 8;
 // r, six vectors, ipvt (one int per float64 slot), and the staged row block of the Jacobian pass
@@ -409,17 +616,45 @@ struct LaneLM {
     }
 
     PFX_HD void trial_begin(const LaneWs& s) {
-        lmpar_seq(N, N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.sdiag, s.wa1, s.wa2);
-        for (int j = 0; j < N; ++j) s.wa1[j] = 0.0;
-        for (int j = 0; j < N; ++j) {
-            double temp = -s.step[s.ipvt[j]];
-            for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + N * j] * temp;
+        double stepv[N];
+        if (N <= 4) {
+            // load the sub-problem into registers, solve there
+            SmallLM<N> q;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) q.r[i][j] = (i <= j) ? s.r[i + N * j] : 0.0;
+                q.ipvt[j] = s.ipvt[j];
+                q.diag[j] = diag[j];
+                q.qtb[j] = s.qtf[j];
+            }
+            double sd[N];
+            q.lmpar(delta, par, stepv, sd);
+            double w3[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) w3[j] = 0.0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double temp = -SmallLM<N>::sel(stepv, q.ipvt[j]);
+#pragma unroll
+                for (int i = 0; i <= j; ++i) w3[i] += q.r[i][j] * temp;
+            }
+            rpnorm = SmallLM<N>::nrm(w3);
+        } else {
+            lmpar_seq(N, N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.sdiag, s.wa1, s.wa2);
+            for (int j = 0; j < N; ++j) s.wa1[j] = 0.0;
+            for (int j = 0; j < N; ++j) {
+                double temp = -s.step[s.ipvt[j]];
+                for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + N * j] * temp;
+            }
+            rpnorm = enorm_seq(N, s.wa1);
+#pragma unroll
+            for (int j = 0; j < N; ++j) stepv[j] = s.step[j];
         }
-        rpnorm = enorm_seq(N, s.wa1);
         double sq = 0.0;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            double p = -s.step[j];
+            double p = -stepv[j];
             xnew[j] = x[j] + p;
             double t = diag[j] * p;
             sq += t * t;
