@@ -50,6 +50,129 @@ __device__ __forceinline__ void lyon_u8_row(const Group<LYON_W>& g, const uint4*
     }
 }
 
+// ---- fast path: uint8 rows held in registers ---------------------------------------------
+// PV / DV = 16-byte vectors per lane for the profile / DM row (row length = 128 * PV resp.
+// 128 * DV bytes with 8 lanes per candidate).  All loads of a candidate are issued up front,
+// the raw first and second moments are exact integer dot products (dp4a), the third and fourth
+// central sums run on D = n*x - S1 held exactly in a double, and the eight statistics are
+// finished by all eight lanes at once (lanes 0-3 own the profile, 4-7 the DM row; lane k writes
+// statistic k & 3), so a warp writes 4 x 64 contiguous bytes.
+//
+// kbias = 2^31 - S1 (mod 2^32): n*x + kbias is D = n*x - S1 with the sign bit flipped, which is
+// the low word of the double 2^52 + 2^31 + D; subtracting the magic constant leaves D exactly
+// (no int->double conversion instruction, no rounding of the mean).
+__device__ __forceinline__ void lyon_accum(unsigned w, unsigned n, unsigned kbias, double& s3, double& s4) {
+    const double magic = 4503601774854144.0;   // 2^52 + 2^31
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const unsigned x = __byte_perm(w, 0, 0x4440 + b);
+        const double d = __hiloint2double(0x43300000, (int)(n * x + kbias)) - magic;
+        const double d2 = d * d;
+        s3 = fma(d2, d, s3);
+        s4 = fma(d2, d2, s4);
+    }
+}
+
+// butterflies over the 8 lanes of a candidate with the full-warp mask: all 32 lanes run the same
+// code (the loop below is warp uniform), and a compile-time mask spares the collective
+// synchronisation the compiler wraps around shuffles with a run-time mask
+__device__ __forceinline__ int bfly8(int v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+__device__ __forceinline__ double bfly8(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+template <int PV, int DV>
+__global__ void __launch_bounds__(LYON_THREADS)
+k_lyon8_u8(const uint4* __restrict__ profile, const uint4* __restrict__ dmstat, long long n, double* feat,
+           long long ld) {
+    const int lane = threadIdx.x & (LYON_W - 1);
+    const long long gpb = LYON_THREADS / LYON_W;
+    const long long stride = (long long)gridDim.x * gpb;
+    constexpr unsigned NP = 128 * PV, ND = 128 * DV;
+    // warp-uniform loop: the four candidates of a warp are consecutive; candidates past the end
+    // are clamped for the loads and masked for the store
+    for (long long c0 = (long long)blockIdx.x * gpb + (threadIdx.x / 32) * 4; c0 < n; c0 += stride) {
+        const long long cw = c0 + ((threadIdx.x & 31) / LYON_W);
+        const bool live = cw < n;
+        const long long c = live ? cw : n - 1;
+        uint4 vp[PV], vd[DV];
+#pragma unroll
+        for (int k = 0; k < PV; ++k) vp[k] = __ldcs(profile + c * (8 * PV) + k * 8 + lane);
+#pragma unroll
+        for (int k = 0; k < DV; ++k) vd[k] = __ldcs(dmstat + c * (8 * DV) + k * 8 + lane);
+        unsigned a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+        for (int k = 0; k < PV; ++k) {
+            const unsigned w[4] = {vp[k].x, vp[k].y, vp[k].z, vp[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a1 = __dp4a(w[j], 0x01010101u, a1);
+                a2 = __dp4a(w[j], w[j], a2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DV; ++k) {
+            const unsigned w[4] = {vd[k].x, vd[k].y, vd[k].z, vd[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                b1 = __dp4a(w[j], 0x01010101u, b1);
+                b2 = __dp4a(w[j], w[j], b2);
+            }
+        }
+        const int ps1 = bfly8((int)a1), ps2 = bfly8((int)a2);
+        const int ds1 = bfly8((int)b1), ds2 = bfly8((int)b2);
+        double p3 = 0.0, p4 = 0.0, d3 = 0.0, d4 = 0.0;
+        const unsigned pk = 0x80000000u - (unsigned)ps1, dk = 0x80000000u - (unsigned)ds1;
+#pragma unroll
+        for (int k = 0; k < PV; ++k) {
+            lyon_accum(vp[k].x, NP, pk, p3, p4);
+            lyon_accum(vp[k].y, NP, pk, p3, p4);
+            lyon_accum(vp[k].z, NP, pk, p3, p4);
+            lyon_accum(vp[k].w, NP, pk, p3, p4);
+        }
+#pragma unroll
+        for (int k = 0; k < DV; ++k) {
+            lyon_accum(vd[k].x, ND, dk, d3, d4);
+            lyon_accum(vd[k].y, ND, dk, d3, d4);
+            lyon_accum(vd[k].z, ND, dk, d3, d4);
+            lyon_accum(vd[k].w, ND, dk, d3, d4);
+        }
+        p3 = bfly8(p3);
+        p4 = bfly8(p4);
+        d3 = bfly8(d3);
+        d4 = bfly8(d4);
+        // lanes 0-3: profile, lanes 4-7: DM row; row lengths are powers of two here, so scaling by
+        // 1/n^k is exact
+        const bool isd = (lane & 4) != 0;
+        const double in = isd ? 1.0 / (double)ND : 1.0 / (double)NP;
+        const long long S1 = isd ? ds1 : ps1, S2 = isd ? ds2 : ps2;
+        const double c3 = isd ? d3 : p3, c4 = isd ? d4 : p4;
+        const long long nint = isd ? ND : NP;
+        const double in2 = in * in;
+        const double mean = (double)S1 * in;
+        const double m2 = (double)(nint * S2 - S1 * S1) * in2;      // exact integer numerator
+        const double m3 = c3 * (in2 * in2);                          // sum(D^3) / n^3 / n
+        const double m4 = c4 * (in2 * in2 * in);                     // sum(D^4) / n^4 / n
+        const double sd = sqrt(m2);
+        const double thr = (LM_EPSMCH * mean) * (LM_EPSMCH * mean);
+        const bool degenerate = m2 <= thr;
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        const double skew = degenerate ? qnan : m3 / (m2 * sd);
+        const double kurt = degenerate ? qnan : m4 / (m2 * m2) - 3.0;
+        const int k = lane & 3;
+        const double v = (k == 0) ? mean : (k == 1) ? sd : (k == 2) ? skew : kurt;
+        if (live) __stcs(feat + c * ld + lane, v);
+    }
+}
+
 __global__ void __launch_bounds__(LYON_THREADS)
 k_lyon8(const void* __restrict__ profile, int dtype, int nbin, const void* __restrict__ dmstat,
         int ds_dtype, int n_ds, long long n, double* feat, long long ld) {
@@ -86,8 +209,17 @@ int pfx::launch_lyon(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* pr
     const long long cap = (long long)ctx->sm_count * 32;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k_lyon8<<<(int)blocks, LYON_THREADS, 0, st>>>(profile, s->dtype, s->nbin, dmstat, s->dmstat_dtype,
-                                                   s->n_dmstat, n, feat, ld);
+    const bool u8 = s->dtype == PFX_U8 && s->dmstat_dtype == PFX_U8 &&
+                    ((uintptr_t)profile % 16 == 0) && ((uintptr_t)dmstat % 16 == 0);
+    if (u8 && s->nbin == 128 && s->n_dmstat == 256)
+        k_lyon8_u8<1, 2><<<(int)blocks, LYON_THREADS, 0, st>>>((const uint4*)profile, (const uint4*)dmstat, n, feat, ld);
+    else if (u8 && s->nbin == 128 && s->n_dmstat == 128)
+        k_lyon8_u8<1, 1><<<(int)blocks, LYON_THREADS, 0, st>>>((const uint4*)profile, (const uint4*)dmstat, n, feat, ld);
+    else if (u8 && s->nbin == 256 && s->n_dmstat == 256)
+        k_lyon8_u8<2, 2><<<(int)blocks, LYON_THREADS, 0, st>>>((const uint4*)profile, (const uint4*)dmstat, n, feat, ld);
+    else
+        k_lyon8<<<(int)blocks, LYON_THREADS, 0, st>>>(profile, s->dtype, s->nbin, dmstat, s->dmstat_dtype,
+                                                       s->n_dmstat, n, feat, ld);
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }
