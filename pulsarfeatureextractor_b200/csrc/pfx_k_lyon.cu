@@ -131,6 +131,25 @@ k_lyon8_u8(const uint4* __restrict__ profile, const uint4* __restrict__ dmstat, 
         const int ds1 = bfly8((int)b1), ds2 = bfly8((int)b2);
         double p3 = 0.0, p4 = 0.0, d3 = 0.0, d4 = 0.0;
         const unsigned pk = 0x80000000u - (unsigned)ps1, dk = 0x80000000u - (unsigned)ds1;
+#if defined(PFX_LYON_SPLIT)
+        // two independent accumulator pairs per row (shorter dependency chains)
+        double p3b = 0.0, p4b = 0.0, d3b = 0.0, d4b = 0.0;
+#pragma unroll
+        for (int k = 0; k < PV; ++k) {
+            lyon_accum(vp[k].x, NP, pk, p3, p4);
+            lyon_accum(vp[k].y, NP, pk, p3b, p4b);
+            lyon_accum(vp[k].z, NP, pk, p3, p4);
+            lyon_accum(vp[k].w, NP, pk, p3b, p4b);
+        }
+#pragma unroll
+        for (int k = 0; k < DV; ++k) {
+            lyon_accum(vd[k].x, ND, dk, d3, d4);
+            lyon_accum(vd[k].y, ND, dk, d3b, d4b);
+            lyon_accum(vd[k].z, ND, dk, d3, d4);
+            lyon_accum(vd[k].w, ND, dk, d3b, d4b);
+        }
+        p3 += p3b; p4 += p4b; d3 += d3b; d4 += d4b;
+#else
 #pragma unroll
         for (int k = 0; k < PV; ++k) {
             lyon_accum(vp[k].x, NP, pk, p3, p4);
@@ -145,6 +164,7 @@ k_lyon8_u8(const uint4* __restrict__ profile, const uint4* __restrict__ dmstat, 
             lyon_accum(vd[k].z, ND, dk, d3, d4);
             lyon_accum(vd[k].w, ND, dk, d3, d4);
         }
+#endif
         p3 = bfly8(p3);
         p4 = bfly8(p4);
         d3 = bfly8(d3);

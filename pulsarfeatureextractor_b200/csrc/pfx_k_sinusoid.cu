@@ -1,36 +1,56 @@
-// pfx_k_sinusoid.cu -- scores 1-4 (ProfileOperations.py:190-587), one warp per candidate.
+// pfx_k_sinusoid.cu -- scores 1-4 (ProfileOperations.py:190-587): profile statistics, peak count and
+// the sine / sine-squared fits, one lane per candidate (state machine of pfx_lane_misc.cuh).
 #include "pfx_internal.cuh"
+#include "pfx_lane_misc.cuh"
 
 using namespace pfx;
 
 namespace {
-// ---- scores 1-4 ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK_THREADS, 4)
-k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, double* feat,
-           long long ld, int8_t* ier, u64* counter, int work_doubles) {
+
+__global__ void __launch_bounds__(128, 3)
+k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
+           int8_t* ier, u64* counter) {
     extern __shared__ double smem[];
-    Group<WARP> g;
-    double* ws = smem + (threadIdx.x / WARP) * work_doubles;
+    LaneWs ws;
+    ws.carve(smem + threadIdx.x, blockDim.x, 2);
+    SinLane g;
+    g.phase = GP_IDLE;
+    g.cand = -1;
+    bool more = true;
     for (;;) {
-        const long long c = next_candidate(g, counter);
-        if (c >= n) break;
-        sinusoid_candidate(g, ws, profile, dtype, c, m, feat + c * ld, ier ? ier + c * PFX_NIER : nullptr);
+        if (g.phase == GP_IDLE) {
+            if (g.cand >= 0) {
+                g.write(feat + g.cand * ld);
+                if (ier) {
+                    ier[g.cand * PFX_NIER + PFX_FIT_SINE] = g.ier[0];
+                    ier[g.cand * PFX_NIER + PFX_FIT_SINESQ] = g.ier[1];
+                }
+                g.cand = -1;
+            }
+            if (more) {
+                const long long c = (long long)atomicAdd(counter, 1ULL);
+                if (c < n) g.start(profile, dtype, c, m);
+                else more = false;
+            }
+        }
+        if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
+        g.step(ws);
     }
 }
 
 }  // namespace
 
 int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                           int64_t ld, int8_t* ier, cudaStream_t st, int ck) {
+                         int64_t ld, int8_t* ier, cudaStream_t st, int ck) {
     if (s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin < 2");
-    const int wd = sin_work_doubles(s->nbin);
-    const size_t smem = (size_t)wd * 8 * GROUPS_PER_BLOCK;
+    const int threads = 128;
+    const size_t smem = (size_t)lane_ws_doubles(2) * 8 * threads;
     int grid;
-    int rc = persistent_grid(ctx, k_sinusoid, BLOCK_THREADS, smem, &grid);
+    int rc = persistent_grid(ctx, k_sinusoid, threads, smem, &grid);
     if (rc) return rc;
-    k_sinusoid<<<grid, BLOCK_THREADS, smem, st>>>(profile, s->dtype, n, s->nbin, feat, ld, ier,
-                                                   take_counter(ctx, ck, st), wd);
+    if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
+    k_sinusoid<<<grid, threads, smem, st>>>(profile, s->dtype, n, s->nbin, feat, ld, ier,
+                                             take_counter(ctx, ck, st));
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }
-

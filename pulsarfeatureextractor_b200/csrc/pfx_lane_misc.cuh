@@ -1,0 +1,394 @@
+// pfx_lane_misc.cuh -- one lane per candidate for scores 1-4 (two sinusoid fits) and scores 12-19
+// (DM-curve fit).  Same execution model as pfx_lane_gauss.cuh: a per-lane state machine whose trip
+// is "one Jacobian pass + one trial point"; the data row of a candidate is read straight from the
+// input arrays (a lane walks its own row, which stays in L1), only the small trust-region
+// workspace lives in shared memory.
+#pragma once
+
+#include "pfx_driver.cuh"
+#include "pfx_lane_gauss.cuh"
+
+namespace pfx {
+
+// =============================================================================================
+// scores 1-4                                                                   PO:190-587
+// =============================================================================================
+struct SinLane {
+    const void* profile;
+    int dtype;
+    long long cand;
+    int m, phase, stage, maxima;
+    double half, s4, chi[2];
+    LaneLM<2> lm;
+    int8_t ier[2];
+
+    PFX_HD double y(int i) const { return load_elem(profile, dtype, cand * (long long)m + i); }
+
+    PFX_HD void start(const void* prof, int dt, long long c, int m_) {
+        profile = prof;
+        dtype = dt;
+        cand = c;
+        m = m_;
+        stage = 0;
+        phase = GP_SETUP;
+        ier[0] = ier[1] = 0;
+    }
+
+    PFX_HD void setup() {
+        if (stage == 0) {
+            double s = 0.0, vmax = -INFINITY, vmin = INFINITY;
+            for (int i = 0; i < m; ++i) {
+                const double v = y(i);
+                s += v;
+                vmax = fmax(vmax, v);
+                vmin = fmin(vmin, v);
+            }
+            const double mean = s / (double)m;
+            double q = 0.0;
+            for (int i = 0; i < m; ++i) {
+                const double d = y(i) - mean;
+                q = PFX_FMA(d, d, q);
+            }
+            const double sd = sqrt(q / (double)m);
+            half = fabs(vmax - vmin) / 2.0;
+            double acc = 0.0;
+            for (int i = 0; i < m; ++i) acc += half - y(i);        // score 4, PO:246-247
+            s4 = acc;
+            // block scan of PO:294-326 (see count_peaks in pfx_scores.cuh)
+            int peaks = 0, zeros = 0;
+            bool nonzero = false;
+            for (int i = 0; i < m; ++i) {
+                double v = (y(i) - mean) - sd;
+                if (v < 0.0) v = 0.0;
+                if (v != 0.0) nonzero = true;
+                else if (zeros < 4) ++zeros;
+                else {
+                    if (nonzero) ++peaks;
+                    nonzero = false;
+                    zeros = 0;
+                }
+            }
+            if (nonzero) ++peaks;
+            maxima = peaks;
+        }
+        double x0[2];
+        const double y0 = y(0);
+        if (stage == 0) {
+            const double freq = (double)maxima / ((double)m - 1.0);
+            double phi0;
+            if (y0 == half) phi0 = 0.0;
+            else if (y0 < half) phi0 = (freq != 0.0) ? -1.0 / (4.0 * freq) : -1.0 / (4.0 * 0.00000000001);
+            else phi0 = (freq != 0.0) ? 1.0 / (4.0 * freq) : 1.0 / (4.0 * 0.00000000001);
+            x0[0] = freq;
+            x0[1] = phi0;
+        } else {
+            const double freq = (double)maxima / ((double)m - 1.0) / 2.0;
+            double phi0;
+            if (y0 == 0.0) phi0 = 0.0;
+            else phi0 = (freq != 0.0) ? -1.0 / (4.0 * freq) : -1.0 / (4.0 * 0.00000000001);
+            x0[0] = freq;
+            x0[1] = phi0;
+        }
+        lm.init(x0);
+        phase = GP_JAC;
+    }
+
+    // residual of row i: stage 0  y - (A sin t + bg)      (PO:418)
+    //                    stage 1  (y - A sin^2 t) + bg    (PO:522; the +bg sits outside the bracket)
+    PFX_HD double resid(double w, double phi, int i, double yv) const {
+        const double sn = sin(PFX_ADD(PFX_MUL(w, (double)i), phi));
+        if (stage == 0) return PFX_SUB(yv, PFX_ADD(PFX_MUL(half, sn), half));
+        return PFX_ADD(PFX_SUB(yv, PFX_MUL(half, PFX_MUL(sn, sn))), half);
+    }
+
+    PFX_HD void jac_pass(const LaneWs& ws) {
+        lm.jac_begin();
+        const double w0 = PFX_MUL(TWO_PI, lm.x[0]), w1 = PFX_MUL(TWO_PI, lm.x[0] + lm.h[0]);
+        const double p0 = lm.x[1], p1 = lm.x[1] + lm.h[1];
+        const double ih0 = 1.0 / lm.h[0], ih1 = 1.0 / lm.h[1];
+        constexpr int B = LANE_BLOCK_ROWS;
+        for (int i0 = 0; i0 < m; i0 += B) {
+            const int rows = (m - i0 < B) ? m - i0 : B;
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
+                const int i = i0 + r;
+                const double yv = y(i);
+                const double f0 = resid(w0, p0, i, yv);
+                const double a0 = (resid(w1, p0, i, yv) - f0) * ih0;
+                const double a1 = (resid(w0, p1, i, yv) - f0) * ih1;
+                lm.acn2[0] = PFX_FMA(a0, a0, lm.acn2[0]);
+                lm.acn2[1] = PFX_FMA(a1, a1, lm.acn2[1]);
+                lm.f2 = PFX_FMA(f0, f0, lm.f2);
+                ws.blk[r * 3 + 0] = a0;
+                ws.blk[r * 3 + 1] = a1;
+                ws.blk[r * 3 + 2] = f0;
+            }
+            lm.jac_block_staged<B>(ws.blk, rows);
+        }
+        const int r = lm.jac_end(ws, m);
+        phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+    }
+
+    PFX_HD void trial_pass(const LaneWs& ws) {
+        lm.trial_begin(ws);
+        const double w = PFX_MUL(TWO_PI, lm.xnew[0]), ph = lm.xnew[1];
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double f = resid(w, ph, i, y(i));
+            s = PFX_FMA(f, f, s);
+        }
+        const int r = lm.trial_end(sqrt(s));
+        phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+    }
+
+    PFX_HD void finish() {
+        ier[stage] = (int8_t)lm.info;
+        // chi-square against the evaluated curve A sin(..) + bg resp. A sin^2(..) + bg (PO:425,529)
+        const double w = PFX_MUL(TWO_PI, lm.x[0]), ph = lm.x[1];
+        double c = 0.0;
+        for (int i = 0; i < m; ++i) {
+            const double sn = sin(PFX_ADD(PFX_MUL(w, (double)i), ph));
+            const double fit = (stage == 0) ? PFX_ADD(PFX_MUL(half, sn), half)
+                                            : PFX_ADD(PFX_MUL(half, PFX_MUL(sn, sn)), half);
+            const double d = y(i) - fit;
+            c = PFX_FMA(d, d, c);
+        }
+        chi[stage] = c / (double)m;
+        ++stage;
+        phase = (stage > 1) ? GP_IDLE : GP_SETUP;
+    }
+
+    PFX_HD void step(const LaneWs& ws) {
+        if (phase == GP_SETUP) setup();
+        if (phase == GP_JAC) jac_pass(ws);
+        if (phase == GP_TRIAL) trial_pass(ws);
+        if (phase == GP_FIN) finish();
+    }
+
+    PFX_HD void write(double* feat) const {
+        feat[0] = chi[0] / (double)maxima;      // maxima == 0 -> inf / nan as numpy (PO:373-374)
+        feat[1] = chi[1] / (double)maxima;
+        feat[2] = (double)(maxima > 0 ? maxima - 1 : 0);
+        feat[3] = s4;
+    }
+};
+
+// =============================================================================================
+// scores 12-19                                              PHXO:81-233, PFDO:274-393, CFI:84-112
+// =============================================================================================
+template <int N>    // 3: PHCX family, 4: PFD family
+struct DmLane {
+    const void* dmcurve;
+    int dm_dtype;
+    long long cand;
+    int n_dm, phase;
+    bool pfd;
+    double snr, dm, period, width, dm_start, dm_step, wint, df, f3, amp0, yscale;
+    double s16, s17, s18, s19;
+    unsigned status;
+    LaneLM<N> lm;
+    int8_t ier;
+
+    PFX_HD double xval(int i) const {
+        const double xi = pfd ? (double)i : (double)(128 * i - 1);      // PHXO:251-257
+        return PFX_ADD(dm_start, PFX_MUL(xi, dm_step));
+    }
+    PFX_HD double yval(int i) const {
+        if (pfd && dm_dtype == PFX_F32)   // float32 arithmetic of PFDO:332 on the float32 curve
+            return (double)((float)yscale * ((const float*)dmcurve)[cand * (long long)n_dm + i]);
+        const double v = load_elem(dmcurve, dm_dtype, cand * (long long)n_dm + i);
+        return pfd ? yscale * v : v;
+    }
+    // sqrt((P - weff)/weff), weff = sqrt(wint + (prop kdm |dm + shift - x| df / f^3)^2)
+    PFX_HD double shape(double prop, double shift, double xv) const {
+        const double a = fabs(PFX_SUB(PFX_ADD(dm, shift), xv));
+        const double q = PFX_DIV(PFX_MUL(PFX_MUL(PFX_MUL(prop, 8300000.0), a), df), f3);
+        double weff = sqrt(PFX_ADD(wint, PFX_MUL(q, q)));
+        if (pfd && weff > period) weff = period;
+        return sqrt(PFX_DIV(PFX_SUB(period, weff), weff));
+    }
+    PFX_HD double theo_shape(double xv) const {
+        const double q = PFX_DIV(PFX_MUL(PFX_MUL(8300000.0, fabs(PFX_SUB(dm, xv))), df), f3);
+        double weff = sqrt(PFX_ADD(wint, PFX_MUL(q, q)));
+        if (pfd && weff > period) weff = period;
+        return sqrt(PFX_DIV(PFX_SUB(period, weff), weff));
+    }
+
+    PFX_HD void start(const void* curve, int dt, long long c, int n, int family, const double* prm) {
+        dmcurve = curve;
+        dm_dtype = dt;
+        cand = c;
+        n_dm = n;
+        pfd = (family == PFX_FAMILY_PFD);
+        snr = prm[0];
+        dm = prm[1];
+        period = prm[2] * 1000.0;
+        width = prm[3];
+        dm_start = prm[4];
+        double length_all = prm[6];
+        if (!(length_all > 0.0)) length_all = pfd ? (double)n : 128.0 * (double)n;
+        dm_step = fabs(prm[4] - prm[5]) / length_all;
+        wint = (width * period) * (width * period);
+        df = pfd ? 32.0 : 400.0;
+        f3 = pfd ? 2460375.0 : 2593941624.0;
+        status = 0;
+        ier = 0;
+        phase = GP_SETUP;
+    }
+
+    PFX_HD void setup() {
+        const double sw = sqrt(wint);
+        s16 = snr / sqrt((period - sw) / sw);
+        yscale = 1.0;
+        if (pfd) {
+            // yData = 255./max(yData)*yData  (PFDO:332), builtin max
+            if (dm_dtype == PFX_F32) {
+                const float* p = (const float*)dmcurve + cand * (long long)n_dm;
+                float mx = p[0];
+                for (int i = 1; i < n_dm; ++i)
+                    if (p[i] > mx) mx = p[i];
+                yscale = (double)(255.0f / mx);
+            } else {
+                double mx = load_elem(dmcurve, dm_dtype, cand * (long long)n_dm);
+                for (int i = 1; i < n_dm; ++i) {
+                    const double v = load_elem(dmcurve, dm_dtype, cand * (long long)n_dm + i);
+                    if (v > mx) mx = v;
+                }
+                yscale = 255.0 / mx;
+            }
+        }
+        // max(_help) with Python's builtin max: a NaN survives only when it is first
+        double hmax = theo_shape(xval(0));
+        for (int i = 1; i < n_dm; ++i) {
+            const double h = theo_shape(xval(i));
+            if (h > hmax) hmax = h;
+        }
+        amp0 = 255.0 / hmax;
+        double x0[N];
+        x0[0] = amp0;
+        x0[1] = 1.0;
+        x0[2] = 0.0;
+        if (N == 4) x0[N - 1] = 0.0;
+        lm.init(x0);
+        phase = GP_JAC;
+    }
+
+    PFX_HD void jac_pass(const LaneWs& ws) {
+        lm.jac_begin();
+        const double* x = lm.x;
+        const double* h = lm.h;
+        double ih[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) ih[k] = 1.0 / h[k];
+        const double up = (N == 4) ? x[N - 1] : 0.0;
+        constexpr int B = LANE_BLOCK_ROWS;
+        for (int i0 = 0; i0 < n_dm; i0 += B) {
+            const int rows = (n_dm - i0 < B) ? n_dm - i0 : B;
+#pragma unroll 1
+            for (int r = 0; r < rows; ++r) {
+                const int i = i0 + r;
+                const double xv = xval(i), yv = yval(i);
+                const double s0 = shape(x[1], x[2], xv);
+                const double s1 = shape(x[1] + h[1], x[2], xv);
+                const double s2 = shape(x[1], x[2] + h[2], xv);
+                double a[N], f0;
+                if (N == 3) {
+                    f0 = PFX_SUB(yv, PFX_MUL(x[0], s0));
+                    a[0] = (PFX_SUB(yv, PFX_MUL(x[0] + h[0], s0)) - f0) * ih[0];
+                    a[1] = (PFX_SUB(yv, PFX_MUL(x[0], s1)) - f0) * ih[1];
+                    a[2] = (PFX_SUB(yv, PFX_MUL(x[0], s2)) - f0) * ih[2];
+                } else {
+                    f0 = PFX_SUB(yv, PFX_ADD(up, PFX_MUL(x[0], s0)));
+                    a[0] = (PFX_SUB(yv, PFX_ADD(up, PFX_MUL(x[0] + h[0], s0))) - f0) * ih[0];
+                    a[1] = (PFX_SUB(yv, PFX_ADD(up, PFX_MUL(x[0], s1))) - f0) * ih[1];
+                    a[2] = (PFX_SUB(yv, PFX_ADD(up, PFX_MUL(x[0], s2))) - f0) * ih[2];
+                    a[N - 1] = (PFX_SUB(yv, PFX_ADD(up + h[N - 1], PFX_MUL(x[0], s0))) - f0) * ih[N - 1];
+                }
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    lm.acn2[k] = PFX_FMA(a[k], a[k], lm.acn2[k]);
+                    ws.blk[r * (N + 1) + k] = a[k];
+                }
+                lm.f2 = PFX_FMA(f0, f0, lm.f2);
+                ws.blk[r * (N + 1) + N] = f0;
+            }
+            lm.template jac_block_staged<B>(ws.blk, rows);
+        }
+        const int r = lm.jac_end(ws, n_dm);
+        phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+    }
+
+    PFX_HD double model(const double* p, double xv) const {
+        const double v = PFX_MUL(p[0], shape(p[1], p[2], xv));
+        return (N == 4) ? PFX_ADD(p[N - 1], v) : v;
+    }
+
+    PFX_HD void trial_pass(const LaneWs& ws) {
+        lm.trial_begin(ws);
+        double s = 0.0;
+        for (int i = 0; i < n_dm; ++i) {
+            const double f = PFX_SUB(yval(i), model(lm.xnew, xval(i)));
+            s = PFX_FMA(f, f, s);
+        }
+        const int r = lm.trial_end(sqrt(s));
+        phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+    }
+
+    PFX_HD void finish() {
+        ier = (int8_t)lm.info;
+        s17 = fabs(1.0 - lm.x[1]);
+        s18 = fabs(lm.x[2]);                          // filterScore(18, .), CFI:110
+        if (!pfd) {
+            // PHXO:222-230: chi-square of the THEORETICAL curve where the FIT is >= 1
+            double c = 0.0;
+            for (int i = 0; i < n_dm; ++i) {
+                const double xv = xval(i);
+                if (model(lm.x, xv) >= 1.0) {
+                    const double d = yval(i) - PFX_MUL(amp0, theo_shape(xv));
+                    c = PFX_FMA(d, d, c);
+                }
+            }
+            s19 = c / (double)n_dm;
+        } else {
+            double c = 0.0;
+            int ndeg = 0;
+            for (int i = 0; i < n_dm; ++i) {
+                const double th = PFX_MUL(amp0, theo_shape(xval(i)));
+                if (th > 0.0) {
+                    const double d = yval(i) - th;
+                    c += (d * d) / th;
+                    ++ndeg;
+                }
+            }
+            if (ndeg == 0) {
+                status |= PFX_ST_DM_NDEG_ZERO;      // ZeroDivisionError, PFDO:385
+                s19 = NAN;
+            } else {
+                s19 = c / (double)ndeg;
+            }
+        }
+        phase = GP_IDLE;
+    }
+
+    PFX_HD void step(const LaneWs& ws) {
+        if (phase == GP_SETUP) setup();
+        if (phase == GP_JAC) jac_pass(ws);
+        if (phase == GP_TRIAL) trial_pass(ws);
+        if (phase == GP_FIN) finish();
+    }
+
+    PFX_HD void write(double* feat) const {
+        feat[11] = period;
+        feat[12] = filter_13_14(snr);
+        feat[13] = filter_13_14(dm);
+        feat[14] = width;
+        if (!(status & PFX_ST_FAIL_MASK)) {
+            feat[15] = s16;
+            feat[16] = s17;
+            feat[17] = s18;
+            feat[18] = s19;
+        }
+    }
+};
+
+}  // namespace pfx

@@ -203,3 +203,39 @@ extern "C" unsigned hs_hist(const void* profile, int dtype, int m, int cap_smem,
     return hist_candidate(g, ws.data(), cap_smem, cap_global > 0 ? gs.data() : nullptr, cap_global,
                           profile, dtype, 0, m, pow_m, pow_m1, feat, ier, ph_expect);
 }
+
+// ---- lane-per-candidate scores 1-4 and 12-19 (pfx_lane_misc.cuh) ---------------------------------
+#include "../../pulsarfeatureextractor_b200/csrc/pfx_lane_misc.cuh"
+extern "C" int hs_sin_lane(const void* profile, int dtype, int m, double* feat, int8_t* ier) {
+    std::vector<double> wsbuf(lane_ws_doubles(4) + 8);
+    LaneWs ws;
+    ws.carve(wsbuf.data(), 1, 2);
+    SinLane g;
+    g.start(profile, dtype, 0, m);
+    while (g.phase != GP_IDLE) g.step(ws);
+    g.write(feat);
+    ier[PFX_FIT_SINE] = g.ier[0];
+    ier[PFX_FIT_SINESQ] = g.ier[1];
+    return 0;
+}
+extern "C" unsigned hs_dm_lane(const void* dmcurve, int dm_dtype, int n_dm, int family, const double* prm,
+                               double* feat, int8_t* ier) {
+    std::vector<double> wsbuf(lane_ws_doubles(4) + 8);
+    LaneWs ws;
+    if (family == PFX_FAMILY_PFD) {
+        ws.carve(wsbuf.data(), 1, 4);
+        DmLane<4> g;
+        g.start(dmcurve, dm_dtype, 0, n_dm, family, prm);
+        while (g.phase != GP_IDLE) g.step(ws);
+        g.write(feat);
+        ier[PFX_FIT_DM] = g.ier;
+        return g.status;
+    }
+    ws.carve(wsbuf.data(), 1, 3);
+    DmLane<3> g;
+    g.start(dmcurve, dm_dtype, 0, n_dm, family, prm);
+    while (g.phase != GP_IDLE) g.step(ws);
+    g.write(feat);
+    ier[PFX_FIT_DM] = g.ier;
+    return g.status;
+}
