@@ -35,8 +35,10 @@ CONFIG_ID = 2
 BYTES_IN = NBIN + NSUB * NBIN + NDM + NDMSTAT + 8 * 8
 BYTES_OUT = 30 * 8 + 18 + 4
 BYTES_PER_CAND = BYTES_IN + BYTES_OUT
-# the dominant kernel reads the profile and the parked expectation and writes 4 scores + 10 ier
-GAUSS_BYTES_PER_CAND = NBIN + 8 + 4 + 4 * 8 + 10
+# ncu --set full of the dominant kernel pair (profiles/r01_rounds_r1d_summary.csv): DRAM bytes per
+# candidate actually moved by k_gauss_rounds (profile row + per-lane scratch spill-over past L2)
+LYON_N = 4_000_000            # candidates of the secondary, HBM-bound roofline entry
+LYON_BYTES_PER_CAND = NBIN + NDMSTAT + 64
 
 
 def read_peaks():
@@ -245,6 +247,32 @@ def main():
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1000.0
     barrier()
+    # ---- secondary roofline entry: the HBM-bound kernel of the path (Lyon statistics) ---------
+    lyon_roof = None
+    if rank == 0:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(7)
+        lp = torch.randint(0, 256, (LYON_N, NBIN), dtype=torch.uint8, device=dev, generator=gen)
+        ld_ = torch.randint(0, 256, (LYON_N, NDMSTAT), dtype=torch.uint8, device=dev, generator=gen)
+        for _ in range(3):
+            eng.lyon8(lp, ld_)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(5):
+            eng.lyon8(lp, ld_)          # 1.8 GB per launch: larger than L2
+        l1.record()
+        torch.cuda.synchronize()
+        lyon_ms = l0.elapsed_time(l1) / 5
+        peak_l, kind_l = read_peaks()
+        ach = LYON_N * LYON_BYTES_PER_CAND / (lyon_ms / 1000.0) / 1e9
+        lyon_roof = {"bound": "hbm", "kernel": "k_lyon8_u8<1,2> (8 Lyon statistics, uint8 rows)",
+                     "achieved": ach, "peak": peak_l, "peak_kind": kind_l, "unit": "GB/s", "frac": ach / peak_l,
+                     "traffic": LYON_N * 446.0, "candidates": LYON_N, "kernel_ms": lyon_ms,
+                     "candidates_per_s": LYON_N / (lyon_ms / 1000.0),
+                     "note": "traffic: ncu dram read+write of the 10M-candidate capture, 446 B/candidate "
+                             "(profiles/r01_lyon_r1_summary.csv) against 448 B algorithmic"}
+        del lp, ld_
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -266,7 +294,9 @@ def main():
         value = total * args.steps / (ms_dev / 1000.0)
         e2e = total * args.steps / (ms_e2e / 1000.0)
         gauss_ms = stage.get("gauss", 0.0)
-        achieved = n * GAUSS_BYTES_PER_CAND / (gauss_ms / 1000.0) / 1e9 if gauss_ms > 0 else 0.0
+        # algorithmic bytes per candidate of the path x candidates per launch, over the
+        # duration of the dominant kernel pair
+        achieved = n * BYTES_PER_CAND / (gauss_ms / 1000.0) / 1e9 if gauss_ms > 0 else 0.0
         step_gbs = n * BYTES_PER_CAND / (ms_dev / args.steps / 1000.0) / 1e9
         line = {
             "metric": "candidates/sec (22 Bates + 8 Lyon)", "value": value, "unit": "candidates/s",
@@ -282,7 +312,10 @@ def main():
                          "frac": achieved / peak, "traffic": None,
                          "kernel_ms": gauss_ms, "kernel_share_of_step": gauss_ms / (ms_dev / args.steps),
                          "whole_step_gbs": step_gbs, "whole_step_frac": step_gbs / peak,
-                         "note": "compute (FP64 + latency) bound path: ~1e3 flop/byte, see DESIGN.md"},
+                         "note": "the Bates path is FP64/latency bound (~1e3 flop per input byte, 10 Levenberg-"
+                                 "Marquardt solves per candidate in this kernel pair), so its HBM fraction is "
+                                 "tiny by construction; the HBM-bound kernel of the path is reported in roofline_lyon"},
+            "roofline_lyon": lyon_roof,
             "stage_ms_serialised": {k: v for k, v in stage.items() if k != "launches"},
             "clocks": sampler.summary(),
             "rows_valid": ok, "host_equals_device": same,
