@@ -30,11 +30,12 @@ SO = os.path.join(HERE, "hostsim", "_hostsim.so")
 def hs():
     src = [os.path.join(HERE, "hostsim", "hostsim.cpp")] + \
           [os.path.join(HERE, "..", "pulsarfeatureextractor_b200", "csrc", f)
-           for f in ("pfx_group.cuh", "pfx_lm.cuh", "pfx_scores.cuh", "pfx_driver.cuh")]
+           for f in ("pfx_group.cuh", "pfx_lm.cuh", "pfx_scores.cuh", "pfx_driver.cuh", "pfx_lane_lm.cuh",
+                     "pfx_lane_gauss.cuh", "pfx_lane_misc.cuh")]
     if (not os.path.isfile(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
         subprocess.check_call(["sh", os.path.join(HERE, "hostsim", "build.sh")])
     lib = ctypes.CDLL(SO)
-    for f in ("hs_gaussian", "hs_dmfit", "hs_subband"):
+    for f in ("hs_gaussian", "hs_dmfit", "hs_subband", "hs_hist", "hs_gauss_lane", "hs_dm_lane"):
         getattr(lib, f).restype = ctypes.c_uint
     return lib
 
@@ -43,13 +44,24 @@ def P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def host_bates(lib, prof, sub, dmc, prm):
+def host_bates(lib, prof, sub, dmc, prm, lanes=True):
+    """The kernel logic on the host.  lanes=True follows the product kernels (lane-per-candidate
+    state machines for scores 1-4, 8-11, 12-19; warp-form routines for 5-7 and 20-22);
+    lanes=False runs the warp-form routines everywhere."""
     feat = np.full(22, np.nan)
     ier = np.zeros(18, np.int8)
     st = 0
-    lib.hs_sinusoid(P(prof), 0, prof.size, P(feat), P(ier))
-    st |= lib.hs_gaussian(P(prof), 0, prof.size, 192, 4096, P(feat), P(ier))
-    st |= lib.hs_dmfit(P(dmc), 0, dmc.size, 0, P(prm), P(feat), P(ier))
+    if lanes:
+        lib.hs_sin_lane(P(prof), 0, prof.size, P(feat), P(ier))
+        ph = ctypes.c_double(0.0)
+        st |= lib.hs_hist(P(prof), 0, prof.size, 192, 4096, P(feat), P(ier), ctypes.byref(ph))
+        if not (st & O.ST_FAIL_MASK):
+            st |= lib.hs_gauss_lane(P(prof), 0, prof.size, ph, P(feat), P(ier))
+        st |= lib.hs_dm_lane(P(dmc), 0, dmc.size, 0, P(prm), P(feat), P(ier))
+    else:
+        lib.hs_sinusoid(P(prof), 0, prof.size, P(feat), P(ier))
+        st |= lib.hs_gaussian(P(prof), 0, prof.size, 192, 4096, P(feat), P(ier))
+        st |= lib.hs_dmfit(P(dmc), 0, dmc.size, 0, P(prm), P(feat), P(ier))
     st |= lib.hs_subband(P(prof), P(sub), 0, prof.size, sub.shape[0], ctypes.c_double(prm[3]), P(feat))
     return feat, ier, st
 
@@ -109,6 +121,44 @@ def test_minpack_port_matches_scipy_on_identical_residuals(hs):
             same_nfev += int(info["nfev"] == nf)
     assert same_ier == total
     assert same_nfev >= 0.97 * total
+
+
+def test_lane_lm_streaming_qr_against_scipy(hs):
+    """The lane form (one lane per fit, Jacobian never stored, Householder blocks + MINPACK pivoting
+    on the n x n factor) with the same residual callbacks: same ier on >= 95 %, and on the
+    well-conditioned sine fits the same nfev every time."""
+    warnings.simplefilter("ignore")
+    rng = np.random.default_rng(9)
+    xx = np.arange(128)
+    tot = same = sine_same = sine_tot = 0
+    for t in range(40):
+        prof = rng.uniform(5, 50) * np.exp(-0.5 * ((xx - rng.uniform(0, 128)) / rng.uniform(1, 12)) ** 2) + rng.normal(0, 1, 128)
+        y = np.round((prof - prof.min()) / (prof.max() - prof.min()) * 255)
+        amp = (y.max() - y.min()) / 2
+        fits = [(lambda p: y - (amp * np.sin(2 * np.pi * p[0] * xx + p[1]) + amp), [2 / 127., -1 / (4 * 2 / 127.)]),
+                (lambda p: y - (abs(p[2]) * np.exp((-((xx - p[1]) / abs(p[0])) ** 2) / 2) + p[3]),
+                 [np.std(y), float(np.argmax(y)), y.max(), 1.0])]
+        for k, (res, p0) in enumerate(fits):
+            with np.errstate(all="ignore"):
+                xs, _c, info, _m, ier = leastsq(res, p0, full_output=True)
+            n = len(p0)
+            x = np.array(p0, dtype=np.float64)
+
+            def cb(pp, out, res=res, n=n):
+                p = np.ctypeslib.as_array(pp, (n,)).copy()
+                with np.errstate(all="ignore"):
+                    np.ctypeslib.as_array(out, (128,))[:] = res(p)
+
+            nfev = ctypes.c_int(0)
+            im = hs.hs_lanelm_cb(n, 128, x.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), CB(cb), ctypes.byref(nfev))
+            tot += 1
+            same += int(im == ier)
+            if k == 0:
+                sine_tot += 1
+                sine_same += int(nfev.value == info["nfev"])
+                assert np.allclose(x, xs, rtol=1e-6, atol=1e-9)
+    assert same >= 0.95 * tot
+    assert sine_same == sine_tot
 
 
 def test_nan_residuals_return_start_with_ier4(hs):
@@ -203,6 +253,22 @@ def test_fit_scores_on_the_oracle_noise_floor(scored):
     ier_host = np.mean([np.array_equal(ier[:16], r.ier[:16]) for r, tws, feat, ier in good])
     ier_twin = np.mean([np.array_equal(tws[0].ier[:16], r.ier[:16]) for r, tws, feat, ier in good])
     assert ier_host >= ier_twin - 0.10, (ier_host, ier_twin)
+
+
+def test_warp_form_routines_agree_with_lane_form(hs):
+    """Both mappings of the LM engine are the same algorithm: on well-conditioned (single pulse)
+    candidates they give the same scores to 1e-6."""
+    b = synth.generate(33, 0, 4096)
+    idx = np.nonzero(b.klass == synth.CLASS_PULSE)[0][:12]
+    agree = 0
+    for i in idx:
+        args = [np.ascontiguousarray(a[i]) for a in (b.profile, b.subbands, b.dmcurve, b.params)]
+        f1, _i1, s1 = host_bates(hs, *args, lanes=True)
+        f2, _i2, s2 = host_bates(hs, *args, lanes=False)
+        assert (s1 & O.ST_FAIL_MASK) == (s2 & O.ST_FAIL_MASK)
+        e = _rel(f1, f2)
+        agree += int(np.all(e[[0, 1, 8, 15, 18]] <= 1e-6))
+    assert agree >= len(idx) - 2
 
 
 def test_lyon_rows(hs):
