@@ -1012,6 +1012,41 @@ def bates22_pfd(profile, subbands, chi_curve, dms, bary_p1, bestdm, log=None):
     return res
 
 
+def bates22_pfd_arrays(profile, subbands, chi_curve, params, log=None):
+    """PFD-family scoring of already extracted arrays with the candidate scalars GIVEN in ``params``
+    (snr, dm, bary_period_s, width, dm_start, dm_end, ...), i.e. everything of PFD.compute()
+    (PFDFile.py:587-613) except the derivation of period/SNR/width from the profile
+    (PFDOperations.py:93-233, see cand_params_pfd).  This is what the engine's PFX_FAMILY_PFD path
+    computes: float64 profile and sub-bands, float32 chi-square curve, the 4-parameter DM model with
+    df = 32, f = 135 and the theo > 0 chi-square (PFDOperations.py:274-393)."""
+    res = Result(22)
+    log = log if log is not None else FitLog()
+    profile = np.asarray(profile, dtype=np.float64)
+    snr, dm, bary_p, width, dm_start, dm_end = [float(v) for v in params[:6]]
+    try:
+        res.features[0:4] = sinusoid_fittings(profile.copy(), log)
+        g, st = gaussian_fittings(profile.copy(), log)
+        res.features[4:11] = g
+        res.status |= st
+        res.features[11:15] = [bary_p * 1000, filter_score(13, snr), filter_score(14, dm), width]
+        n = len(chi_curve)
+        # trial DMs whose element 1 and last are dm_start / dm_end (PFDO:337)
+        dms = np.concatenate([[dm_start], np.linspace(dm_start, dm_end, n - 1)]) if n > 2 else np.array([dm_start, dm_end])
+        res.features[15:19] = dm_fittings_pfd(np.asarray(chi_curve), dms, snr, dm, bary_p * 1000, width, log)
+        nsub = len(subbands)
+        nbin = len(subbands[0])
+        s20, s21 = subband_scores(np.asarray(subbands), nbin, nsub, width)
+        s22 = profile_corr(np.asarray(subbands), nsub, profile)
+        res.features[19:22] = [s20, s21, s22]
+    except Exception as e:
+        res.status |= _exc_status(e)
+    res.ier = log.ier
+    res.nfev = log.nfev
+    res.cost = log.cost
+    res.params = log.params
+    return res
+
+
 # ==========================================================================================
 # Output rows                                                             DP:305-325,405-447
 # ==========================================================================================

@@ -228,6 +228,29 @@ def generate(config_id, start, count, nbin=128, nsub=16, n_dm=256, n_dmstat=256,
                  cat("params"), cat("klass"), cat("edge"))
 
 
+def generate_pfd_shaped(config_id, start, count, nbin=64, nsub=64, n_dm=256):
+    """PFD-shaped candidates (BASELINE configs[3]): float64 profile scaled to [0, 255]
+    (reference PFDFile.py:282-310), float64 sub-bands (not rescaled: profs.sum(0), PFDFile.py:442-456),
+    float32 reduced chi-square curve over n_dm trial DMs (PFDFile.py:393), params with
+    dm_start = first trial DM, dm_end = last, dm_len_all = n_dm."""
+    b = generate(config_id, start, count, nbin=nbin, nsub=nsub, n_dm=n_dm, n_dmstat=n_dm)
+    rng = np.random.Generator(np.random.Philox(key=[KEY_BASE + 7000 + config_id, start]))
+    n = len(b)
+    prof = b.profile.astype(np.float64) + rng.uniform(-0.4, 0.4, (n, nbin))
+    lo = prof.min(axis=1, keepdims=True)
+    hi = prof.max(axis=1, keepdims=True)
+    prof = np.where(hi > lo, (prof - lo) / np.where(hi > lo, hi - lo, 1) * 255.0, prof)
+    sub = b.subbands.astype(np.float64) * 0.37 + rng.normal(0, 0.2, (n, nsub, nbin)) + 1.25
+    const = b.edge == 9
+    sub[const] = 3.5
+    curve = (b.dmcurve.astype(np.float32) / np.float32(17.0) + np.float32(0.5) +
+             rng.uniform(0, 0.05, (n, n_dm)).astype(np.float32))
+    params = b.params.copy()
+    params[:, PARAM_DM_LEN_ALL] = n_dm
+    c = np.ascontiguousarray
+    return Batch(c(prof), c(sub), c(curve), b.dmstat, c(params), b.klass, b.edge)
+
+
 def to_pfd_family(batch, n_trials=None):
     """Re-express a uint8 batch as PFD-shaped arrays: float64 profile scaled to [0, 255]
     (reference PFDFile.py:282-310), float64 sub-bands, float32 chi-square curve

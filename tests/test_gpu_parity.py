@@ -193,6 +193,42 @@ def test_lyon_only_and_other_dtypes(eng):
             assert np.isnan(out[3, 2]) and np.isnan(out[3, 3])
 
 
+def test_pfd_family_shape(eng):
+    """BASELINE configs[3] shape: float64 64-bin profile, 64 x 64 float64 sub-bands, float32 256-trial
+    chi-square curve, PFD constants (4-parameter DM model, df = 32, f = 135, theo > 0 chi-square,
+    float32 curve scaling).  Candidate scalars are given in params."""
+    import torch
+    from pulsarfeatureextractor_b200 import _lib
+    warnings.simplefilter("ignore")
+    n = 96
+    b = synth.generate_pfd_shaped(4, 0, n)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = eng.score_device(t(b.profile), t(b.subbands), t(b.dmcurve), t(b.dmstat), t(b.params),
+                           features="all", family=_lib.PFX_FAMILY_PFD)
+    torch.cuda.synchronize()
+    feat, status = out.features.cpu().numpy(), out.status.cpu().numpy()
+    O.FAST_CORR = True
+    try:
+        nok = 0
+        for i in range(n):
+            r = O.bates22_pfd_arrays(b.profile[i], b.subbands[i], b.dmcurve[i], b.params[i])
+            assert ((r.status & O.ST_FAIL_MASK) != 0) == ((status[i] & O.ST_FAIL_MASK) != 0), (i, hex(r.status), hex(status[i]))
+            ly = O.lyon8(b.profile[i], b.dmstat[i])
+            assert _rel(ly, feat[i, 22:30]).max() <= 1e-9
+            if r.status & O.ST_FAIL_MASK:
+                continue
+            nok += 1
+            assert feat[i, 2] == r.features[2]
+            e = _rel(r.features, feat[i, :22])
+            for k in DET:
+                assert e[k] <= 1e-9, (i, k + 1, r.features[k], feat[i, k])
+            assert e[0] <= 1e-6, (i, "sine chi-square", r.features[0], feat[i, 0])
+        assert nok >= 20
+    finally:
+        O.FAST_CORR = False
+
+
 def test_large_batch_properties(eng):
     """BASELINE-size run (100 000 candidates): size-independent properties."""
     import torch
