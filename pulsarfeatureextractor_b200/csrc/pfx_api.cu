@@ -62,6 +62,10 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->lane_buf[i]) cudaFree(ctx->lane_buf[i]);
     for (int i = 0; i < 2; ++i) {
+        if (ctx->hist_lane_buf[i]) cudaFree(ctx->hist_lane_buf[i]);
+        if (ctx->ovf_list[i]) cudaFree(ctx->ovf_list[i]);
+    }
+    for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         cudaStreamDestroy(ctx->streams[i]);
         cudaStreamDestroy(ctx->side[i]);
@@ -228,7 +232,7 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
             PFX_CUDA(ctx, cudaEventRecord(ctx->join_ev[par], sd));
             PFX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join_ev[par], 0));
         }
-        launches += 6;
+        launches += 7;
     }
     ctx->last_launches = launches;
     if (timed) ctx->ev_valid = bates;

@@ -37,6 +37,10 @@ struct pfx_ctx {
     size_t carry_bytes;
     void* lane_buf[4];        // per-lane data vectors of the lane-per-candidate kernels
     size_t lane_bytes[4];
+    void* hist_lane_buf[2];   // per-lane arrays of k_hist_lane
+    size_t hist_lane_bytes[2];
+    int* ovf_list[2];         // candidates whose histogram overflowed the per-lane capacity
+    size_t ovf_bytes[2];
     cudaEvent_t ev[pfx::N_EVENTS];
     // fork/join: the independent score groups of one call run on a side stream
     cudaStream_t side[2];

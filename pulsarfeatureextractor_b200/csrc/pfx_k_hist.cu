@@ -5,6 +5,7 @@
 // The expectation of the profile-histogram fit, needed by scores 8-11, is parked in the score-8
 // column of the feature row; the next kernel (pfx_k_gauss.cu) consumes it.
 #include "pfx_internal.cuh"
+#include "pfx_lane_hist.cuh"
 
 using namespace pfx;
 
@@ -13,7 +14,8 @@ namespace {
 __global__ void __launch_bounds__(BLOCK_THREADS, 4)
 k_hist(const void* __restrict__ profile, int dtype, long long n, int m, double pow_m, double pow_m1,
        double* feat, long long ld, int8_t* ier, int32_t* status, u64* counter, int work_doubles,
-       int cap_smem, double* gscratch, int cap_global) {
+       int cap_smem, double* gscratch, int cap_global, const int* __restrict__ list,
+       const u64* __restrict__ list_count) {
     extern __shared__ double smem[];
     Group<WARP> g;
     const int gid = threadIdx.x / WARP;
@@ -21,9 +23,13 @@ k_hist(const void* __restrict__ profile, int dtype, long long n, int m, double p
     double* gs = gscratch
                      ? gscratch + ((size_t)blockIdx.x * GROUPS_PER_BLOCK + gid) * hist_scratch_doubles(cap_global)
                      : nullptr;
+    // with an index list the kernel scores only those candidates (histograms that overflowed the
+    // per-lane capacity of k_hist_lane)
+    const long long total = list ? (long long)*list_count : n;
     for (;;) {
-        const long long c = next_candidate(g, counter);
-        if (c >= n) break;
+        const long long q = next_candidate(g, counter);
+        if (q >= total) break;
+        const long long c = list ? (long long)list[q] : q;
         double ph_expect;
         unsigned st = hist_candidate(g, ws, cap_smem, gs, cap_global, profile, dtype, c, m, pow_m, pow_m1,
                                      feat + c * ld, ier ? ier + c * PFX_NIER : nullptr, &ph_expect);
@@ -31,6 +37,53 @@ k_hist(const void* __restrict__ profile, int dtype, long long n, int m, double p
             feat[c * ld + 7] = ph_expect;
             if (st) atomicOr(status + c, (int)st);
         }
+    }
+}
+
+__global__ void __launch_bounds__(128, 3)
+k_hist_lane(const void* __restrict__ profile, int dtype, long long n, int m, double pow_m, double pow_m1,
+            double* feat, long long ld, int8_t* ier, int32_t* status, u64* counter, double* gbuf,
+            int* ovf_list, u64* ovf_count) {
+    extern __shared__ double smem[];
+    LaneWs ws;
+    ws.carve(smem + threadIdx.x, blockDim.x, 3);
+    HistLaneBuf b;
+    b.carve(gbuf + (size_t)blockIdx.x * blockDim.x + threadIdx.x, (int)(gridDim.x * blockDim.x), m);
+    HistLane g;
+    g.phase = GP_IDLE;
+    g.cand = -1;
+    bool more = true;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (;;) {
+        if (g.phase == GP_IDLE) {
+            if (g.cand >= 0) {
+                double* row = feat + g.cand * ld;
+                if (g.overflow) {
+                    ovf_list[atomicAdd(ovf_count, 1ULL)] = (int)g.cand;
+                } else {
+                    double ph = qnan;
+                    if (g.complete()) g.write(row, &ph);
+                    row[7] = ph;                   // parked for the Gaussian kernels
+                    if (ier) {
+                        int8_t* ir = ier + g.cand * PFX_NIER;
+                        ir[PFX_FIT_DYHIST] = g.ier[0];
+                        ir[PFX_FIT_PROFHIST] = g.ier[1];
+                        ir[PFX_FIT_FIXED] = g.ier[2];
+                        ir[PFX_FIT_DYHIST_COUNT] = g.counts[0];
+                        ir[PFX_FIT_PROFHIST_COUNT] = g.counts[1];
+                    }
+                    if (g.status) atomicOr(status + g.cand, (int)g.status);
+                }
+                g.cand = -1;
+            }
+            if (more) {
+                const long long c = (long long)atomicAdd(counter, 1ULL);
+                if (c < n) g.start(c, m, dtype == PFX_U8, pow_m, pow_m1);
+                else more = false;
+            }
+        }
+        if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
+        g.step(b, ws, profile, dtype);
     }
 }
 
@@ -63,9 +116,52 @@ int pfx::launch_hist(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* pr
     }
     const double pow_m = pow((double)m, -0.3333333);        // POI:151, evaluated by the C library
     const double pow_m1 = pow((double)(m - 1), -0.3333333);
-    k_hist<<<grid, BLOCK_THREADS, smem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
-                                               take_counter(ctx, ck, st), wd, cap_smem, ctx->hist_scratch,
-                                               HIST_CAP_GLOBAL);
-    PFX_CUDA(ctx, cudaGetLastError());
+    // pass 1: one lane per candidate, histograms up to HIST_LANE_CAP bins
+    {
+        const int threads = 128;
+        const size_t lsmem = (size_t)lane_ws_doubles(3) * 8 * threads;
+        int lgrid;
+        rc = persistent_grid(ctx, k_hist_lane, threads, lsmem, &lgrid);
+        if (rc) return rc;
+        if ((long long)lgrid * threads > n) lgrid = (int)((n + threads - 1) / threads);
+        const size_t lanes = (size_t)lgrid * threads;
+        const int par = ctx->counter_slot & 1;
+        const size_t lneed = lanes * (size_t)hist_lane_doubles(m) * 8;
+        if (ctx->hist_lane_bytes[par] < lneed) {
+            if (ctx->hist_lane_buf[par]) {
+                cudaDeviceSynchronize();
+                cudaFree(ctx->hist_lane_buf[par]);
+                ctx->scratch_bytes -= ctx->hist_lane_bytes[par];
+                ctx->hist_lane_buf[par] = nullptr;
+                ctx->hist_lane_bytes[par] = 0;
+            }
+            PFX_CUDA(ctx, cudaMalloc(&ctx->hist_lane_buf[par], lneed));
+            ctx->hist_lane_bytes[par] = lneed;
+            ctx->scratch_bytes += lneed;
+        }
+        const size_t oneed = (size_t)n * sizeof(int);
+        if (ctx->ovf_bytes[par] < oneed) {
+            if (ctx->ovf_list[par]) {
+                cudaDeviceSynchronize();
+                cudaFree(ctx->ovf_list[par]);
+                ctx->scratch_bytes -= ctx->ovf_bytes[par];
+            }
+            PFX_CUDA(ctx, cudaMalloc(&ctx->ovf_list[par], oneed));
+            ctx->ovf_bytes[par] = oneed;
+            ctx->scratch_bytes += oneed;
+        }
+        u64* ovf_count = take_counter(ctx, 7, st);
+        k_hist_lane<<<lgrid, threads, lsmem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
+                                                    take_counter(ctx, ck, st), (double*)ctx->hist_lane_buf[par],
+                                                    ctx->ovf_list[par], ovf_count);
+        PFX_CUDA(ctx, cudaGetLastError());
+        // pass 2: the few candidates whose histogram has more bins go through the warp-form kernel
+        // (4096-bin scratch slot per warp); the launch is tiny when the list is empty
+        int wgrid = grid < 64 ? grid : 64;
+        k_hist<<<wgrid, BLOCK_THREADS, smem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
+                                                    take_counter(ctx, 6, st), wd, cap_smem, ctx->hist_scratch,
+                                                    HIST_CAP_GLOBAL, ctx->ovf_list[par], ovf_count);
+        PFX_CUDA(ctx, cudaGetLastError());
+    }
     return PFX_OK;
 }

@@ -239,3 +239,26 @@ extern "C" unsigned hs_dm_lane(const void* dmcurve, int dm_dtype, int n_dm, int 
     ier[PFX_FIT_DM] = g.ier;
     return g.status;
 }
+
+// ---- lane-per-candidate scores 5-7 (pfx_lane_hist.cuh) --------------------------------------------
+#include "../../pulsarfeatureextractor_b200/csrc/pfx_lane_hist.cuh"
+// returns status; *overflow = 1 when the candidate must go to the warp-form kernel
+extern "C" unsigned hs_hist_lane(const void* profile, int dtype, int m, double* feat, int8_t* ier,
+                                 double* ph_expect, int* overflow) {
+    std::vector<double> buf(hist_lane_doubles(m) + 8), wsbuf(lane_ws_doubles(4) + 8);
+    HistLaneBuf b;
+    b.carve(buf.data(), 1, m);
+    LaneWs ws;
+    ws.carve(wsbuf.data(), 1, 3);
+    HistLane g;
+    g.start(0, m, dtype == PFX_U8, pow((double)m, -0.3333333), pow((double)(m - 1), -0.3333333));
+    while (g.phase != GP_IDLE) g.step(b, ws, profile, dtype);
+    *overflow = g.overflow ? 1 : 0;
+    ier[PFX_FIT_DYHIST] = g.ier[0];
+    ier[PFX_FIT_PROFHIST] = g.ier[1];
+    ier[PFX_FIT_FIXED] = g.ier[2];
+    ier[PFX_FIT_DYHIST_COUNT] = g.counts[0];
+    ier[PFX_FIT_PROFHIST_COUNT] = g.counts[1];
+    if (g.complete()) g.write(feat, ph_expect);
+    return g.status;
+}
