@@ -165,6 +165,13 @@ int pfx_dmfit_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* p
                   const void* dmcurve, const double* params,
                   double* feat, int64_t feat_ld, int8_t* ier, int32_t* status, void* stream);
 
+/* PFD family only: derive S/N and width from the profile the way PFDOperations.getCandidateParameters
+ * does (PFDOperations.py:130-231: 3-sigma clipped S/N, half-maximum width of the centred profile)
+ * and store them in params[i][0] and params[i][3]; the other parameters (period, DM, DM range)
+ * come from the file header and are left untouched.  Call before pfx_dmfit_dev / pfx_score_dev. */
+int pfx_pfd_params_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                       double* params, void* stream);
+
 /* scores 20-22: getSubbandParameters (PHCXOperations.py:305-415, PFDOperations.py:401-466,
  * ProfileOperations.py:1585-1686) */
 int pfx_subband_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,

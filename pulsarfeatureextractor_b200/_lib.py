@@ -31,7 +31,7 @@ ST_FAIL_MASK = (ST_HIST_ZERO_BINS | ST_LSQ_IMPROPER | ST_INDEX_OOB | ST_SUBBAND_
 # every symbol include/pfx.h declares
 EXPORTS = [
     "pfx_version", "pfx_create", "pfx_destroy", "pfx_last_error", "pfx_device_info",
-    "pfx_lyon8_dev", "pfx_sinusoid_dev", "pfx_gaussian_dev", "pfx_dmfit_dev", "pfx_subband_dev",
+    "pfx_lyon8_dev", "pfx_pfd_params_dev", "pfx_sinusoid_dev", "pfx_gaussian_dev", "pfx_dmfit_dev", "pfx_subband_dev",
     "pfx_score_dev", "pfx_score_host", "pfx_last_timing", "pfx_set_stage_timing",
 ]
 
@@ -73,6 +73,7 @@ def load():
     lib.pfx_sinusoid_dev.argtypes = [vp, sp, i64, vp, dp, i64, vp, vp, vp]
     lib.pfx_gaussian_dev.argtypes = [vp, sp, i64, vp, dp, i64, vp, vp, vp]
     lib.pfx_dmfit_dev.argtypes = [vp, sp, i64, vp, vp, vp, dp, i64, vp, vp, vp]
+    lib.pfx_pfd_params_dev.argtypes = [vp, sp, i64, vp, vp, vp]
     lib.pfx_subband_dev.argtypes = [vp, sp, i64, vp, vp, vp, dp, i64, vp, vp]
     lib.pfx_score_dev.argtypes = [vp, sp, i64, ctypes.c_uint32, vp, vp, vp, vp, vp, dp, i64, vp, vp, vp]
     lib.pfx_score_host.argtypes = [vp, sp, i64, ctypes.c_uint32, vp, vp, vp, vp, vp, dp, i64, vp, vp, i64]

@@ -155,6 +155,16 @@ extern "C" int pfx_dmfit_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, co
     return launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, (cudaStream_t)stream, 0);
 }
 
+extern "C" int pfx_pfd_params_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
+                                  double* params, void* stream) {
+    int rc = check_shape(ctx, shape, n);
+    if (rc) return rc;
+    if (n == 0) return PFX_OK;
+    if (!profile || !params) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return launch_pfd_params(ctx, shape, n, profile, params, (cudaStream_t)stream);
+}
+
 extern "C" int pfx_subband_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
                                const void* subbands, const double* params, double* feat, int64_t feat_ld,
                                int32_t* status, void* stream) {

@@ -110,6 +110,8 @@ int launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* prof
                    const double* params, double* feat, int64_t ld, int32_t* status, cudaStream_t st, int ck);
 int launch_lyon(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, const void* dmstat,
                 double* feat, int64_t ld, cudaStream_t st);
+int launch_pfd_params(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* params,
+                      cudaStream_t st);
 int launch_fill_nan(pfx_ctx* ctx, double* feat, int64_t n, int64_t ld, int ncol, cudaStream_t st);
 
 }  // namespace pfx

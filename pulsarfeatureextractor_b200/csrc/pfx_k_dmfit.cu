@@ -54,7 +54,24 @@ int launch_n(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, c
     return PFX_OK;
 }
 
+__global__ void k_pfd_params(const void* __restrict__ profile, int dtype, long long n, int nbin, double* params) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double snr, width;
+    pfd_params(profile, dtype, c, nbin, snr, width);
+    params[c * PFX_NPARAM + 0] = snr;
+    params[c * PFX_NPARAM + 3] = width;
+}
+
 }  // namespace
+
+int pfx::launch_pfd_params(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* params,
+                           cudaStream_t st) {
+    if (s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin < 2");
+    k_pfd_params<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(profile, s->dtype, n, s->nbin, params);
+    PFX_CUDA(ctx, cudaGetLastError());
+    return PFX_OK;
+}
 
 int pfx::launch_dmfit(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
                       double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {

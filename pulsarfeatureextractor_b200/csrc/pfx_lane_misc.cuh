@@ -391,4 +391,111 @@ struct DmLane {
     }
 };
 
+// =============================================================================================
+// PFD family: S/N and width derived from the profile              PFDOperations.py:93-233
+// =============================================================================================
+// snr   = sum((p - avg') / sqrt(var')) with avg', var' over the bins inside avg +- 3 sigma; < 0 -> 0.1
+// width = (right - left - 1) / n from the half-maximum walk on the profile rotated so that its peak
+//         sits at n//2, minus its minimum.  fft_rotate (PFDO:490-500) by an integer number of bins
+//         is a circular shift; the reference's FFT round trip adds ~1e-13 of noise, which can only
+//         matter when a bin equals the half maximum exactly.
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src: pairwise_sum): fewer than
+// 8 terms sequentially; up to 128 terms with eight interleaved accumulators combined as
+// ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) and a sequential remainder; longer inputs split in halves
+// (the first a multiple of 8).  Reproduced because the PFD S/N below is a sum that cancels to
+// rounding noise whenever no bin is clipped, and its SIGN decides between ~1e-15 and 0.1.
+template <class F>
+PFX_HD double np_pairwise_sum(const F& f, int lo, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += f(lo + i);
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] += f(lo + i + k);
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += f(lo + i);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(f, lo, n2) + np_pairwise_sum(f, lo + n2, n - n2);
+}
+
+PFX_HD inline void pfd_params(const void* profile, int dtype, long long cand, int n, double& snr, double& width) {
+    const long long off = cand * (long long)n;
+    auto p = [&](int i) { return load_elem(profile, dtype, off + i); };
+    // profile.mean(), profile.var() (numpy: pairwise sums)
+    const double avg = np_pairwise_sum(p, 0, n) / (double)n;
+    const double var = np_pairwise_sum([&](int i) { const double d = p(i) - avg; return d * d; }, 0, n) / (double)n;
+    const double sigma = sqrt(var);
+    // the clipped sub-array is compacted by the reference; its sums run over the kept bins in order
+    const double lo3 = avg - 3 * sigma, hi3 = avg + 3 * sigma;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) cnt += (p(i) > lo3 && p(i) < hi3) ? 1 : 0;
+    auto kept = [&](int k) {            // k-th kept bin (n is small: 64..1024)
+        int seen = -1;
+        for (int i = 0; i < n; ++i) {
+            const double v = p(i);
+            if (v > lo3 && v < hi3) {
+                if (++seen == k) return v;
+            }
+        }
+        return (double)NAN;
+    };
+    const bool all_kept = (cnt == n);
+    double avg2, var2;
+    if (all_kept) {
+        avg2 = avg;
+        var2 = var;
+    } else {
+        avg2 = np_pairwise_sum(kept, 0, cnt) / (double)cnt;      // cnt == 0 -> NaN like numpy
+        var2 = np_pairwise_sum([&](int k) { const double d = kept(k) - avg2; return d * d; }, 0, cnt) / (double)cnt;
+    }
+    const double sd2 = sqrt(var2);
+    const double acc = np_pairwise_sum([&](int i) { return (p(i) - avg2) / sd2; }, 0, n);
+    snr = (acc < 0.0) ? 0.1 : acc;
+    int peak = 0;
+    double vmax = p(0), vmin = vmax;
+    for (int i = 1; i < n; ++i) {
+        const double v = p(i);
+        if (argmax_better(v, i, vmax, peak)) {
+            vmax = v;
+            peak = i;
+        }
+        if (v < vmin) vmin = v;
+    }
+    const int shift = peak - n / 2;
+    auto rot = [&](int k) {
+        int src = (k + shift) % n;
+        if (src < 0) src += n;
+        return load_elem(profile, dtype, off + src) - vmin;
+    };
+    int rpeak = 0;
+    double rmax = rot(0);
+    for (int k = 1; k < n; ++k) {
+        const double v = rot(k);
+        if (argmax_better(v, k, rmax, rpeak)) {
+            rmax = v;
+            rpeak = k;
+        }
+    }
+    const double half = rmax / 2.0;
+    int left = rpeak;
+    while (left > 0) {
+        if (rot(left) < half) break;
+        --left;
+    }
+    int right = rpeak;
+    while (right < n) {
+        if (rot(right) < half) break;
+        ++right;
+    }
+    width = (1.0 * ((double)(right - left) - 1.0)) / (double)n;
+}
+
 }  // namespace pfx

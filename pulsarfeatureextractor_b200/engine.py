@@ -205,6 +205,14 @@ class Engine(object):
                                               self._stream()))
         return Scores(feat[:, 19:22], status, None)
 
+    def pfd_params(self, profile, params):
+        """PFD family: fill params[:, 0] (S/N) and params[:, 3] (width) from the profile on the device
+        (PFDOperations.py:130-231).  In place; returns params."""
+        shape = self.make_shape(profile)
+        self._check(self._lib.pfx_pfd_params_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
+                                                 _ptr(params), self._stream()))
+        return params
+
     def lyon8(self, profile, dmstat):
         torch = self._torch
         n = profile.shape[0]

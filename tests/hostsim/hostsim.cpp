@@ -262,3 +262,7 @@ extern "C" unsigned hs_hist_lane(const void* profile, int dtype, int m, double* 
     if (g.complete()) g.write(feat, ph_expect);
     return g.status;
 }
+
+extern "C" void hs_pfd_params(const void* profile, int dtype, int n, double* snr, double* width) {
+    pfd_params(profile, dtype, 0, n, *snr, *width);
+}

@@ -238,6 +238,24 @@ def test_pfd_family_shape(eng):
         O.FAST_CORR = False
 
 
+def test_pfd_params_on_device(eng):
+    """S/N (3-sigma clipped) and half-maximum width derived from the profile, PFDOperations.py:130-231.
+    The S/N cancels to rounding noise when nothing is clipped and its sign picks 0.1 or ~1e-15, so the
+    kernel reproduces numpy's pairwise summation order: results are bit-exact."""
+    import torch
+    b = synth.generate_pfd_shaped(4, 0, 512)
+    dev = torch.device("cuda", 0)
+    prof = torch.from_numpy(b.profile).to(dev)
+    par = torch.zeros((512, 8), dtype=torch.float64, device=dev)
+    eng.pfd_params(prof, par)
+    torch.cuda.synchronize()
+    got = par.cpu().numpy()
+    for i in range(512):
+        _sc, (_per, snr, _dm, width) = O.cand_params_pfd(b.profile[i], 0.5, 100.0)
+        assert got[i, 3] == width, (i, got[i, 3], width)
+        assert got[i, 0] == snr or (np.isnan(snr) and np.isnan(got[i, 0])), (i, got[i, 0], snr)
+
+
 def test_large_batch_properties(eng):
     """BASELINE-size run (100 000 candidates): size-independent properties."""
     import torch
