@@ -408,7 +408,7 @@ template <class F>
 PFX_HD double np_pairwise_sum(const F& f, int lo, int n) {
     if (n < 8) {
         double r = 0.0;
-        for (int i = 0; i < n; ++i) r += f(lo + i);
+        for (int i = 0; i < n; ++i) r = PFX_ADD(r, f(lo + i));      // PFX_ADD: never fused with a product
         return r;
     }
     if (n <= 128) {
@@ -416,14 +416,15 @@ PFX_HD double np_pairwise_sum(const F& f, int lo, int n) {
         for (int k = 0; k < 8; ++k) r[k] = f(lo + k);
         int i;
         for (i = 8; i < n - (n % 8); i += 8)
-            for (int k = 0; k < 8; ++k) r[k] += f(lo + i + k);
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += f(lo + i);
+            for (int k = 0; k < 8; ++k) r[k] = PFX_ADD(r[k], f(lo + i + k));
+        double res = PFX_ADD(PFX_ADD(PFX_ADD(r[0], r[1]), PFX_ADD(r[2], r[3])),
+                             PFX_ADD(PFX_ADD(r[4], r[5]), PFX_ADD(r[6], r[7])));
+        for (; i < n; ++i) res = PFX_ADD(res, f(lo + i));
         return res;
     }
     int n2 = n / 2;
     n2 -= n2 % 8;
-    return np_pairwise_sum(f, lo, n2) + np_pairwise_sum(f, lo + n2, n - n2);
+    return PFX_ADD(np_pairwise_sum(f, lo, n2), np_pairwise_sum(f, lo + n2, n - n2));
 }
 
 PFX_HD inline void pfd_params(const void* profile, int dtype, long long cand, int n, double& snr, double& width) {
@@ -431,10 +432,10 @@ PFX_HD inline void pfd_params(const void* profile, int dtype, long long cand, in
     auto p = [&](int i) { return load_elem(profile, dtype, off + i); };
     // profile.mean(), profile.var() (numpy: pairwise sums)
     const double avg = np_pairwise_sum(p, 0, n) / (double)n;
-    const double var = np_pairwise_sum([&](int i) { const double d = p(i) - avg; return d * d; }, 0, n) / (double)n;
+    const double var = np_pairwise_sum([&](int i) { const double d = PFX_SUB(p(i), avg); return PFX_MUL(d, d); }, 0, n) / (double)n;
     const double sigma = sqrt(var);
     // the clipped sub-array is compacted by the reference; its sums run over the kept bins in order
-    const double lo3 = avg - 3 * sigma, hi3 = avg + 3 * sigma;
+    const double lo3 = PFX_SUB(avg, PFX_MUL(3.0, sigma)), hi3 = PFX_ADD(avg, PFX_MUL(3.0, sigma));
     int cnt = 0;
     for (int i = 0; i < n; ++i) cnt += (p(i) > lo3 && p(i) < hi3) ? 1 : 0;
     auto kept = [&](int k) {            // k-th kept bin (n is small: 64..1024)
@@ -454,10 +455,10 @@ PFX_HD inline void pfd_params(const void* profile, int dtype, long long cand, in
         var2 = var;
     } else {
         avg2 = np_pairwise_sum(kept, 0, cnt) / (double)cnt;      // cnt == 0 -> NaN like numpy
-        var2 = np_pairwise_sum([&](int k) { const double d = kept(k) - avg2; return d * d; }, 0, cnt) / (double)cnt;
+        var2 = np_pairwise_sum([&](int k) { const double d = PFX_SUB(kept(k), avg2); return PFX_MUL(d, d); }, 0, cnt) / (double)cnt;
     }
     const double sd2 = sqrt(var2);
-    const double acc = np_pairwise_sum([&](int i) { return (p(i) - avg2) / sd2; }, 0, n);
+    const double acc = np_pairwise_sum([&](int i) { return PFX_DIV(PFX_SUB(p(i), avg2), sd2); }, 0, n);
     snr = (acc < 0.0) ? 0.1 : acc;
     int peak = 0;
     double vmax = p(0), vmin = vmax;
