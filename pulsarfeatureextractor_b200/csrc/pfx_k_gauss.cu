@@ -42,6 +42,16 @@ __device__ __forceinline__ LaneBuf lane_buf(double* gdat, unsigned short* gxs) {
     b.xs = gxs + lane;
     return b;
 }
+// shared-memory variant: ws[nws][T] float64 | dat[m][T] float64 | xs[m][T] uint16.  Measured
+// faster than the global scratch whenever one block of >= 96 lanes fits: the kernels are bound by
+// the latency of a candidate's dependent chain, so fewer, faster lanes win over more resident warps.
+__device__ __forceinline__ LaneBuf lane_buf_smem(double* smem, int m, int nws) {
+    LaneBuf b;
+    b.stride = blockDim.x;
+    b.dat = smem + (size_t)nws * blockDim.x + threadIdx.x;
+    b.xs = (unsigned short*)(smem + (size_t)(nws + m) * blockDim.x) + threadIdx.x;
+    return b;
+}
 __device__ __forceinline__ LaneWs lane_ws(double* smem, int n) {
     LaneWs w;
     w.carve(smem + threadIdx.x, blockDim.x, n);
@@ -53,7 +63,8 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
                int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
                unsigned short* gxs) {
     extern __shared__ double smem[];
-    const LaneBuf b = lane_buf(gdat, gxs);
+    // lane data in shared memory when it fits (gdat == nullptr), else in the global scratch
+    const LaneBuf b = gdat ? lane_buf(gdat, gxs) : lane_buf_smem(smem, m, lane_ws_doubles(4));
     const LaneWs ws = lane_ws(smem, 4);
     GaussLane g;
     g.phase = GP_IDLE;
@@ -131,7 +142,7 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
               int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat,
               unsigned short* gxs) {
     extern __shared__ double smem[];
-    const LaneBuf b = lane_buf(gdat, gxs);
+    const LaneBuf b = gdat ? lane_buf(gdat, gxs) : lane_buf_smem(smem, m, lane_ws_doubles(8));
     const LaneWs ws = lane_ws(smem, 8);
     Gauss8Lane g;
     g.phase = GP_IDLE;
@@ -235,6 +246,24 @@ extern "C" float pfx_micro_rows(const void* profile, int dtype, long long n, int
 
 static const int LANE_THREADS = 128;
 
+// Block size and dynamic shared memory of a lane kernel.  Returns true when the per-lane data
+// vectors go to shared memory (one block of 128 or 96 lanes fits), false for the global scratch.
+static bool lane_layout(pfx_ctx* ctx, int m, int np, int* threads, size_t* smem) {
+    const size_t ws = (size_t)lane_ws_doubles(np) * 8;
+    const size_t per_lane = ws + (size_t)m * 10;
+    const size_t budget = (size_t)ctx->smem_optin;
+    for (int t = 128; t >= 96; t -= 32) {
+        if (per_lane * t + 64 <= budget) {
+            *threads = t;
+            *smem = (per_lane * t + 15) / 16 * 16;
+            return true;
+        }
+    }
+    *threads = LANE_THREADS;
+    *smem = ws * LANE_THREADS;
+    return false;
+}
+
 // scratch for the per-lane data vectors of one launch: lanes x m x (8 + 2) bytes
 static int lane_scratch(pfx_ctx* ctx, size_t lanes, int m, int slot, double** gdat, unsigned short** gxs) {
     const size_t need = ((lanes * (size_t)m * 10) + 255) / 256 * 256;
@@ -259,7 +288,6 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
                       int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
     const int m = s->nbin;
     if (m < 8 || m > 65535) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin out of range");
-    const int threads = LANE_THREADS;
     const int par = ctx->counter_slot & 1;      // calls in flight alternate between two scratch sets
     // carry records
     const size_t need = (size_t)n * sizeof(GaussCarry);
@@ -280,23 +308,35 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     unsigned short* gxs;
     int grid, rc;
     {
-        const size_t smem = (size_t)lane_ws_doubles(4) * 8 * threads;
+        int threads;
+        size_t smem;
+        const bool in_smem = lane_layout(ctx, m, 4, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
         if (rc) return rc;
         if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
-        rc = lane_scratch(ctx, (size_t)grid * threads, m, par * 2 + 0, &gdat, &gxs);
-        if (rc) return rc;
+        gdat = nullptr;
+        gxs = nullptr;
+        if (!in_smem) {
+            rc = lane_scratch(ctx, (size_t)grid * threads, m, par * 2 + 0, &gdat, &gxs);
+            if (rc) return rc;
+        }
         k_gauss_rounds<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                      take_counter(ctx, ck, st), carry, gdat, gxs);
         PFX_CUDA(ctx, cudaGetLastError());
     }
     {
-        const size_t smem = (size_t)lane_ws_doubles(8) * 8 * threads;
+        int threads;
+        size_t smem;
+        const bool in_smem = lane_layout(ctx, m, 8, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
         if (rc) return rc;
         if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
-        rc = lane_scratch(ctx, (size_t)grid * threads, m, par * 2 + 1, &gdat, &gxs);
-        if (rc) return rc;
+        gdat = nullptr;
+        gxs = nullptr;
+        if (!in_smem) {
+            rc = lane_scratch(ctx, (size_t)grid * threads, m, par * 2 + 1, &gdat, &gxs);
+            if (rc) return rc;
+        }
         k_gauss_final<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier,
                                                     take_counter(ctx, ck + 4, st), carry, gdat, gxs);
         PFX_CUDA(ctx, cudaGetLastError());

@@ -351,7 +351,12 @@ struct SmallLM {
 // per-lane workspace of the n x n sub-problem: r (n x n, column major), six n-vectors, ipvt
 constexpr int LANE_BLOCK_ROWS = 8;
 // r, six vectors, ipvt (one int per float64 slot), and the staged row block of the Jacobian pass
-PFX_HD inline int lane_ws_doubles(int n) { return n * n + 7 * n + LANE_BLOCK_ROWS * (n + 1); }
+// The staged block is only live during the row loop of a Jacobian pass and the n x n vectors only
+// after it, so they share the same storage.
+PFX_HD inline int lane_ws_doubles(int n) {
+    const int a = n * n + 7 * n, b = LANE_BLOCK_ROWS * (n + 1);
+    return a > b ? a : b;
+}
 struct LaneWs {
     SPtr<double> r, diag, qtf, step, sdiag, wa1, wa2, blk;
     SPtr<int> ipvt;
@@ -368,7 +373,7 @@ struct LaneWs {
         // one int per float64 slot (low half), strided like the rest
         ipvt.p = (int*)(base + (size_t)(n * n + 6 * n) * stride);
         ipvt.stride = 2 * stride;
-        blk = at(n * n + 7 * n);
+        blk = at(0);      // aliases r .. ipvt (see lane_ws_doubles)
     }
 };
 
