@@ -234,6 +234,10 @@ def main():
     eng.set_stage_timing(True)
     step_dev()
     stage = eng.last_timing()
+    # and one with the production stream layout, recording when each group completed
+    eng.set_stage_timing(2)
+    step_dev()
+    trace = eng.last_timing()
     eng.set_stage_timing(False)
     launches = int(stage.get("launches", 0)) * args.steps
 
@@ -317,6 +321,7 @@ def main():
                                  "tiny by construction; the HBM-bound kernel of the path is reported in roofline_lyon"},
             "roofline_lyon": lyon_roof,
             "stage_ms_serialised": {k: v for k, v in stage.items() if k != "launches"},
+            "stage_done_ms_overlapped": {k: v for k, v in trace.items() if k not in ("launches", "subband")},
             "clocks": sampler.summary(),
             "rows_valid": ok, "host_equals_device": same,
         }

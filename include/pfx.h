@@ -199,7 +199,10 @@ int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t fea
 
 /* Stage timing.  By default pfx_score_dev overlaps independent score groups on a side stream.
  * With stage timing on, the groups run back to back on the caller's stream with a CUDA event
- * between them, and pfx_last_timing (which synchronises) returns their durations. */
+ * between them, and pfx_last_timing (which synchronises) returns their durations.
+ * on == 2 keeps the production stream layout and records when each group completed: the fields
+ * of pfx_timing then hold completion times since the start of the call (overlap trace; subband
+ * is reported with dmfit, which shares its stream). */
 int pfx_set_stage_timing(pfx_ctx* ctx, int on);
 int pfx_last_timing(pfx_ctx* ctx, pfx_timing* out);
 

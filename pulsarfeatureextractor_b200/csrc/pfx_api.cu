@@ -45,6 +45,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     for (int i = 0; i < 2; ++i) {
         cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
         cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&ctx->side2[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->join2_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
     }
@@ -69,6 +71,8 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
         cudaStreamDestroy(ctx->streams[i]);
         cudaStreamDestroy(ctx->side[i]);
+        cudaStreamDestroy(ctx->side2[i]);
+        cudaEventDestroy(ctx->join2_ev[i]);
         cudaEventDestroy(ctx->fork_ev[i]);
         cudaEventDestroy(ctx->join_ev[i]);
     }
@@ -181,7 +185,10 @@ extern "C" int pfx_subband_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, 
 static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t features,
                           const void* profile, const void* subbands, const void* dmcurve,
                           const void* dmstat, const double* params, double* feat, int64_t feat_ld,
-                          int8_t* ier, int32_t* status, cudaStream_t st, bool timed) {
+                          int8_t* ier, int32_t* status, cudaStream_t st, int timing) {
+    // timing 1: stages serialised on one stream and timed each; 2: streams as in production, the
+    // events mark when each group completed since the start of the call (overlap trace)
+    const bool timed = timing == 1, trace = timing == 2;
     const bool bates = (features & PFX_FEAT_BATES) != 0, lyon = (features & PFX_FEAT_LYON) != 0;
     const int ncol = (bates ? PFX_NBATES : 0) + (lyon ? PFX_NLYON : 0);
     if (ncol == 0) return set_err(ctx, PFX_ERR_INVALID, "no feature set selected");
@@ -191,14 +198,14 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
     rotate_counters(ctx);
     int launches = 0;
     int e = 0;
-    if (timed) cudaEventRecord(ctx->ev[e++], st);
+    if (timed || trace) cudaEventRecord(ctx->ev[e++], st);
     int rc;
     if (lyon) {
         rc = launch_lyon(ctx, shape, n, profile, dmstat, feat + (bates ? PFX_NBATES : 0), feat_ld, st);
         if (rc) return rc;
         ++launches;
     }
-    if (timed) cudaEventRecord(ctx->ev[e++], st);
+    if (timed || trace) cudaEventRecord(ctx->ev[e++], st);
     if (bates) {
         PFX_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)n, st));
         if (ier) PFX_CUDA(ctx, cudaMemsetAsync(ier, 0, (size_t)n * PFX_NIER, st));
@@ -208,44 +215,60 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
         // The histogram -> Gaussian chain is the long pole and ends in a tail of slow candidates;
         // scores 1-4, 12-19 and 20-22 do not depend on it and run on a side stream next to it.
         // (Timed calls keep everything on one stream so that the per-stage events mean something.)
-        cudaStream_t sd = st;
+        cudaStream_t sd = st, sd2 = st;
         const int par = ctx->counter_slot & 1;
         if (!timed) {
             sd = ctx->side[par];
+            sd2 = ctx->side2[par];
             PFX_CUDA(ctx, cudaEventRecord(ctx->fork_ev[par], st));
             PFX_CUDA(ctx, cudaStreamWaitEvent(sd, ctx->fork_ev[par], 0));
+            PFX_CUDA(ctx, cudaStreamWaitEvent(sd2, ctx->fork_ev[par], 0));
         }
         if (!timed) {
+            // side stream first: the DM and sinusoid kernels have a short body and a long tail of
+            // slow candidates (a few lingering blocks); launched ahead of the histogram/Gaussian
+            // chain their tails hide behind its body instead of adding to the step
+            rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, 3);
+            if (rc) return rc;
+            if (trace) cudaEventRecord(ctx->ev[5], sd);
+            rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, 0);
+            if (rc) return rc;
+            if (trace) cudaEventRecord(ctx->ev[2], sd2);
+            rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, 4);
+            if (rc) return rc;
             rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
             if (rc) return rc;
+            if (trace) cudaEventRecord(ctx->ev[3], st);
             rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
             if (rc) return rc;
-        }
-        rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd, 0);
-        if (rc) return rc;
-        if (timed) {
-            cudaEventRecord(ctx->ev[e++], st);
-            rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
-            rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
-        }
-        rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, 3);
-        if (rc) return rc;
-        if (timed) cudaEventRecord(ctx->ev[e++], st);
-        rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, 4);
-        if (rc) return rc;
-        if (timed) cudaEventRecord(ctx->ev[e++], st);
-        if (!timed) {
+            if (trace) cudaEventRecord(ctx->ev[4], st);
             PFX_CUDA(ctx, cudaEventRecord(ctx->join_ev[par], sd));
             PFX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join_ev[par], 0));
+            PFX_CUDA(ctx, cudaEventRecord(ctx->join2_ev[par], sd2));
+            PFX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join2_ev[par], 0));
+        } else {
+            rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, 0);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
+            rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
+            rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
+            rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, st, 3);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
+            rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, st, 4);
+            if (rc) return rc;
+            cudaEventRecord(ctx->ev[e++], st);
         }
         launches += 7;
     }
     ctx->last_launches = launches;
-    if (timed) ctx->ev_valid = bates;
+    if (trace && bates) cudaEventRecord(ctx->ev[6], st);
+    if (timed || trace) ctx->ev_valid = bates;
+    ctx->ev_trace = trace;
     return PFX_OK;
 }
 
@@ -258,7 +281,7 @@ extern "C" int pfx_score_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, ui
     if (n == 0) return PFX_OK;
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
     return score_dev_impl(ctx, shape, n, features, profile, subbands, dmcurve, dmstat, params, feat, feat_ld,
-                          ier, status, (cudaStream_t)stream, ctx->stage_timing != 0);
+                          ier, status, (cudaStream_t)stream, ctx->stage_timing);
 }
 
 extern "C" int pfx_set_stage_timing(pfx_ctx* ctx, int on) {
@@ -274,6 +297,17 @@ extern "C" int pfx_last_timing(pfx_ctx* ctx, pfx_timing* out) {
     if (!ctx->ev_valid) return PFX_OK;
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
     PFX_CUDA(ctx, cudaEventSynchronize(ctx->ev[6]));
+    if (ctx->ev_trace) {
+        // completion times since the start of the call, streams as in production
+        cudaEventElapsedTime(&out->lyon, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&out->sinusoid, ctx->ev[0], ctx->ev[2]);
+        cudaEventElapsedTime(&out->histgauss, ctx->ev[0], ctx->ev[3]);
+        cudaEventElapsedTime(&out->gauss, ctx->ev[0], ctx->ev[4]);
+        cudaEventElapsedTime(&out->dmfit, ctx->ev[0], ctx->ev[5]);
+        out->subband = 0.f;
+        cudaEventElapsedTime(&out->total, ctx->ev[0], ctx->ev[6]);
+        return PFX_OK;
+    }
     cudaEventElapsedTime(&out->lyon, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&out->sinusoid, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&out->histgauss, ctx->ev[2], ctx->ev[3]);
@@ -366,7 +400,7 @@ extern "C" int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, u
                                           (size_t)cn * shape->n_dmstat * ess, cudaMemcpyHostToDevice, st));
         rc = score_dev_impl(ctx, shape, cn, features, base + L.profile, base + L.subbands, base + L.dmcurve,
                             base + L.dmstat, (const double*)(base + L.params), (double*)(base + L.feat), ncol,
-                            bates && ier ? (int8_t*)(base + L.ier) : nullptr, (int32_t*)(base + L.status), st, false);
+                            bates && ier ? (int8_t*)(base + L.ier) : nullptr, (int32_t*)(base + L.status), st, 0);
         if (rc) return rc;
         launches += ctx->last_launches;
         if (feat_ld == ncol) {

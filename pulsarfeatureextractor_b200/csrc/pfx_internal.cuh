@@ -43,9 +43,9 @@ struct pfx_ctx {
     size_t ovf_bytes[2];
     cudaEvent_t ev[pfx::N_EVENTS];
     // fork/join: the independent score groups of one call run on a side stream
-    cudaStream_t side[2];
-    cudaEvent_t fork_ev[2], join_ev[2];
-    bool ev_valid;
+    cudaStream_t side[2], side2[2];
+    cudaEvent_t fork_ev[2], join_ev[2], join2_ev[2];
+    bool ev_valid, ev_trace;
     int stage_timing;         // 1: serialise the stages of pfx_score_dev and time each (pfx_last_timing)
     int last_launches;
     // host-path staging

@@ -1,12 +1,18 @@
 // pfx_k_dmfit.cu -- scores 12-19 (PHCXOperations.py:81-233, PFDOperations.py:274-393,
 // CandidateFileInterface.py:84-112): pass-through parameters and the DM-curve fit, one lane per
-// candidate (state machine of pfx_lane_misc.cuh).  N = 3 parameters for the PHCX family, 4 for PFD.
+// candidate group (state machine of pfx_lane_misc.cuh).  N = 3 parameters for the PHCX family, 4
+// for PFD.  The fit is one LM solve over a few hundred rows whose cost varies by two orders of
+// magnitude between candidates (most converge in a handful of iterations, some run to maxfev), so
+// a whole warp shares each candidate (DM_LANES = 32): the rows are dealt to the lanes and the
+// kernel no longer ends in a long tail of single lanes finishing slow fits.
 #include "pfx_internal.cuh"
 #include "pfx_lane_misc.cuh"
 
 using namespace pfx;
 
 namespace {
+
+constexpr int DM_LANES = 32;
 
 template <int N>
 __global__ void __launch_bounds__(128, 3)
@@ -16,20 +22,25 @@ k_dmfit(const void* __restrict__ dmcurve, int dm_dtype, long long n, int n_dm, i
     extern __shared__ double smem[];
     LaneWs ws;
     ws.carve(smem + threadIdx.x, blockDim.x, N);
-    DmLane<N> g;
+    typedef LaneGroup<DM_LANES> G;
+    DmLane<N, DM_LANES> g;
     g.phase = GP_IDLE;
     g.cand = -1;
     bool more = true;
     for (;;) {
         if (g.phase == GP_IDLE) {
             if (g.cand >= 0) {
-                g.write(feat + g.cand * ld);
-                if (ier) ier[g.cand * PFX_NIER + PFX_FIT_DM] = g.ier;
-                if (g.status) atomicOr(status + g.cand, (int)g.status);
+                if (G::rank() == 0) {
+                    g.write(feat + g.cand * ld);
+                    if (ier) ier[g.cand * PFX_NIER + PFX_FIT_DM] = g.ier;
+                    if (g.status) atomicOr(status + g.cand, (int)g.status);
+                }
                 g.cand = -1;
             }
             if (more) {
-                const long long c = (long long)atomicAdd(counter, 1ULL);
+                long long c = 0;
+                if (G::rank() == 0) c = (long long)atomicAdd(counter, 1ULL);
+                c = G::bcast(c);
                 if (c < n) g.start(dmcurve, dm_dtype, c, n_dm, family, params + c * PFX_NPARAM);
                 else more = false;
             }
@@ -42,12 +53,15 @@ k_dmfit(const void* __restrict__ dmcurve, int dm_dtype, long long n, int n_dm, i
 template <int N>
 int launch_n(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
              double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
-    const int threads = 128;
+    // one warp per block: a block leaves when its 32 lanes are done, so the tail of slow candidates
+    // holds little shared memory and the Gaussian kernels' blocks fit next to it
+    const int threads = 32;
     const size_t smem = (size_t)lane_ws_doubles(N) * 8 * threads;
     int grid;
     int rc = persistent_grid(ctx, k_dmfit<N>, threads, smem, &grid);
     if (rc) return rc;
-    if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
+    const long long groups = (long long)grid * threads / DM_LANES;
+    if (groups > n) grid = (int)((n * DM_LANES + threads - 1) / threads);
     k_dmfit<N><<<grid, threads, smem, st>>>(dmcurve, s->dm_dtype, n, s->n_dm, s->family, params, feat, ld, ier,
                                              status, take_counter(ctx, ck, st));
     PFX_CUDA(ctx, cudaGetLastError());

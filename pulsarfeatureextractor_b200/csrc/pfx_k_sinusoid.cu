@@ -43,7 +43,9 @@ k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, doub
 int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
                          int64_t ld, int8_t* ier, cudaStream_t st, int ck) {
     if (s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin < 2");
-    const int threads = 128;
+    // one warp per block: a block leaves when its 32 lanes are done, so the tail of slow candidates
+    // holds little shared memory and the Gaussian kernels' blocks fit next to it
+    const int threads = 32;
     const size_t smem = (size_t)lane_ws_doubles(2) * 8 * threads;
     int grid;
     int rc = persistent_grid(ctx, k_sinusoid, threads, smem, &grid);

@@ -72,7 +72,14 @@ PFX_HD inline double g4_value(const double (&p)[4], G4Flags fl, double xv) {
     return e.value(xv);
 }
 
-struct GaussLane {
+// C lanes of a warp share the candidate (LaneGroup): one copy of the data vector per group.
+// Element-wise passes over the data are dealt to the lanes (element i to lane i % C) and closed
+// by a group barrier; order-sensitive scans (sequential sums, argmax, the index-list surgery of
+// the peak stripping) are done by every lane redundantly on the shared copy (reads) or by lane 0
+// (writes), so that all lanes of a group always hold bit-identical state.
+template <int C = 1>
+struct GaussLaneT {
+    typedef LaneGroup<C> G;
     // candidate
     const void* profile;
     int dtype;
@@ -142,13 +149,13 @@ struct GaussLane {
         double x0[4];
         if (stage == 0) {
             // profile statistics and the T1 data vector (PO:724-739, 1098-1110)
-            double s = 0.0;
-            for (int i = 0; i < m; ++i) {
-                const double v = yrot(i);
-                b.d(i) = v;
+            for (int i = G::rank(); i < m; i += C) {
+                b.d(i) = yrot(i);
                 b.x(i) = (unsigned short)i;
-                s += v;
             }
+            G::sync();
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) s += b.d(i);
             mean = s / (double)m;
             double q = 0.0;
             for (int i = 0; i < m; ++i) {
@@ -157,13 +164,15 @@ struct GaussLane {
             }
             sd = sqrt(q / (double)m);
             minbg = (mean < ph_expect) ? mean : ph_expect;     // builtin min(ph_expect, mean)
+            G::sync();
             if (minbg > 0.0) {
-                for (int i = 0; i < m; ++i) {
+                for (int i = G::rank(); i < m; i += C) {
                     double v = PFX_ADD(PFX_SUB(b.d(i), minbg), sd);
                     if (v < 0.0) v = 0.0;
                     b.d(i) = v;
                 }
             }
+            G::sync();
             double mu, sdev, vmax, bmax;
             int amax;
             stats(b, m, mu, sdev, amax, vmax, bmax);
@@ -176,17 +185,19 @@ struct GaussLane {
             nrows = m;
         } else if (stage == 1) {
             // rotated raw profile, peak stripping (PO:1305-1354)
+            for (int i = G::rank(); i < m; i += C) b.d(i) = yrot(i);
+            G::sync();
             int amax = 0;
             double vmax = 0.0;
             for (int i = 0; i < m; ++i) {
-                const double v = yrot(i);
-                b.d(i) = v;
+                const double v = b.d(i);
                 if (i == 0 || argmax_better(v, i, vmax, amax)) {
                     vmax = v;
                     amax = i;
                 }
             }
             const int nlen = strip_peak(b, amax);
+            G::sync();
             if (nlen < 0) {                 // IndexError -> 1e6 sentinels (PO:762-764)
                 sentinel = true;
                 status |= PFX_ST_DG_SENTINEL;
@@ -200,7 +211,9 @@ struct GaussLane {
                 phase = GP_IDLE;
                 return;
             }
-            for (int k = 0; k < nlen; ++k) b.d(k) = b.d(b.x(k));   // x(k) >= k, so no overwrite hazard
+            if (G::rank() == 0)
+                for (int k = 0; k < nlen; ++k) b.d(k) = b.d(b.x(k));   // x(k) >= k, so no overwrite hazard
+            G::sync();
             double mu, sdev, bmax;
             int am2;
             stats(b, nlen, mu, sdev, am2, vmax, bmax);
@@ -210,10 +223,13 @@ struct GaussLane {
             x0[3] = mu;
             nrows = nlen;
             for (int k = nlen; k < 4; ++k) {     // PO:1373-1377 zero padding
-                b.d(k) = 0.0;
-                b.x(k) = 0;
+                if (G::rank() == 0) {
+                    b.d(k) = 0.0;
+                    b.x(k) = 0;
+                }
                 nrows = 4;
             }
+            G::sync();
             fl.abs_sigma = false;
             fl.abs_bg = true;
         } else {
@@ -237,13 +253,16 @@ struct GaussLane {
     PFX_HD int strip_peak(const LaneBuf& b, int pos) const {
         const int n = m;
         int len = n;
-        for (int i = 0; i < n; ++i) b.x(i) = (unsigned short)i;
+        const bool writer = (G::rank() == 0);     // every lane follows the control flow, lane 0 edits the list
+        if (writer)
+            for (int i = 0; i < n; ++i) b.x(i) = (unsigned short)i;
 #define PFX_DEL(k_)                                                  \
     do {                                                             \
         int k = (k_);                                                \
         if (k < -len || k >= len) return -1;                         \
         if (k < 0) k += len;                                         \
-        for (int q_ = k; q_ < len - 1; ++q_) b.x(q_) = b.x(q_ + 1);  \
+        if (writer)                                                  \
+            for (int q_ = k; q_ < len - 1; ++q_) b.x(q_) = b.x(q_ + 1);  \
         --len;                                                       \
     } while (0)
         PFX_DEL(pos);
@@ -305,7 +324,7 @@ struct GaussLane {
         // rows are produced two at a time (six independent exponentials in flight) into the staged
         // block and eliminated eight at a time
         constexpr int B = LANE_BLOCK_ROWS;
-        for (int i0 = 0; i0 < nrows; i0 += B) {
+        for (int i0 = G::rank() * B; i0 < nrows; i0 += C * B) {     // blocks of rows dealt to the lanes
             const int rows = (nrows - i0 < B) ? nrows - i0 : B;
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) {
@@ -320,6 +339,14 @@ struct GaussLane {
                 const double a1 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e2), bg)) - f0) * ih1;
                 const double a2 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) * ih2;
                 const double a3 = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) * ih3;
+#if defined(PFX_GIVENS_ROWS)
+                // one row at a time with Givens rotations: the whole row loop is a few hundred
+                // instructions and stays in the L0 instruction cache
+                double a[4] = {a0, a1, a2, a3};
+                lm.jac_row(a, f0);
+            }
+        }
+#else
                 lm.acn2[0] = PFX_FMA(a0, a0, lm.acn2[0]);
                 lm.acn2[1] = PFX_FMA(a1, a1, lm.acn2[1]);
                 lm.acn2[2] = PFX_FMA(a2, a2, lm.acn2[2]);
@@ -331,8 +358,10 @@ struct GaussLane {
                 ws.blk[r * 5 + 3] = a3;
                 ws.blk[r * 5 + 4] = f0;
             }
-            lm.jac_block_staged<B>(ws.blk, rows);
+            lm.template jac_block_staged<B>(ws.blk, rows);
         }
+#endif
+        lm.template jac_combine<C>();
         const int r = lm.jac_end(ws, nrows);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
@@ -343,10 +372,11 @@ struct GaussLane {
         ev.set(lm.xnew, fl);
         double s = 0.0;
 #pragma unroll 4
-        for (int i = 0; i < nrows; ++i) {
+        for (int i = G::rank(); i < nrows; i += C) {
             const double f = PFX_SUB(b.d(i), ev.value((double)b.x(i)));
             s = PFX_FMA(f, f, s);
         }
+        s = G::sum(s);
         const int r = lm.trial_end(sqrt(s));
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
     }
@@ -361,10 +391,11 @@ struct GaussLane {
             ev.set(p, fl);
             double c = 0.0;
 #pragma unroll 4
-            for (int i = 0; i < m; ++i) {
+            for (int i = G::rank(); i < m; i += C) {
                 const double dlt = b.d(i) - ev.value((double)i);
                 c = PFX_FMA(dlt, dlt, c);
             }
+            c = G::sum(c);
             t1_chi = c / (double)m;
         } else {
             // rebuild the data for the next round over the full profile (PO:1388-1399)
@@ -373,8 +404,9 @@ struct GaussLane {
             const double hi = p[2] + (1.5 * nfwhm) / 2.0;
             G4Eval fe;
             fe.set(p, fl);
+            G::sync();
 #pragma unroll 4
-            for (int i = 0; i < m && stage < 8; ++i) {
+            for (int i = G::rank(); i < m && stage < 8; i += C) {
                 const double xv = (double)i;
                 const double ev = fe.value(xv);
                 const double yv = yrot(i);
@@ -385,6 +417,7 @@ struct GaussLane {
                 b.d(i) = nv;
                 b.x(i) = (unsigned short)i;
             }
+            G::sync();
             if (stage == 7)
                 for (int k = 0; k < 4; ++k) p2[k] = p[k];
             if (stage == 8)
@@ -408,8 +441,12 @@ struct GaussLane {
     }
 };
 
+typedef GaussLaneT<1> GaussLane;
+
 // ---- final 8-parameter fit -----------------------------------------------------------------
-struct Gauss8Lane {
+template <int C = 1>
+struct Gauss8LaneT {
+    typedef LaneGroup<C> G;
     const void* profile;
     int dtype;
     long long cand;
@@ -428,11 +465,12 @@ struct Gauss8Lane {
         cut = m_ / 2;
         carry = cy;
         finished = false;
-        for (int i = 0; i < m; ++i) {
+        for (int i = G::rank(); i < m; i += C) {
             int src = i + cut;
             if (src >= m) src -= m;
             b.d(i) = load_elem(profile, dtype, cand * (long long)m + src);
         }
+        G::sync();
         double x0[8];
         for (int k = 0; k < 4; ++k) {
             x0[k] = cy.p1[k];
@@ -468,7 +506,7 @@ struct Gauss8Lane {
 #endif
         constexpr int B = PFX_G8_BLOCK;
 #pragma unroll 1
-        for (int i0 = 0; i0 < m; i0 += B) {
+        for (int i0 = G::rank() * B; i0 < m; i0 += C * B) {
             double A[B][8], bv[B];
 #pragma unroll
             for (int r = 0; r < B; ++r) {
@@ -493,8 +531,9 @@ struct Gauss8Lane {
                     bv[r] = 0.0;
                 }
             }
-            lm.jac_block<B>(A, bv);
+            lm.template jac_block<B>(A, bv);
         }
+        lm.template jac_combine<C>();
         const int r = lm.jac_end(ws, m);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
@@ -502,10 +541,11 @@ struct Gauss8Lane {
     PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
         lm.trial_begin(ws);
         double s = 0.0;
-        for (int i = 0; i < m; ++i) {
+        for (int i = G::rank(); i < m; i += C) {
             const double f = PFX_SUB(b.d(i), value(lm.xnew, (double)i));
             s = PFX_FMA(f, f, s);
         }
+        s = G::sum(s);
         const int r = lm.trial_end(sqrt(s));
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
     }
@@ -520,7 +560,7 @@ struct Gauss8Lane {
         const double bgmix = PFX_MUL(PFX_ADD(carry.p1[3], carry.p2[3]), 0.5);
         double c = 0.0, cc = 0.0;
         // pass 1: both chi-squares
-        for (int i = 0; i < m; ++i) {
+        for (int i = G::rank(); i < m; i += C) {
             const double xv = (double)i, yv = b.d(i);
             const double fi = value(q, xv);
             if (fi >= 1.0) {
@@ -534,6 +574,8 @@ struct Gauss8Lane {
                 cc += (dlt * dlt) / (double)m;
             }
         }
+        c = G::sum(c);
+        cc = G::sum(cc);
         const bool use_final = (c <= cc);
         double fw_a, fw_b, dg_chi;
         if (use_final) {
@@ -547,7 +589,8 @@ struct Gauss8Lane {
         }
         // pass 2 and 3: std of (chosen fit) - (T1 fit + minbg - std)   (PO:755-756)
         double ds = 0.0;
-        for (int i = 0; i < m; ++i) {
+        G::sync();
+        for (int i = G::rank(); i < m; i += C) {
             const double xv = (double)i;
             const double dg = use_final ? value(q, xv)
                                         : PFX_ADD(PFX_SUB(PFX_SUB(PFX_ADD(g4_value(carry.p1, rf, xv), g4_value(carry.p2, rf, xv)),
@@ -556,12 +599,15 @@ struct Gauss8Lane {
             b.d(i) = dlt;       // the data vector is no longer needed
             ds += dlt;
         }
+        ds = G::sum(ds);
+        G::sync();
         const double dmean = ds / (double)m;
         double dv = 0.0;
-        for (int i = 0; i < m; ++i) {
+        for (int i = G::rank(); i < m; i += C) {
             const double dlt = b.d(i) - dmean;
             dv = PFX_FMA(dlt, dlt, dv);
         }
+        dv = G::sum(dv);
         const double dstd = fabs(sqrt(dv / (double)m));
         if (dstd < 3.0) s10 = carry.t1_fwhm;
         else s10 = (fw_b < fw_a) ? fw_b : fw_a;
@@ -576,5 +622,7 @@ struct Gauss8Lane {
         if (phase == GP_FIN) finish(b);
     }
 };
+
+typedef Gauss8LaneT<1> Gauss8Lane;
 
 }  // namespace pfx

@@ -33,12 +33,16 @@ namespace pfx {
 // caller to the streamed column norms of the full Jacobian.
 template <class RV, class IV>
 PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag, double* wa) {
+    PFX_ROLL
     for (int j = 0; j < n; ++j) ipvt[j] = j;
+    PFX_ROLL
     for (int j = 0; j < n; ++j) {
         int kmax = j;
+        PFX_ROLL
         for (int k = j; k < n; ++k)
             if (rdiag[k] > rdiag[kmax]) kmax = k;
         if (kmax != j) {
+            PFX_ROLL
             for (int i = 0; i < n; ++i) {
                 double t = a[i + ld * j];
                 a[i + ld * j] = a[i + ld * kmax];
@@ -51,16 +55,21 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
             ipvt[kmax] = t;
         }
         double s = 0.0;
+        PFX_ROLL
         for (int i = j; i < n; ++i) s += a[i + ld * j] * a[i + ld * j];
         double ajnorm = sqrt(s);
         if (ajnorm != 0.0) {
             if (a[j + ld * j] < 0.0) ajnorm = -ajnorm;
+            PFX_ROLL
             for (int i = j; i < n; ++i) a[i + ld * j] /= ajnorm;
             a[j + ld * j] += 1.0;
+            PFX_ROLL
             for (int k = j + 1; k < n; ++k) {
                 double sum = 0.0;
+                PFX_ROLL
                 for (int i = j; i < n; ++i) sum += a[i + ld * j] * a[i + ld * k];
                 double temp = sum / a[j + ld * j];
+                PFX_ROLL
                 for (int i = j; i < n; ++i) a[i + ld * k] -= temp * a[i + ld * j];
                 if (rdiag[k] != 0.0) {
                     temp = a[j + ld * k] / rdiag[k];
@@ -68,6 +77,7 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
                     double q = rdiag[k] / wa[k];
                     if (0.05 * (q * q) <= LM_EPSMCH) {
                         double s2 = 0.0;
+                        PFX_ROLL
                         for (int i = j + 1; i < n; ++i) s2 += a[i + ld * k] * a[i + ld * k];
                         rdiag[k] = sqrt(s2);
                         wa[k] = rdiag[k];
@@ -78,6 +88,56 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
         rdiag[j] = -ajnorm;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// C lanes of a warp share one fit (C = 1, 2, 4, ... 32).  The rows of the residual vector are
+// dealt to the C lanes, every lane accumulates the triangular factor of its own rows, and the C
+// factors are merged by a butterfly (LaneLM::jac_combine) after which all lanes of the group hold
+// bit-identical state and run the n x n sub-problem redundantly.  A slow fit then finishes C
+// times sooner (the kernels end in a tail of slow candidates) and C times more warps are
+// resident for the same shared-memory footprint.  On the host (logic check) C is 1.
+template <int C>
+struct LaneGroup {
+    static constexpr int size = C;
+#if defined(__CUDA_ARCH__)
+    PFX_HD static int rank() { return (C == 1) ? 0 : (int)(threadIdx.x & (C - 1)); }
+    PFX_HD static unsigned mask() {
+        return (C == 32) ? 0xffffffffu : (((1u << (C & 31)) - 1u) << (threadIdx.x & 31 & ~(C - 1)));
+    }
+    PFX_HD static double xchg(double v, int s) { return (C == 1) ? v : __shfl_xor_sync(mask(), v, s); }
+    PFX_HD static double bcast(double v) { return (C == 1) ? v : __shfl_sync(mask(), v, 0, C); }
+    PFX_HD static long long bcast(long long v) { return (C == 1) ? v : __shfl_sync(mask(), v, 0, C); }
+    PFX_HD static void sync() { if (C > 1) __syncwarp(mask()); }
+#else
+    // host build (logic check): groups of one lane only; nvcc's host pass merely has to parse this
+    PFX_HD static int rank() { return 0; }
+    PFX_HD static double xchg(double v, int) { return v; }
+    PFX_HD static double bcast(double v) { return v; }
+    PFX_HD static long long bcast(long long v) { return v; }
+    PFX_HD static void sync() {}
+#endif
+    // IEEE addition and max are commutative, so both partners of an exchange get the same bits
+    PFX_HD static double sum(double v) {
+#pragma unroll
+        for (int s = 1; s < C; s <<= 1) v = PFX_ADD(v, xchg(v, s));
+        return v;
+    }
+    PFX_HD static double max_gt(double v) {     // NaN-free inputs
+#pragma unroll
+        for (int s = 1; s < C; s <<= 1) {
+            const double o = xchg(v, s);
+            v = (o > v) ? o : v;
+        }
+        return v;
+    }
+    PFX_HD static int sum(int v) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int s = 1; s < C; s <<= 1) v += __shfl_xor_sync(mask(), v, s);
+#endif
+        return v;
+    }
+};
 
 enum LanePhase { LANE_JAC = 0, LANE_TRIAL = 1, LANE_DONE = 2 };
 
@@ -349,7 +409,10 @@ struct SmallLM {
 };
 
 // per-lane workspace of the n x n sub-problem: r (n x n, column major), six n-vectors, ipvt
-constexpr int LANE_BLOCK_ROWS = 8;
+#ifndef PFX_BLOCK_ROWS
+#define PFX_BLOCK_ROWS 8
+#endif
+constexpr int LANE_BLOCK_ROWS = PFX_BLOCK_ROWS;
 // r, six vectors, ipvt (one int per float64 slot), and the staged row block of the Jacobian pass
 // The staged block is only live during the row loop of a Jacobian pass and the n x n vectors only
 // after it, so they share the same storage.
@@ -433,6 +496,11 @@ struct LaneLM {
         f2 = PFX_FMA(b, b, f2);
 #pragma unroll
         for (int j = 0; j < N; ++j) acn2[j] = PFX_FMA(a[j], a[j], acn2[j]);
+        rotate_row(a, b);
+    }
+
+    // Givens rotations of one row (a, b) into the triangular factor
+    PFX_HD void rotate_row(double (&a)[N], double b) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const double aj = a[j];
@@ -455,6 +523,41 @@ struct LaneLM {
                 const double qj = q[j];
                 q[j] = PFX_FMA(c, qj, sn * b);
                 b = PFX_FMA(c, b, -sn * qj);
+            }
+        }
+    }
+
+    // Merge the factors of the C lanes of a group (each built from its own rows): log2(C)
+    // exchange steps; in each, both partners stack the factor of the lower lane on top of the
+    // factor of the upper lane and re-triangularise, so they end with the same bits.
+    template <int C>
+    PFX_HD void jac_combine() {
+        typedef LaneGroup<C> G;
+        if (C == 1) return;
+#pragma unroll 1
+        for (int s = 1; s < C; s <<= 1) {
+            const bool upper = (G::rank() & s) != 0;
+            double Ro[N * (N + 1) / 2], qo[N];
+#pragma unroll
+            for (int k = 0; k < N * (N + 1) / 2; ++k) {
+                const double o = G::xchg(R[k], s);
+                Ro[k] = upper ? R[k] : o;       // factor of the upper lane: rows to insert
+                R[k] = upper ? o : R[k];        // factor of the lower lane: the base
+            }
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const double o = G::xchg(q[k], s);
+                qo[k] = upper ? q[k] : o;
+                q[k] = upper ? o : q[k];
+                acn2[k] = PFX_ADD(acn2[k], G::xchg(acn2[k], s));
+            }
+            f2 = PFX_ADD(f2, G::xchg(f2, s));
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                double a[N];
+#pragma unroll
+                for (int j = 0; j < N; ++j) a[j] = (j >= i) ? Ro[ridx(i < j ? i : j, j)] : 0.0;
+                rotate_row(a, qo[i]);
             }
         }
     }
@@ -622,7 +725,10 @@ struct LaneLM {
 
     PFX_HD void trial_begin(const LaneWs& s) {
         double stepv[N];
-        if (N <= 4) {
+#ifndef PFX_SMALL_LM
+#define PFX_SMALL_LM 1
+#endif
+        if (PFX_SMALL_LM && N <= 4) {
             // load the sub-problem into registers, solve there
             SmallLM<N> q;
 #pragma unroll

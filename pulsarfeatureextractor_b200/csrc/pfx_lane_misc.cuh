@@ -176,8 +176,9 @@ struct SinLane {
 // =============================================================================================
 // scores 12-19                                              PHXO:81-233, PFDO:274-393, CFI:84-112
 // =============================================================================================
-template <int N>    // 3: PHCX family, 4: PFD family
+template <int N, int C = 1>    // N = 3: PHCX family, 4: PFD family; C lanes share the candidate
 struct DmLane {
+    typedef LaneGroup<C> G;
     const void* dmcurve;
     int dm_dtype;
     long long cand;
@@ -242,27 +243,32 @@ struct DmLane {
         yscale = 1.0;
         if (pfd) {
             // yData = 255./max(yData)*yData  (PFDO:332), builtin max
+            // builtin max: a NaN survives only when it is first, later ones lose every comparison;
+            // the lanes of the group scan interleaved elements and merge (max of NaN-free values)
             if (dm_dtype == PFX_F32) {
                 const float* p = (const float*)dmcurve + cand * (long long)n_dm;
                 float mx = p[0];
-                for (int i = 1; i < n_dm; ++i)
+                for (int i = 1 + G::rank(); i < n_dm; i += C)
                     if (p[i] > mx) mx = p[i];
+                if (mx == mx) mx = (float)G::max_gt((double)mx);
                 yscale = (double)(255.0f / mx);
             } else {
                 double mx = load_elem(dmcurve, dm_dtype, cand * (long long)n_dm);
-                for (int i = 1; i < n_dm; ++i) {
+                for (int i = 1 + G::rank(); i < n_dm; i += C) {
                     const double v = load_elem(dmcurve, dm_dtype, cand * (long long)n_dm + i);
                     if (v > mx) mx = v;
                 }
+                if (mx == mx) mx = G::max_gt(mx);
                 yscale = 255.0 / mx;
             }
         }
         // max(_help) with Python's builtin max: a NaN survives only when it is first
         double hmax = theo_shape(xval(0));
-        for (int i = 1; i < n_dm; ++i) {
+        for (int i = 1 + G::rank(); i < n_dm; i += C) {
             const double h = theo_shape(xval(i));
             if (h > hmax) hmax = h;
         }
+        if (hmax == hmax) hmax = G::max_gt(hmax);
         amp0 = 255.0 / hmax;
         double x0[N];
         x0[0] = amp0;
@@ -282,7 +288,7 @@ struct DmLane {
         for (int k = 0; k < N; ++k) ih[k] = 1.0 / h[k];
         const double up = (N == 4) ? x[N - 1] : 0.0;
         constexpr int B = LANE_BLOCK_ROWS;
-        for (int i0 = 0; i0 < n_dm; i0 += B) {
+        for (int i0 = G::rank() * B; i0 < n_dm; i0 += C * B) {     // blocks of rows dealt to the lanes
             const int rows = (n_dm - i0 < B) ? n_dm - i0 : B;
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) {
@@ -314,6 +320,7 @@ struct DmLane {
             }
             lm.template jac_block_staged<B>(ws.blk, rows);
         }
+        lm.template jac_combine<C>();
         const int r = lm.jac_end(ws, n_dm);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
@@ -326,10 +333,11 @@ struct DmLane {
     PFX_HD void trial_pass(const LaneWs& ws) {
         lm.trial_begin(ws);
         double s = 0.0;
-        for (int i = 0; i < n_dm; ++i) {
+        for (int i = G::rank(); i < n_dm; i += C) {
             const double f = PFX_SUB(yval(i), model(lm.xnew, xval(i)));
             s = PFX_FMA(f, f, s);
         }
+        s = G::sum(s);
         const int r = lm.trial_end(sqrt(s));
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
     }
@@ -341,18 +349,19 @@ struct DmLane {
         if (!pfd) {
             // PHXO:222-230: chi-square of the THEORETICAL curve where the FIT is >= 1
             double c = 0.0;
-            for (int i = 0; i < n_dm; ++i) {
+            for (int i = G::rank(); i < n_dm; i += C) {
                 const double xv = xval(i);
                 if (model(lm.x, xv) >= 1.0) {
                     const double d = yval(i) - PFX_MUL(amp0, theo_shape(xv));
                     c = PFX_FMA(d, d, c);
                 }
             }
+            c = G::sum(c);
             s19 = c / (double)n_dm;
         } else {
             double c = 0.0;
             int ndeg = 0;
-            for (int i = 0; i < n_dm; ++i) {
+            for (int i = G::rank(); i < n_dm; i += C) {
                 const double th = PFX_MUL(amp0, theo_shape(xval(i)));
                 if (th > 0.0) {
                     const double d = yval(i) - th;
@@ -360,6 +369,8 @@ struct DmLane {
                     ++ndeg;
                 }
             }
+            c = G::sum(c);
+            ndeg = G::sum(ndeg);
             if (ndeg == 0) {
                 status |= PFX_ST_DM_NDEG_ZERO;      // ZeroDivisionError, PFDO:385
                 s19 = NAN;

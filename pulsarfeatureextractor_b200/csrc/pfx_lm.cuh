@@ -51,6 +51,12 @@ struct LmShared {
     int pad[NPMAX];
 };
 
+// Loops of the n x n sub-problem stay rolled: the lane kernels are bound by instruction fetch (a
+// few warps per scheduler, each at its own program counter; ncu: 37% of the instruction-cache
+// requests of k_gauss_rounds missed), so a compact body that stays in the instruction cache beats
+// an unrolled one.
+#define PFX_ROLL _Pragma("unroll 1")
+
 // Strided view: element k of a small per-lane vector lives at p[k * stride].  With stride = block
 // size and the lane index folded into p, the 32 lanes of a warp touch 32 consecutive words, i.e.
 // shared-memory accesses of the lane-per-fit kernels are bank-conflict free.
@@ -58,12 +64,13 @@ template <class T>
 struct SPtr {
     T* p;
     int stride;
-    PFX_HD T& operator[](int k) const { return p[(size_t)k * stride]; }
+    PFX_HD T& operator[](int k) const { return p[k * stride]; }
 };
 
 template <class V>
 PFX_HD inline double enorm_seq(int n, V x) {
     double s = 0.0;
+    PFX_ROLL
     for (int i = 0; i < n; ++i) s += x[i] * x[i];
     return sqrt(s);
 }
@@ -71,17 +78,22 @@ PFX_HD inline double enorm_seq(int n, V x) {
 // MINPACK qrsolv on the n x n system, r column major with leading dimension NPMAX.
 template <class RV, class IV>
 PFX_HD PFX_NOINLINE void qrsolv_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, RV x, RV sdiag, RV wa) {
+    PFX_ROLL
     for (int j = 0; j < n; ++j) {
+        PFX_ROLL
         for (int i = j; i < n; ++i) r[i + ld * j] = r[j + ld * i];
         x[j] = r[j + ld * j];
         wa[j] = qtb[j];
     }
+    PFX_ROLL
     for (int j = 0; j < n; ++j) {
         int l = ipvt[j];
         if (diag[l] != 0.0) {
+            PFX_ROLL
             for (int k = j; k < n; ++k) sdiag[k] = 0.0;
             sdiag[j] = diag[l];
             double qtbpj = 0.0;
+            PFX_ROLL
             for (int k = j; k < n; ++k) {
                 if (sdiag[k] == 0.0) continue;
                 double rkk = r[k + ld * k];
@@ -99,6 +111,7 @@ PFX_HD PFX_NOINLINE void qrsolv_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qt
                 double temp = c * wa[k] + s * qtbpj;
                 qtbpj = -s * wa[k] + c * qtbpj;
                 wa[k] = temp;
+                PFX_ROLL
                 for (int i = k + 1; i < n; ++i) {
                     double rik = r[i + ld * k];
                     temp = c * rik + s * sdiag[i];
@@ -111,16 +124,20 @@ PFX_HD PFX_NOINLINE void qrsolv_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qt
         r[j + ld * j] = x[j];
     }
     int nsing = n;
+    PFX_ROLL
     for (int j = 0; j < n; ++j) {
         if (sdiag[j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa[j] = 0.0;
     }
+    PFX_ROLL
     for (int k = 0; k < nsing; ++k) {
         int j = nsing - 1 - k;
         double sum = 0.0;
+        PFX_ROLL
         for (int i = j + 1; i < nsing; ++i) sum += r[i + ld * j] * wa[i];
         wa[j] = (wa[j] - sum) / sdiag[j];
     }
+    PFX_ROLL
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
 }
 
@@ -130,20 +147,25 @@ PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb
                                    RV x, RV sdiag, RV wa1, RV wa2) {
     const double p1 = 0.1, p001 = 0.001;
     int nsing = n;
+    PFX_ROLL
     for (int j = 0; j < n; ++j) {
         wa1[j] = qtb[j];
         if (r[j + ld * j] == 0.0 && nsing == n) nsing = j;
         if (nsing < n) wa1[j] = 0.0;
     }
+    PFX_ROLL
     for (int k = 0; k < nsing; ++k) {
         int j = nsing - 1 - k;
         wa1[j] = wa1[j] / r[j + ld * j];
         double temp = wa1[j];
+        PFX_ROLL
         for (int i = 0; i < j; ++i) wa1[i] -= r[i + ld * j] * temp;
     }
+    PFX_ROLL
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa1[j];
 
     int iter = 0;
+    PFX_ROLL
     for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
     double dxnorm = enorm_seq(n, wa2);
     double fp = dxnorm - delta;
@@ -153,20 +175,25 @@ PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb
     }
     double parl = 0.0;
     if (nsing >= n) {
+        PFX_ROLL
         for (int j = 0; j < n; ++j) {
             int l = ipvt[j];
             wa1[j] = diag[l] * (wa2[l] / dxnorm);
         }
+        PFX_ROLL
         for (int j = 0; j < n; ++j) {
             double sum = 0.0;
+            PFX_ROLL
             for (int i = 0; i < j; ++i) sum += r[i + ld * j] * wa1[i];
             wa1[j] = (wa1[j] - sum) / r[j + ld * j];
         }
         double temp = enorm_seq(n, wa1);
         parl = ((fp / delta) / temp) / temp;
     }
+    PFX_ROLL
     for (int j = 0; j < n; ++j) {
         double sum = 0.0;
+        PFX_ROLL
         for (int i = 0; i <= j; ++i) sum += r[i + ld * j] * qtb[i];
         wa1[j] = sum / diag[ipvt[j]];
     }
@@ -176,24 +203,30 @@ PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb
     par = fmax(par, parl);
     par = fmin(par, paru);
     if (par == 0.0) par = gnorm / dxnorm;
+    PFX_ROLL
     for (;;) {
         ++iter;
         if (par == 0.0) par = fmax(LM_DWARF, p001 * paru);
         double temp = sqrt(par);
+        PFX_ROLL
         for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
         qrsolv_seq(n, ld, r, ipvt, wa1, qtb, x, sdiag, wa2);
+        PFX_ROLL
         for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
         dxnorm = enorm_seq(n, wa2);
         temp = fp;
         fp = dxnorm - delta;
         if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        PFX_ROLL
         for (int j = 0; j < n; ++j) {
             int l = ipvt[j];
             wa1[j] = diag[l] * (wa2[l] / dxnorm);
         }
+        PFX_ROLL
         for (int j = 0; j < n; ++j) {
             wa1[j] = wa1[j] / sdiag[j];
             double t = wa1[j];
+            PFX_ROLL
             for (int i = j + 1; i < n; ++i) wa1[i] -= r[i + ld * j] * t;
         }
         temp = enorm_seq(n, wa1);

@@ -90,7 +90,7 @@ class Engine(object):
 
     def set_stage_timing(self, on):
         """Serialise and time the score groups of score_device (see pfx_set_stage_timing)."""
-        self._check(self._lib.pfx_set_stage_timing(self._h, 1 if on else 0))
+        self._check(self._lib.pfx_set_stage_timing(self._h, int(on)))
 
     def last_timing(self):
         t = _lib.Timing()
