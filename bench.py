@@ -35,8 +35,6 @@ CONFIG_ID = 2
 BYTES_IN = NBIN + NSUB * NBIN + NDM + NDMSTAT + 8 * 8
 BYTES_OUT = 30 * 8 + 18 + 4
 BYTES_PER_CAND = BYTES_IN + BYTES_OUT
-# ncu --set full of the dominant kernel pair (profiles/r01_rounds_r1d_summary.csv): DRAM bytes per
-# candidate actually moved by k_gauss_rounds (profile row + per-lane scratch spill-over past L2)
 LYON_N = 4_000_000            # candidates of the secondary, HBM-bound roofline entry
 LYON_BYTES_PER_CAND = NBIN + NDMSTAT + 64
 
@@ -313,12 +311,16 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_gauss_rounds + k_gauss_final (scores 8-11, 10 LM solves per candidate)",
                          "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": n * 337.7,
                          "kernel_ms": gauss_ms, "kernel_share_of_step": gauss_ms / (ms_dev / args.steps),
                          "whole_step_gbs": step_gbs, "whole_step_frac": step_gbs / peak,
                          "note": "the Bates path is FP64/latency bound (~1e3 flop per input byte, 10 Levenberg-"
                                  "Marquardt solves per candidate in this kernel pair), so its HBM fraction is "
-                                 "tiny by construction; the HBM-bound kernel of the path is reported in roofline_lyon"},
+                                 "tiny by construction; the HBM-bound kernel of the path is reported in roofline_lyon. "
+                                 "traffic: ncu dram read+write of k_gauss_rounds at 100k candidates, 337.7 B/candidate "
+                                 "(profiles/r01_gauss_final_build_summary.csv: profile row in, carry record and scores "
+                                 "out; no re-reads); same capture: issue slots 25.7% busy, FP64 pipe 19.8%, 14.9 of 32 "
+                                 "lanes active per instruction, top stall = fixed-latency dependency (wait)"},
             "roofline_lyon": lyon_roof,
             "stage_ms_serialised": {k: v for k, v in stage.items() if k != "launches"},
             "stage_done_ms_overlapped": {k: v for k, v in trace.items() if k not in ("launches", "subband")},

@@ -5,6 +5,9 @@
 // magnitude between candidates (most converge in a handful of iterations, some run to maxfev), so
 // a whole warp shares each candidate (DM_LANES = 32): the rows are dealt to the lanes and the
 // kernel no longer ends in a long tail of single lanes finishing slow fits.
+// the n x n trust-region solve runs from the rolled shared-memory routines here (smaller code;
+// measured slightly faster than the register-resident SmallLM for this kernel)
+#define PFX_SMALL_LM 0
 #include "pfx_internal.cuh"
 #include "pfx_lane_misc.cuh"
 
@@ -12,7 +15,10 @@ using namespace pfx;
 
 namespace {
 
-constexpr int DM_LANES = 32;
+#ifndef PFX_DM_LANES
+#define PFX_DM_LANES 32
+#endif
+constexpr int DM_LANES = PFX_DM_LANES;
 
 template <int N>
 __global__ void __launch_bounds__(128, 3)

@@ -185,14 +185,15 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
 // block (multiple of 32 lanes, at most max_threads) whose groups fit with their data vectors in
 // shared memory.  Returns false when not even two warps fit (long profiles): the data vectors then
 // go to the global scratch and only the n x n workspaces stay in shared memory.
-static bool lane_layout(pfx_ctx* ctx, int m, int np, int lanes_per_cand, int max_threads, int* threads, size_t* smem) {
-    const size_t ws = (size_t)lane_ws_doubles(np) * 8;
+static bool lane_layout(pfx_ctx* ctx, int m, int np, int lanes_per_cand, int max_threads, int extra_doubles,
+                        int* threads, size_t* smem) {
+    const size_t ws = (size_t)lane_ws_doubles(np) * 8 + (size_t)extra_doubles * 8;
     const size_t per_group = ws * lanes_per_cand + (size_t)m * 10;
     const size_t budget = (size_t)ctx->smem_optin;
     for (int t = max_threads; t >= 64; t -= 32) {
         if (per_group * (t / lanes_per_cand) + 64 <= budget) {
             *threads = t;
-            *smem = (per_group * (t / lanes_per_cand) + 15) / 16 * 16;
+            *smem = (per_group * (t / lanes_per_cand) + 64 + 15) / 16 * 16;
             return true;
         }
     }
@@ -247,7 +248,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     {
         int threads;
         size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, &threads, &smem);
+        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, 0, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
         if (rc) return rc;
         const int per_block = threads / ROUNDS_LANES;
@@ -265,7 +266,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     {
         int threads;
         size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, &threads, &smem);
+        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, 0, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
         if (rc) return rc;
         const int per_block = threads / FINAL_LANES;

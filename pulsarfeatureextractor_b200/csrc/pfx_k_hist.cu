@@ -4,6 +4,9 @@
 // memory, or in the warp's global scratch slot when it has more bins than fit there.
 // The expectation of the profile-histogram fit, needed by scores 8-11, is parked in the score-8
 // column of the feature row; the next kernel (pfx_k_gauss.cu) consumes it.
+// the n x n trust-region solve runs from the rolled shared-memory routines here (smaller code;
+// measured slightly faster than the register-resident SmallLM for this kernel)
+#define PFX_SMALL_LM 0
 #include "pfx_internal.cuh"
 #include "pfx_lane_hist.cuh"
 
@@ -123,6 +126,9 @@ int pfx::launch_hist(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* pr
         int lgrid;
         rc = persistent_grid(ctx, k_hist_lane, threads, lsmem, &lgrid);
         if (rc) return rc;
+#if defined(PFX_HIST_BLOCKS_PER_SM)
+        if (lgrid > PFX_HIST_BLOCKS_PER_SM * ctx->sm_count) lgrid = PFX_HIST_BLOCKS_PER_SM * ctx->sm_count;
+#endif
         if ((long long)lgrid * threads > n) lgrid = (int)((n + threads - 1) / threads);
         const size_t lanes = (size_t)lgrid * threads;
         const int par = ctx->counter_slot & 1;

@@ -1,5 +1,6 @@
 // pfx_k_sinusoid.cu -- scores 1-4 (ProfileOperations.py:190-587): profile statistics, peak count and
-// the sine / sine-squared fits, one lane per candidate (state machine of pfx_lane_misc.cuh).
+// the sine / sine-squared fits, a group of four lanes per candidate (LaneGroup; state machine of
+// pfx_lane_misc.cuh).
 #include "pfx_internal.cuh"
 #include "pfx_lane_misc.cuh"
 
@@ -7,28 +8,38 @@ using namespace pfx;
 
 namespace {
 
+#ifndef PFX_SIN_LANES
+#define PFX_SIN_LANES 4
+#endif
+constexpr int SIN_LANES = PFX_SIN_LANES;      // lanes per candidate (LaneGroup)
+
 __global__ void __launch_bounds__(128, 3)
 k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
            int8_t* ier, u64* counter) {
     extern __shared__ double smem[];
     LaneWs ws;
     ws.carve(smem + threadIdx.x, blockDim.x, 2);
-    SinLane g;
+    typedef LaneGroup<SIN_LANES> G;
+    SinLaneT<SIN_LANES> g;
     g.phase = GP_IDLE;
     g.cand = -1;
     bool more = true;
     for (;;) {
         if (g.phase == GP_IDLE) {
             if (g.cand >= 0) {
-                g.write(feat + g.cand * ld);
-                if (ier) {
-                    ier[g.cand * PFX_NIER + PFX_FIT_SINE] = g.ier[0];
-                    ier[g.cand * PFX_NIER + PFX_FIT_SINESQ] = g.ier[1];
+                if (G::rank() == 0) {
+                    g.write(feat + g.cand * ld);
+                    if (ier) {
+                        ier[g.cand * PFX_NIER + PFX_FIT_SINE] = g.ier[0];
+                        ier[g.cand * PFX_NIER + PFX_FIT_SINESQ] = g.ier[1];
+                    }
                 }
                 g.cand = -1;
             }
             if (more) {
-                const long long c = (long long)atomicAdd(counter, 1ULL);
+                long long c = 0;
+                if (G::rank() == 0) c = (long long)atomicAdd(counter, 1ULL);
+                c = G::bcast(c);
                 if (c < n) g.start(profile, dtype, c, m);
                 else more = false;
             }
@@ -50,7 +61,8 @@ int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void
     int grid;
     int rc = persistent_grid(ctx, k_sinusoid, threads, smem, &grid);
     if (rc) return rc;
-    if ((long long)grid * threads > n) grid = (int)((n + threads - 1) / threads);
+    const int per_block = threads / SIN_LANES;
+    if ((long long)grid * per_block > n) grid = (int)((n + per_block - 1) / per_block);
     k_sinusoid<<<grid, threads, smem, st>>>(profile, s->dtype, n, s->nbin, feat, ld, ier,
                                              take_counter(ctx, ck, st));
     PFX_CUDA(ctx, cudaGetLastError());

@@ -72,6 +72,38 @@ PFX_HD inline double g4_value(const double (&p)[4], G4Flags fl, double xv) {
     return e.value(xv);
 }
 
+// one Jacobian row of the 4-parameter family: residual f0 and the four forward differences.  Three
+// exponentials per row (the max and background columns reuse the base exponential, which gives
+// bit-identical values to re-evaluating the model).  The constants are prepared once per pass.
+struct G4Jac {
+    double isg, isgh, mu, muh, amx, amxh, bg, bgh, ih0, ih1, ih2, ih3;
+    PFX_HD void set(const double* x, const double* h, G4Flags fl) {
+        isg = 1.0 / (fl.abs_sigma ? fabs(x[0]) : x[0]);
+        isgh = 1.0 / (fl.abs_sigma ? fabs(x[0] + h[0]) : (x[0] + h[0]));
+        mu = x[1];
+        muh = x[1] + h[1];
+        amx = fabs(x[2]);
+        amxh = fabs(x[2] + h[2]);
+        bg = fl.abs_bg ? fabs(x[3]) : x[3];
+        bgh = fl.abs_bg ? fabs(x[3] + h[3]) : (x[3] + h[3]);
+        ih0 = 1.0 / h[0];
+        ih1 = 1.0 / h[1];
+        ih2 = 1.0 / h[2];
+        ih3 = 1.0 / h[3];
+    }
+    PFX_HD void row(double xv, double yv, double& a0, double& a1, double& a2, double& a3, double& f0) const {
+        const double e0 = gauss_fast(xv, mu, isg);
+        const double e1 = gauss_fast(xv, mu, isgh);
+        const double e2 = gauss_fast(xv, muh, isg);
+        const double base = PFX_MUL(amx, e0);
+        f0 = PFX_SUB(yv, PFX_ADD(base, bg));
+        a0 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e1), bg)) - f0) * ih0;
+        a1 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e2), bg)) - f0) * ih1;
+        a2 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) * ih2;
+        a3 = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) * ih3;
+    }
+};
+
 // C lanes of a warp share the candidate (LaneGroup): one copy of the data vector per group.
 // Element-wise passes over the data are dealt to the lanes (element i to lane i % C) and closed
 // by a group barrier; order-sensitive scans (sequential sums, argmax, the index-list surgery of
@@ -308,45 +340,19 @@ struct GaussLaneT {
         return len;
     }
 
-    // one Jacobian pass: three exponentials per row (the max and background columns reuse the
-    // base exponential, which gives bit-identical values to re-evaluating the model)
+    // one Jacobian pass; rows are produced into the staged block and eliminated eight at a time
     PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
         lm.jac_begin();
-        const double* x = lm.x;
-        const double* h = lm.h;
-        const double isg = 1.0 / (fl.abs_sigma ? fabs(x[0]) : x[0]);
-        const double isgh = 1.0 / (fl.abs_sigma ? fabs(x[0] + h[0]) : (x[0] + h[0]));
-        const double mu = x[1], muh = x[1] + h[1];
-        const double amx = fabs(x[2]), amxh = fabs(x[2] + h[2]);
-        const double bg = fl.abs_bg ? fabs(x[3]) : x[3];
-        const double bgh = fl.abs_bg ? fabs(x[3] + h[3]) : (x[3] + h[3]);
-        const double ih0 = 1.0 / h[0], ih1 = 1.0 / h[1], ih2 = 1.0 / h[2], ih3 = 1.0 / h[3];
-        // rows are produced two at a time (six independent exponentials in flight) into the staged
-        // block and eliminated eight at a time
+        G4Jac J;
+        J.set(lm.x, lm.h, fl);
         constexpr int B = LANE_BLOCK_ROWS;
         for (int i0 = G::rank() * B; i0 < nrows; i0 += C * B) {     // blocks of rows dealt to the lanes
             const int rows = (nrows - i0 < B) ? nrows - i0 : B;
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) {
                 const int i = i0 + r;
-                const double xv = (double)b.x(i), yv = b.d(i);
-                const double e0 = gauss_fast(xv, mu, isg);
-                const double e1 = gauss_fast(xv, mu, isgh);
-                const double e2 = gauss_fast(xv, muh, isg);
-                const double base = PFX_MUL(amx, e0);
-                const double f0 = PFX_SUB(yv, PFX_ADD(base, bg));
-                const double a0 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e1), bg)) - f0) * ih0;
-                const double a1 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amx, e2), bg)) - f0) * ih1;
-                const double a2 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) * ih2;
-                const double a3 = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) * ih3;
-#if defined(PFX_GIVENS_ROWS)
-                // one row at a time with Givens rotations: the whole row loop is a few hundred
-                // instructions and stays in the L0 instruction cache
-                double a[4] = {a0, a1, a2, a3};
-                lm.jac_row(a, f0);
-            }
-        }
-#else
+                double a0, a1, a2, a3, f0;
+                J.row((double)b.x(i), b.d(i), a0, a1, a2, a3, f0);
                 lm.acn2[0] = PFX_FMA(a0, a0, lm.acn2[0]);
                 lm.acn2[1] = PFX_FMA(a1, a1, lm.acn2[1]);
                 lm.acn2[2] = PFX_FMA(a2, a2, lm.acn2[2]);
@@ -360,7 +366,6 @@ struct GaussLaneT {
             }
             lm.template jac_block_staged<B>(ws.blk, rows);
         }
-#endif
         lm.template jac_combine<C>();
         const int r = lm.jac_end(ws, nrows);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
@@ -439,6 +444,7 @@ struct GaussLaneT {
         if (phase == GP_TRIAL) trial_pass(b, ws);
         if (phase == GP_FIN) finish(b);
     }
+
 };
 
 typedef GaussLaneT<1> GaussLane;

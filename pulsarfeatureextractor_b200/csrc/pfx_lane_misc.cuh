@@ -1,8 +1,8 @@
-// pfx_lane_misc.cuh -- one lane per candidate for scores 1-4 (two sinusoid fits) and scores 12-19
-// (DM-curve fit).  Same execution model as pfx_lane_gauss.cuh: a per-lane state machine whose trip
-// is "one Jacobian pass + one trial point"; the data row of a candidate is read straight from the
-// input arrays (a lane walks its own row, which stays in L1), only the small trust-region
-// workspace lives in shared memory.
+// pfx_lane_misc.cuh -- lane state machines for scores 1-4 (two sinusoid fits) and scores 12-19
+// (DM-curve fit).  Same execution model as pfx_lane_gauss.cuh: a trip is "one Jacobian pass + one
+// trial point"; a candidate belongs to a group of C lanes (LaneGroup, pfx_lane_lm.cuh) that share
+// its rows; the data row is read straight from the input arrays (it stays in L1), only the small
+// trust-region workspace lives in shared memory.
 #pragma once
 
 #include "pfx_driver.cuh"
@@ -13,7 +13,12 @@ namespace pfx {
 // =============================================================================================
 // scores 1-4                                                                   PO:190-587
 // =============================================================================================
-struct SinLane {
+// C lanes share the candidate (LaneGroup): the profile statistics of setup() are computed by every
+// lane redundantly in the reference's order (scores 3 and 4 are exact), the rows of the two fits
+// and of the chi-squares are dealt to the lanes.
+template <int C = 1>
+struct SinLaneT {
+    typedef LaneGroup<C> G;
     const void* profile;
     int dtype;
     long long cand;
@@ -107,7 +112,7 @@ struct SinLane {
         const double p0 = lm.x[1], p1 = lm.x[1] + lm.h[1];
         const double ih0 = 1.0 / lm.h[0], ih1 = 1.0 / lm.h[1];
         constexpr int B = LANE_BLOCK_ROWS;
-        for (int i0 = 0; i0 < m; i0 += B) {
+        for (int i0 = G::rank() * B; i0 < m; i0 += C * B) {
             const int rows = (m - i0 < B) ? m - i0 : B;
 #pragma unroll 1
             for (int r = 0; r < rows; ++r) {
@@ -123,8 +128,9 @@ struct SinLane {
                 ws.blk[r * 3 + 1] = a1;
                 ws.blk[r * 3 + 2] = f0;
             }
-            lm.jac_block_staged<B>(ws.blk, rows);
+            lm.template jac_block_staged<B>(ws.blk, rows);
         }
+        lm.template jac_combine<C>();
         const int r = lm.jac_end(ws, m);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
@@ -133,10 +139,11 @@ struct SinLane {
         lm.trial_begin(ws);
         const double w = PFX_MUL(TWO_PI, lm.xnew[0]), ph = lm.xnew[1];
         double s = 0.0;
-        for (int i = 0; i < m; ++i) {
+        for (int i = G::rank(); i < m; i += C) {
             const double f = resid(w, ph, i, y(i));
             s = PFX_FMA(f, f, s);
         }
+        s = G::sum(s);
         const int r = lm.trial_end(sqrt(s));
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
     }
@@ -146,13 +153,14 @@ struct SinLane {
         // chi-square against the evaluated curve A sin(..) + bg resp. A sin^2(..) + bg (PO:425,529)
         const double w = PFX_MUL(TWO_PI, lm.x[0]), ph = lm.x[1];
         double c = 0.0;
-        for (int i = 0; i < m; ++i) {
+        for (int i = G::rank(); i < m; i += C) {
             const double sn = sin(PFX_ADD(PFX_MUL(w, (double)i), ph));
             const double fit = (stage == 0) ? PFX_ADD(PFX_MUL(half, sn), half)
                                             : PFX_ADD(PFX_MUL(half, PFX_MUL(sn, sn)), half);
             const double d = y(i) - fit;
             c = PFX_FMA(d, d, c);
         }
+        c = G::sum(c);
         chi[stage] = c / (double)m;
         ++stage;
         phase = (stage > 1) ? GP_IDLE : GP_SETUP;
@@ -172,6 +180,8 @@ struct SinLane {
         feat[3] = s4;
     }
 };
+
+typedef SinLaneT<1> SinLane;
 
 // =============================================================================================
 // scores 12-19                                              PHXO:81-233, PFDO:274-393, CFI:84-112

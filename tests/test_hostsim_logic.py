@@ -23,7 +23,7 @@ import pfx_oracle as O
 from pulsarfeatureextractor_b200 import synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "hostsim", "_hostsim.so")
+SO = os.environ.get("PFX_HOSTSIM_SO") or os.path.join(HERE, "hostsim", "_hostsim.so")
 
 
 @pytest.fixture(scope="module")
@@ -33,7 +33,7 @@ def hs():
            for f in ("pfx_group.cuh", "pfx_lm.cuh", "pfx_scores.cuh", "pfx_driver.cuh", "pfx_lane_lm.cuh",
                      "pfx_lane_gauss.cuh", "pfx_lane_misc.cuh")]
     if (not os.path.isfile(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in src):
-        subprocess.check_call(["sh", os.path.join(HERE, "hostsim", "build.sh")])
+        subprocess.check_call(["sh", os.path.join(HERE, "hostsim", "build.sh")] + (["asan"] if SO.endswith("_asan.so") else []))
     lib = ctypes.CDLL(SO)
     for f in ("hs_gaussian", "hs_dmfit", "hs_subband", "hs_hist", "hs_gauss_lane", "hs_dm_lane"):
         getattr(lib, f).restype = ctypes.c_uint
