@@ -28,11 +28,19 @@ int pfx::launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void*
                           int32_t* status, cudaStream_t st, int ck) {
     if (s->nsub < 1 || s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "bad sub-band shape");
     const int wd = align_up(sub_work_doubles(s->nbin, s->nsub), 2);
-    const size_t smem = (size_t)wd * 8 * GROUPS_PER_BLOCK;
+    // the box-car sums of one candidate (nsub x nbin float64) live in shared memory; as many warps
+    // per block as fit (HTRU 16 x 128: four; survey 16 x 1024: one)
+    int warps = GROUPS_PER_BLOCK;
+    while (warps > 1 && (size_t)wd * 8 * warps > (size_t)ctx->smem_optin) warps >>= 1;
+    const size_t smem = (size_t)wd * 8 * warps;
+    if (smem > (size_t)ctx->smem_optin)
+        return set_err(ctx, PFX_ERR_UNSUPPORTED, "sub-bands %d x %d need %zu bytes of shared memory per candidate, limit %d",
+                       s->nsub, s->nbin, smem, ctx->smem_optin);
+    const int threads = warps * WARP;
     int grid;
-    int rc = persistent_grid(ctx, k_subband, BLOCK_THREADS, smem, &grid);
+    int rc = persistent_grid(ctx, k_subband, threads, smem, &grid);
     if (rc) return rc;
-    k_subband<<<grid, BLOCK_THREADS, smem, st>>>(profile, subbands, s->dtype, n, s->nbin, s->nsub, params, feat,
+    k_subband<<<grid, threads, smem, st>>>(profile, subbands, s->dtype, n, s->nbin, s->nsub, params, feat,
                                                   ld, status, take_counter(ctx, ck, st), wd);
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;

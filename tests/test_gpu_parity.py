@@ -238,6 +238,44 @@ def test_pfd_family_shape(eng):
         O.FAST_CORR = False
 
 
+def test_survey_shape_1024_bins(eng):
+    """BASELINE configs[4] shape: 1024-bin uint8 profiles.  The data vectors of the Gaussian lane
+    kernels no longer fit in shared memory (global scratch layout) and the histograms are larger;
+    checked against the oracle like the HTRU batch, plus host path == device path."""
+    warnings.simplefilter("ignore")
+    n = 40
+    b = synth.generate(5, 0, n, nbin=1024)
+    feat, status, ier = _dev(eng, b)
+    O.FAST_CORR = True
+    try:
+        nok = 0
+        good = {0: 0, 7: 0, 8: 0}
+        for i in range(n):
+            r = O.bates22_phcx(b.profile[i].astype(np.int64), b.subbands[i].astype(np.int64),
+                               b.dmcurve[i].astype(np.int64), b.params[i])
+            assert (r.status & O.ST_FAIL_MASK) == (status[i] & O.ST_FAIL_MASK), (i, hex(r.status), hex(status[i]))
+            assert _rel(O.lyon8(b.profile[i], b.dmstat[i]), feat[i, 22:30]).max() <= 1e-9
+            if r.status & O.ST_FAIL_MASK:
+                continue
+            nok += 1
+            assert feat[i, 2] == r.features[2]
+            for k in DET:
+                assert _det_ok(r.features[k], feat[i, k]), (i, k + 1, r.features[k], feat[i, k])
+            e = _rel(r.features, feat[i, :22])
+            for k in good:
+                good[k] += int(e[k] <= 1e-6)
+        assert nok >= 20
+        # least-squares columns: most candidates agree to 1e-6 (the rest sit on the noise floor the
+        # HTRU test quantifies with the oracle's twins)
+        for k, c in good.items():
+            assert c >= 0.7 * nok, (k + 1, c, nok)
+    finally:
+        O.FAST_CORR = False
+    h = eng.score_host(b.profile, b.subbands, b.dmcurve, b.dmstat, b.params, features="all", chunk=16)
+    assert np.array_equal(h.features, feat, equal_nan=True)
+    assert np.array_equal(h.status, status) and np.array_equal(h.ier, ier)
+
+
 def test_pfd_params_on_device(eng):
     """S/N (3-sigma clipped) and half-maximum width derived from the profile, PFDOperations.py:130-231.
     The S/N cancels to rounding noise when nothing is clipped and its sign picks 0.1 or ~1e-15, so the
