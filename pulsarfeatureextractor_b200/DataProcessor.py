@@ -121,8 +121,27 @@ class DataProcessor(object):
         eng = self._engine()
         for lo in range(0, len(paths), self.batch):
             chunk = paths[lo:lo + self.batch]
-            cands, keep = [], []
             results = [None] * len(chunk)
+            if phcx_io.native_available() and not any(".pfd" in p for p in chunk):
+                # bulk path: native scanner, rows gathered per shape into pinned buffers
+                scan = phcx_io.Scan(chunk)
+                groups = {}
+                for k in range(len(chunk)):
+                    if scan.ok(k):
+                        groups.setdefault(scan.shape_key(k), []).append(k)
+                    else:
+                        print("Error reading profile data :\n\t", chunk[k])
+                for _key, ks in groups.items():
+                    prof, sub, dmc, dms, par = scan.gather(ks)
+                    out = eng.score_host(prof, sub, dmc, dms, par, features=features)
+                    ok = out.ok() if features != "lyon" else np.ones(len(ks), dtype=bool)
+                    for j, k in enumerate(ks):
+                        results[k] = out.features[j] if ok[j] else None
+                scan.close()
+                for p, r in zip(chunk, results):
+                    yield p, r
+                continue
+            cands, keep = [], []
             for k, p in enumerate(chunk):
                 try:
                     c = Candidate(p, p)

@@ -3,9 +3,12 @@ PHCX candidate files: writer for synthetic candidates and the host-side packer (
 
 The reference reads a candidate with ``gzip`` + ``xml.dom.minidom`` and per-character Python
 hex loops (PHCXFile.py:90-186, PHCXOperations.py:172-182,237-297,353-383) and, for the Lyon
-statistics, parses every file twice (Candidate.py:218,277).  Here a file is scanned once with
-compiled regular expressions and ``bytes.fromhex`` straight into rows of a pinned
-structure-of-arrays batch.  Quirks kept:
+statistics, parses every file twice (Candidate.py:218,277).  Here a file is scanned once.  Two
+readers with the same behaviour: ``Scan`` drives the native multi-threaded scanner (libpfxio.so,
+include/pfx_io.h: zlib inflate -> tag scan -> hex decode, rows gathered into pinned
+structure-of-arrays buffers) and is what DataProcessor uses for bulk work; ``read_phcx`` is the
+single-file reader in Python (compiled regular expressions and ``bytes.fromhex``) behind the
+Candidate facade.  tests/test_abi_and_io.py holds the two against each other.  Quirks kept:
 
 * section index 1 for HTRU ``.phcx.gz`` and 0 for SUPERB ``.phcx``
   (PHCXFile.py:80, SUPERBPHCXFile.py:80); the Lyon DM statistics always use DataBlock[0]
@@ -17,10 +20,101 @@ structure-of-arrays batch.  Quirks kept:
 * hex decoding skips new-lines and stops at the first pair that is not hexadecimal
   (PHCXFile.py:166-184).
 """
+import ctypes
 import gzip
+import os
 import re
 
 import numpy as np
+
+# ---- native scanner (include/pfx_io.h, csrc/pfx_phcx.cpp) ------------------------------------
+_IO_PATH = os.environ.get("PFX_IO_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpfxio.so")
+IO_EXPORTS = ["pfx_phcx_scan", "pfx_phcx_gather", "pfx_phcx_free", "pfx_io_version"]
+_io = None
+
+
+class PhcxInfo(ctypes.Structure):
+    _fields_ = [("ok", ctypes.c_int32), ("nbin", ctypes.c_int32), ("nsub", ctypes.c_int32),
+                ("n_dm", ctypes.c_int32), ("n_dmstat", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("params", ctypes.c_double * 8)]
+
+
+def native_available():
+    return os.path.isfile(_IO_PATH)
+
+
+def _load_io():
+    global _io
+    if _io is None:
+        lib = ctypes.CDLL(_IO_PATH)
+        vp, i64 = ctypes.c_void_p, ctypes.c_int64
+        lib.pfx_phcx_scan.argtypes = [ctypes.POINTER(ctypes.c_char_p), i64, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(PhcxInfo), ctypes.POINTER(vp)]
+        lib.pfx_phcx_gather.argtypes = [vp, ctypes.POINTER(i64), i64, vp, vp, vp, vp, vp]
+        lib.pfx_phcx_free.argtypes = [vp]
+        lib.pfx_io_version.restype = ctypes.c_char_p
+        _io = lib
+    return _io
+
+
+class Scan(object):
+    """Result of scanning a list of PHCX files with the native reader: per-file ``ok`` and shape,
+    and ``gather(indices)`` -> (profile, subbands, dmcurve, dmstat, params) rows of files that
+    share a shape, written straight into pinned host arrays when torch is importable."""
+
+    def __init__(self, paths, section=-1, threads=0):
+        lib = _load_io()
+        n = len(paths)
+        arr = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        self.info = (PhcxInfo * n)()
+        self._h = ctypes.c_void_p()
+        if lib.pfx_phcx_scan(arr, n, int(section), int(threads), self.info, ctypes.byref(self._h)) != 0:
+            raise RuntimeError("pfx_phcx_scan failed")
+        self.n = n
+
+    def ok(self, i):
+        return bool(self.info[i].ok)
+
+    def shape_key(self, i):
+        f = self.info[i]
+        return (f.nbin, f.nsub, f.n_dm, f.n_dmstat)
+
+    @staticmethod
+    def _buffer(shape, dtype):
+        try:
+            import torch
+            t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name),
+                            pin_memory=torch.cuda.is_available())
+            return t.numpy()
+        except ImportError:
+            return np.empty(shape, dtype=dtype)
+
+    def gather(self, indices):
+        lib = _load_io()
+        k = len(indices)
+        nbin, nsub, n_dm, n_dms = self.shape_key(indices[0])
+        prof = self._buffer((k, nbin), np.uint8)
+        sub = self._buffer((k, nsub, nbin), np.uint8)
+        dmc = self._buffer((k, n_dm), np.uint8)
+        dms = self._buffer((k, n_dms), np.uint8)
+        par = self._buffer((k, 8), np.float64)
+        idx = (ctypes.c_int64 * k)(*indices)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rc = lib.pfx_phcx_gather(self._h, idx, k, p(prof), p(sub), p(dmc), p(dms), p(par))
+        if rc != 0:
+            raise RuntimeError("pfx_phcx_gather failed (%d)" % rc)
+        return prof, sub, dmc, dms, par
+
+    def close(self):
+        if self._h:
+            _load_io().pfx_phcx_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001 - interpreter shutdown
+            pass
 
 _HEX_RE = re.compile(rb"^(?:[0-9A-Fa-f]{2})*")
 

@@ -2,7 +2,7 @@
 10 M candidates, configs[3] PFD shape, configs[4] survey 1024-bin shape) on one B200.  Seeded
 synthetic data of the stated shapes; a few thousand generated candidates are tiled to the batch
 size (host generation of millions of candidates would dominate the run).  Prints one JSON line
-per config.  usage: python scripts/gpu_configs.py [lyon] [pfd] [survey]"""
+per config.  usage: python scripts/gpu_configs.py [cli] [lyon] [pfd] [survey]"""
 import json
 import os
 import sys
@@ -18,7 +18,7 @@ from pulsarfeatureextractor_b200.engine import Engine
 
 dev = torch.device("cuda", 0)
 eng = Engine(0)
-which = sys.argv[1:] or ["lyon", "pfd", "survey"]
+which = sys.argv[1:] or ["cli", "lyon", "pfd", "survey"]
 
 
 def timed(fn, reps):
@@ -37,6 +37,49 @@ def tile(a, n):
     reps = (n + a.shape[0] - 1) // a.shape[0]
     return np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:n])
 
+
+if "cli" in which:
+    # configs[0]: Lyon-8 (and Bates-22) through the CLI classes on 1 000 synthetic HTRU .phcx.gz files:
+    # directory walk, gunzip + scan, scoring, CSV rows; reading reported separately
+    import shutil
+    import tempfile
+    from pulsarfeatureextractor_b200 import phcx_io
+    from pulsarfeatureextractor_b200.DataProcessor import DataProcessor
+    nfiles = 1000
+    b = synth.generate(1, 0, nfiles)
+    d = tempfile.mkdtemp(prefix="pfx_cli_")
+    for i in range(nfiles):
+        phcx_io.write_phcx(os.path.join(d, "cand_%05d.phcx.gz" % i), b.profile[i], b.subbands[i], b.dmcurve[i],
+                           b.dmstat[i], b.params[i])
+    paths = sorted(os.path.join(d, f) for f in os.listdir(d))
+    t0 = time.perf_counter()
+    sc = phcx_io.Scan(paths)
+    t_native = time.perf_counter() - t0
+    sc.close()
+    t0 = time.perf_counter()
+    for p_ in paths[:200]:
+        phcx_io.read_phcx(p_)
+    t_python = (time.perf_counter() - t0) * nfiles / 200
+    res = {"config": "configs[0] CLI on %d synthetic .phcx.gz files" % nfiles, "files": nfiles,
+           "read_native_scanner_s": t_native, "read_python_reader_s": t_python, "host_threads": os.cpu_count()}
+    import contextlib
+    import io
+    for feats, method in (("lyon", "dmprofPHCX"), ("bates", "processPHCXCollectively")):
+        out = os.path.join(d, "scores_%s.csv" % feats)
+        dp = DataProcessor(engine=eng, features=feats, error_log=os.path.join(d, "CandidateErrorLog.txt"))
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            if feats == "lyon":
+                dp.dmprofPHCX(d, False, out, False, False)
+            else:
+                dp.processPHCXCollectively(d, False, out, False, False, False)
+            dt = time.perf_counter() - t0
+        rows = sum(1 for _ in open(out))
+        res["cli_%s_s" % feats] = dt
+        res["cli_%s_files_per_s" % feats] = nfiles / dt
+        res["cli_%s_rows" % feats] = rows
+    print(json.dumps(res))
+    shutil.rmtree(d, ignore_errors=True)
 
 if "lyon" in which:
     # configs[2]: Lyon-8, 10 M candidates, profile u8[128] + DM curve u8[256]

@@ -92,3 +92,82 @@ def test_synthetic_stream_is_shard_invariant():
     for name in ("profile", "subbands", "dmcurve", "dmstat", "params"):
         assert np.array_equal(getattr(a, name), np.concatenate([getattr(lo, name), getattr(hi, name)]))
     assert set(np.unique(a.edge)) >= set(range(synth.N_EDGE_KINDS))
+
+
+# ---- native PHCX scanner (include/pfx_io.h) against the Python reader ---------------------------
+def _ensure_io():
+    if not phcx_io.native_available():
+        import __graft_entry__ as ge
+        ge.build()
+
+
+def test_io_header_symbols_exported():
+    _ensure_io()
+    hdr = open(os.path.join(ROOT, "include", "pfx_io.h")).read()
+    declared = set(re.findall(r"\b(pfx_[a-z0-9_]+)\s*\(", hdr))
+    lib = ctypes.CDLL(phcx_io._IO_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(phcx_io.IO_EXPORTS)
+
+
+def test_native_scanner_equals_python_reader(tmp_path):
+    _ensure_io()
+    b = synth.generate(1, 0, 48)
+    paths = []
+    for i in range(48):
+        gz = i % 4 != 0
+        p = str(tmp_path / ("c%03d.phcx%s" % (i, ".gz" if gz else "")))
+        phcx_io.write_phcx(p, b.profile[i], b.subbands[i], b.dmcurve[i], b.dmstat[i], b.params[i], gz=gz)
+        paths.append(p)
+    # malformed files: what makes the Python reader (and the reference's) raise must give ok = 0
+    import gzip
+    with gzip.open(paths[1], "rb") as fh:
+        good = fh.read()
+
+    def variant(name, data, gz=True):
+        p = str(tmp_path / name)
+        with (gzip.open(p, "wb") if gz else open(p, "wb")) as fh:
+            fh.write(data)
+        paths.append(p)
+
+    variant("not_gzip.phcx.gz", b"plain text, no gzip header", gz=False)
+    variant("truncated.phcx.gz", good[: len(good) // 2])
+    variant("no_profile.phcx.gz", good.replace(b"<Profile", b"<Profilx").replace(b"</Profile>", b"</Profilx>"))
+    variant("one_section.phcx.gz", good[: good.index(b"</Section>") + 10] + b"</phcf>")
+    variant("bad_number.phcx.gz", good.replace(b"<Snr>", b"<Snr>abc"))
+    variant("subband_size.phcx.gz", good.replace(b"nSub='16'", b"nSub='15'"))
+    variant("short_dmindex.phcx.gz", re.sub(rb"(<DmIndex[^>]*>)\n.*?(</DmIndex>)", rb"\g<1>1.0\n\g<2>", good, flags=re.S))
+    variant("lower_hex_and_junk.phcx.gz", good.replace(b"<Profile nBins='128' format='02X' min='0' max='1'>\n",
+                                                      b"<Profile nBins='128' format='02X' min='0' max='1'>\n").lower()
+            .replace(b"<profile", b"<Profile").replace(b"</profile>", b"</Profile>").replace(b"<subbands", b"<SubBands")
+            .replace(b"</subbands>", b"</SubBands>").replace(b"<datablock", b"<DataBlock").replace(b"</datablock>", b"</DataBlock>")
+            .replace(b"<dmindex", b"<DmIndex").replace(b"</dmindex>", b"</DmIndex>").replace(b"<snr>", b"<Snr>")
+            .replace(b"</snr>", b"</Snr>").replace(b"<dm ", b"<Dm ").replace(b"</dm>", b"</Dm>")
+            .replace(b"<baryperiod", b"<BaryPeriod").replace(b"</baryperiod>", b"</BaryPeriod>")
+            .replace(b"<width", b"<Width").replace(b"</width>", b"</Width>").replace(b"nbins=", b"nBins=").replace(b"nsub=", b"nSub="))
+    scan = phcx_io.Scan(paths, threads=3)
+    nbad = 0
+    for i, p in enumerate(paths):
+        try:
+            r = phcx_io.read_phcx(p)
+            if r.subbands.shape[1] != r.profile.size:
+                r = None
+        except Exception:       # noqa: BLE001 - any exception = the candidate is skipped
+            r = None
+        assert scan.ok(i) == (r is not None), p
+        if r is None:
+            nbad += 1
+            continue
+        prof, sub, dmc, dms, par = scan.gather([i])
+        assert np.array_equal(prof[0], r.profile) and np.array_equal(sub[0], r.subbands), p
+        assert np.array_equal(dmc[0], r.dmcurve) and np.array_equal(dms[0], r.dmstat), p
+        assert np.array_equal(par[0], r.params), p
+    assert nbad == 7
+    # one gather for all files of the most common shape, rows in the order asked for
+    idx = [i for i in range(48) if scan.ok(i) and i % 4 != 0][::-1]       # the two-section .gz files share a shape
+    prof, sub, dmc, dms, par = scan.gather(idx)
+    assert np.array_equal(prof, b.profile[idx]) and np.array_equal(sub, b.subbands[idx])
+    assert np.array_equal(dmc, b.dmcurve[idx]) and np.array_equal(dms, b.dmstat[idx])
+    assert np.array_equal(par[:, :4], b.params[idx, :4])     # dm_start / dm_end pass through '%.4f' in the file
+    scan.close()
