@@ -1,4 +1,5 @@
-/* pfx_io.h -- C ABI of libpfxio.so: PHCX candidate files -> structure-of-arrays batch rows.
+/* pfx_io.h -- C ABI of libpfxio.so: PHCX candidate files -> structure-of-arrays batch rows, and
+ * feature rows -> output text.
  *
  * Host-only companion of libpfx (include/pfx.h).  It replaces, for a whole list of files at once,
  * the reading half of the reference's candidate objects:
@@ -56,6 +57,21 @@ int pfx_phcx_gather(const pfx_scan* scan, const int64_t* idx, int64_t count, uin
                     uint8_t* subbands, uint8_t* dmcurve, uint8_t* dmstat, double* params);
 
 void pfx_phcx_free(pfx_scan* scan);
+
+/* Output rows (DataProcessor.storeScore / storeScoreARFF, DataProcessor.py:305-325,405-425).
+ * Formats rows i < count with skip[i] == 0 (skip may be NULL) of feat[count][ld] (first ncol columns):
+ *   mode 0  CSV   "<name>,s1,...,sN\n"
+ *   mode 1  ARFF  "s1,...,sN,?%<name>\n"
+ *   mode 2  bare  "s1,...,sN\n"            (names may be NULL)
+ * Numbers as Python 2's str(float) when py2 != 0 ('%.12g', integer-valued results get '.0'), else as
+ * Python 3's repr (shortest digits that round-trip).  As in the reference, every "nan" and then every
+ * "inf" of the finished line -- the candidate name included -- is replaced by "0" (so "-inf" becomes
+ * "-0").  Rows are formatted by `threads` workers (<= 0: hardware concurrency) and concatenated in
+ * order.  *out is allocated by the library (free with pfx_io_free), *out_len is its length in bytes
+ * (no terminating NUL counted).  Returns 0, -1 on bad arguments / out of memory. */
+int pfx_format_rows(const double* feat, int64_t count, int64_t ld, int ncol, const char* const* names,
+                    const int8_t* skip, int mode, int py2, int threads, char** out, int64_t* out_len);
+void pfx_io_free(void* p);
 
 const char* pfx_io_version(void);
 

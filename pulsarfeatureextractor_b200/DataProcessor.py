@@ -116,12 +116,23 @@ class DataProcessor(object):
         return found
 
     # ---- the batched core ------------------------------------------------------------------------
-    def _score_files(self, paths, features):
-        """Yields (path, scores or None) in input order.  None = the reference would have raised."""
+    def _score_chunks(self, paths, features):
+        """Yields (chunk of paths, feature matrix [len(chunk)][ncol], ok mask) in input order; rows of
+        candidates the reference would have raised for are NaN with ok = False."""
         eng = self._engine()
+        ncol = {"bates": 22, "lyon": 8, "all": 30}[features]
         for lo in range(0, len(paths), self.batch):
             chunk = paths[lo:lo + self.batch]
-            results = [None] * len(chunk)
+            feat = np.full((len(chunk), ncol), np.nan, dtype=np.float64)
+            okm = np.zeros(len(chunk), dtype=bool)
+
+            def score_group(ks, prof, sub, dmc, dms, par):
+                out = eng.score_host(prof, sub, dmc, dms, par, features=features)
+                ok = out.ok() if features != "lyon" else np.ones(len(ks), dtype=bool)
+                ks = np.asarray(ks)
+                feat[ks] = out.features
+                okm[ks] = ok
+
             if phcx_io.native_available() and not any(".pfd" in p for p in chunk):
                 # bulk path: native scanner, rows gathered per shape into pinned buffers
                 scan = phcx_io.Scan(chunk)
@@ -132,62 +143,65 @@ class DataProcessor(object):
                     else:
                         print("Error reading profile data :\n\t", chunk[k])
                 for _key, ks in groups.items():
-                    prof, sub, dmc, dms, par = scan.gather(ks)
-                    out = eng.score_host(prof, sub, dmc, dms, par, features=features)
-                    ok = out.ok() if features != "lyon" else np.ones(len(ks), dtype=bool)
-                    for j, k in enumerate(ks):
-                        results[k] = out.features[j] if ok[j] else None
+                    score_group(ks, *scan.gather(ks))
                 scan.close()
-                for p, r in zip(chunk, results):
-                    yield p, r
-                continue
-            cands, keep = [], []
+            else:
+                groups = {}
+                for k, p in enumerate(chunk):
+                    try:
+                        c = Candidate(p, p).load()
+                    except Exception as e:      # noqa: BLE001 - mirrors DataProcessor.py:517
+                        print("Error reading profile data :\n\t", type(e).__name__, e)
+                        continue
+                    key = (c.profile.size, c.subbands.shape, c.dmcurve.size, c.dmstat.size)
+                    groups.setdefault(key, []).append((k, c))
+                for _key, items in groups.items():
+                    stack = lambda name: np.ascontiguousarray(np.stack([getattr(c, name) for _k, c in items]))
+                    score_group([k for k, _c in items], stack("profile"), stack("subbands"), stack("dmcurve"),
+                                stack("dmstat"), stack("params"))
+            yield chunk, feat, okm
+
+    def _score_files(self, paths, features):
+        """Yields (path, scores or None) in input order.  None = the reference would have raised."""
+        for chunk, feat, okm in self._score_chunks(paths, features):
             for k, p in enumerate(chunk):
-                try:
-                    c = Candidate(p, p)
-                    cands.append(c.load())
-                    keep.append(k)
-                except Exception as e:      # noqa: BLE001 - mirrors DataProcessor.py:517
-                    print("Error reading profile data :\n\t", type(e).__name__, e)
-            # group by array shapes so every group is one SoA batch
-            groups = {}
-            for k, c in zip(keep, cands):
-                key = (c.profile.size, c.subbands.shape, c.dmcurve.size, c.dmstat.size)
-                groups.setdefault(key, []).append((k, c))
-            for _key, items in groups.items():
-                prof = np.ascontiguousarray(np.stack([c.profile for _k, c in items]))
-                sub = np.ascontiguousarray(np.stack([c.subbands for _k, c in items]))
-                dmc = np.ascontiguousarray(np.stack([c.dmcurve for _k, c in items]))
-                dms = np.ascontiguousarray(np.stack([c.dmstat for _k, c in items]))
-                par = np.ascontiguousarray(np.stack([c.params for _k, c in items]))
-                out = eng.score_host(prof, sub, dmc, dms, par, features=features)
-                ok = out.ok() if features != "lyon" else np.ones(len(items), dtype=bool)
-                for j, (k, _c) in enumerate(items):
-                    results[k] = out.features[j] if ok[j] else None
-            for p, r in zip(chunk, results):
-                yield p, r
+                yield p, (feat[k] if okm[k] else None)
 
     def _run(self, directory, fileTypeRegexes, outPath, arff, features, processSingleCandidate, separate=False):
         start = datetime.datetime.now()
         paths = self.find(directory, fileTypeRegexes, processSingleCandidate)
         successes = failures = 0
-        for cand, scores in self._score_files(paths, features):
-            if scores is None:
-                print(cand, " did not have scores generated.")
-                self.appendToFile(self.candidateErrorLog, cand + "\n")
-                failures += 1
-                continue
-            if separate:
-                self.outputScores(scores, cand)
-            elif arff:
-                self.storeScoreARFF(cand, scores, outPath)
-            else:
-                self.storeScore(cand, scores, outPath)
-            successes += 1
-        end = datetime.datetime.now()
-        if not separate:
-            self.appendToFile(outPath, "".join(s + "\n" for s in self.scoreStore))
-            self.scoreStore = []
+        if not separate and phcx_io.native_available():
+            # rows of a chunk are formatted at once by the native formatter (include/pfx_io.h);
+            # all text is buffered and appended at the end, as the reference does (DataProcessor.py:590-594)
+            blobs = []
+            for chunk, feat, okm in self._score_chunks(paths, features):
+                for k in np.nonzero(~okm)[0]:
+                    print(chunk[k], " did not have scores generated.")
+                    self.appendToFile(self.candidateErrorLog, chunk[k] + "\n")
+                blobs.append(phcx_io.format_rows(feat, chunk, skip=~okm, mode="arff" if arff else "csv", py2=self.py2))
+                successes += int(okm.sum())
+                failures += int((~okm).sum())
+            end = datetime.datetime.now()
+            self.appendToFile(outPath, "".join(blobs))
+        else:
+            for cand, scores in self._score_files(paths, features):
+                if scores is None:
+                    print(cand, " did not have scores generated.")
+                    self.appendToFile(self.candidateErrorLog, cand + "\n")
+                    failures += 1
+                    continue
+                if separate:
+                    self.outputScores(scores, cand)
+                elif arff:
+                    self.storeScoreARFF(cand, scores, outPath)
+                else:
+                    self.storeScore(cand, scores, outPath)
+                successes += 1
+            end = datetime.datetime.now()
+            if not separate:
+                self.appendToFile(outPath, "".join(s + "\n" for s in self.scoreStore))
+                self.scoreStore = []
         print("\nCandidates processed:\t", len(paths))
         print("Successes:\t", successes)
         print("Failures:\t", failures)

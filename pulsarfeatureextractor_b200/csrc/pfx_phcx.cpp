@@ -326,4 +326,160 @@ extern "C" int pfx_phcx_gather(const pfx_scan* scan, const int64_t* idx, int64_t
 
 extern "C" void pfx_phcx_free(pfx_scan* scan) { delete scan; }
 
-extern "C" const char* pfx_io_version(void) { return "pfxio 0.1 (PHCX scanner)"; }
+// ---- output rows ---------------------------------------------------------------------------------
+namespace {
+
+// Python 2 str(float): '%.12g'; a result without '.', 'e' (and not nan/inf) gets '.0'
+void fmt_py2(double v, std::string* out) {
+    if (v != v) {
+        out->append("nan");
+        return;
+    }
+    if (std::isinf(v)) {
+        out->append(v > 0 ? "inf" : "-inf");
+        return;
+    }
+    char buf[40];
+    const int n = snprintf(buf, sizeof(buf), "%.12g", v);
+    out->append(buf, (size_t)n);
+    if (!memchr(buf, '.', (size_t)n) && !memchr(buf, 'e', (size_t)n)) out->append(".0");
+}
+
+// Python 3 repr(float): the shortest digit string that round-trips, fixed notation for decimal
+// exponents in [-4, 16), else d.ddde+XX (float_repr_style 'short')
+void fmt_repr(double v, std::string* out) {
+    if (v != v) {
+        out->append("nan");
+        return;
+    }
+    if (std::isinf(v)) {
+        out->append(v > 0 ? "inf" : "-inf");
+        return;
+    }
+    if (v == 0.0) {
+        out->append(std::signbit(v) ? "-0.0" : "0.0");
+        return;
+    }
+    char buf[48];
+    int prec = 0;
+    for (prec = 0; prec < 17; ++prec) {       // prec = digits after the point in scientific notation
+        snprintf(buf, sizeof(buf), "%.*e", prec, v);
+        if (strtod(buf, nullptr) == v) break;
+    }
+    // buf = [-]d[.ddd]e[+-]XX
+    const char* p = buf;
+    if (*p == '-') {
+        out->push_back('-');
+        ++p;
+    }
+    std::string digits;
+    digits.push_back(*p++);
+    if (*p == '.') {
+        ++p;
+        while (*p && *p != 'e') digits.push_back(*p++);
+    }
+    const int exp10 = atoi(p + 1);           // after 'e'
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int nd = (int)digits.size();
+    const int decpt = exp10 + 1;             // position of the decimal point relative to the digits
+    if (decpt > -4 && decpt <= 16) {
+        if (decpt <= 0) {
+            out->append("0.");
+            out->append((size_t)(-decpt), '0');
+            out->append(digits);
+        } else if (decpt >= nd) {
+            out->append(digits);
+            out->append((size_t)(decpt - nd), '0');
+            out->append(".0");
+        } else {
+            out->append(digits, 0, (size_t)decpt);
+            out->push_back('.');
+            out->append(digits, (size_t)decpt, std::string::npos);
+        }
+    } else {
+        out->push_back(digits[0]);
+        if (nd > 1) {
+            out->push_back('.');
+            out->append(digits, 1, std::string::npos);
+        }
+        char e[16];
+        snprintf(e, sizeof(e), "e%c%02d", exp10 < 0 ? '-' : '+', exp10 < 0 ? -exp10 : exp10);
+        out->append(e);
+    }
+}
+
+// line.replace("nan", "0").replace("inf", "0")
+void replace_all(std::string* s, const char* what) {
+    size_t pos = 0;
+    while ((pos = s->find(what, pos)) != std::string::npos) {
+        s->replace(pos, 3, "0");
+        pos += 1;
+    }
+}
+
+}  // namespace
+
+extern "C" int pfx_format_rows(const double* feat, int64_t count, int64_t ld, int ncol, const char* const* names,
+                               const int8_t* skip, int mode, int py2, int threads, char** out, int64_t* out_len) {
+    if (!feat || count < 0 || ncol < 1 || ld < ncol || mode < 0 || mode > 2 || !out || !out_len) return -1;
+    if (mode != 2 && !names) return -1;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if ((int64_t)nt * 256 > count) nt = (int)(count / 256 > 0 ? count / 256 : 1);
+    std::vector<std::string> parts((size_t)nt);
+    std::atomic<bool> failed(false);
+    auto work = [&](int t) {
+        try {
+            const int64_t lo = count * t / nt, hi = count * (t + 1) / nt;
+            std::string& acc = parts[(size_t)t];
+            acc.reserve((size_t)(hi - lo) * (size_t)(ncol * 14 + 48));
+            std::string line;
+            for (int64_t i = lo; i < hi; ++i) {
+                if (skip && skip[i]) continue;
+                line.clear();
+                if (mode == 0) {
+                    line.append(names[i] ? names[i] : "");
+                    line.push_back(',');
+                }
+                const double* row = feat + i * ld;
+                for (int k = 0; k < ncol; ++k) {
+                    if (k) line.push_back(',');
+                    if (py2) fmt_py2(row[k], &line);
+                    else fmt_repr(row[k], &line);
+                }
+                if (mode == 1) {
+                    line.append(",?%");
+                    line.append(names[i] ? names[i] : "");
+                }
+                replace_all(&line, "nan");
+                replace_all(&line, "inf");
+                line.push_back('\n');
+                acc.append(line);
+            }
+        } catch (...) {
+            failed = true;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    if (failed) return -1;
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    char* buf = (char*)malloc(total + 1);
+    if (!buf) return -1;
+    size_t off = 0;
+    for (auto& p : parts) {
+        memcpy(buf + off, p.data(), p.size());
+        off += p.size();
+    }
+    buf[total] = 0;
+    *out = buf;
+    *out_len = (int64_t)total;
+    return 0;
+}
+
+extern "C" void pfx_io_free(void* p) { free(p); }
+
+extern "C" const char* pfx_io_version(void) { return "pfxio 0.2 (PHCX scanner, row formatter)"; }

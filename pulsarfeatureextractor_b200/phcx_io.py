@@ -29,7 +29,7 @@ import numpy as np
 
 # ---- native scanner (include/pfx_io.h, csrc/pfx_phcx.cpp) ------------------------------------
 _IO_PATH = os.environ.get("PFX_IO_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpfxio.so")
-IO_EXPORTS = ["pfx_phcx_scan", "pfx_phcx_gather", "pfx_phcx_free", "pfx_io_version"]
+IO_EXPORTS = ["pfx_phcx_scan", "pfx_phcx_gather", "pfx_phcx_free", "pfx_format_rows", "pfx_io_free", "pfx_io_version"]
 _io = None
 
 
@@ -53,8 +53,39 @@ def _load_io():
         lib.pfx_phcx_gather.argtypes = [vp, ctypes.POINTER(i64), i64, vp, vp, vp, vp, vp]
         lib.pfx_phcx_free.argtypes = [vp]
         lib.pfx_io_version.restype = ctypes.c_char_p
+        lib.pfx_format_rows.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), vp,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp),
+                                        ctypes.POINTER(i64)]
+        lib.pfx_io_free.argtypes = [vp]
         _io = lib
     return _io
+
+
+def format_rows(features, names=None, skip=None, mode="csv", py2=True, threads=0):
+    """Output text of a block of feature rows (native formatter, include/pfx_io.h): one line per
+    row with skip[i] == 0, '<name>,s1,...' (csv), 's1,...,?%<name>' (arff) or 's1,...' (bare),
+    Python-2 number formatting by default, 'nan' / 'inf' -> '0' over the whole line as the
+    reference does (DataProcessor.py:321-325,421-425).  Returns ``str``."""
+    lib = _load_io()
+    feat = np.ascontiguousarray(features, dtype=np.float64)
+    n, ncol = feat.shape
+    m = {"csv": 0, "arff": 1, "bare": 2}[mode]
+    arr = None
+    if names is not None:
+        arr = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in names])
+    sk = None
+    if skip is not None:
+        sk = np.ascontiguousarray(skip, dtype=np.int8)
+    out, out_len = ctypes.c_void_p(), ctypes.c_int64()
+    rc = lib.pfx_format_rows(feat.ctypes.data_as(ctypes.c_void_p), n, ncol, ncol, arr,
+                             sk.ctypes.data_as(ctypes.c_void_p) if sk is not None else None, m,
+                             1 if py2 else 0, int(threads), ctypes.byref(out), ctypes.byref(out_len))
+    if rc != 0:
+        raise RuntimeError("pfx_format_rows failed")
+    try:
+        return ctypes.string_at(out, out_len.value).decode("utf-8", "surrogateescape")
+    finally:
+        lib.pfx_io_free(out)
 
 
 class Scan(object):

@@ -171,3 +171,34 @@ def test_native_scanner_equals_python_reader(tmp_path):
     assert np.array_equal(dmc, b.dmcurve[idx]) and np.array_equal(dms, b.dmstat[idx])
     assert np.array_equal(par[:, :4], b.params[idx, :4])     # dm_start / dm_end pass through '%.4f' in the file
     scan.close()
+
+
+def test_native_row_formatter_equals_reference_format(tmp_path):
+    """pfx_format_rows against the oracle's row writer (DataProcessor.py:321-325,421-425): Python-2
+    '%.12g' numbers and Python-3 repr, CSV / ARFF / bare, 'nan' and 'inf' -> '0' over the whole line
+    (the candidate name included), skipped rows."""
+    _ensure_io()
+    import pfx_oracle as O
+    rng = np.random.default_rng(0)
+    special = [0.0, -0.0, 1.0, -1.0, 5.0, 1e15, 1e16, 1e17, 123456789012.0, 1234567890123.0, 0.1, 1 / 3, 1e-4, 1e-5,
+               5e-324, 1.7976931348623157e308, float("nan"), float("inf"), float("-inf"), 2.5e-7, 100.0,
+               99999999999.5, 999999999999.5, 0.000123456789012345, 1e22, 1e21, 123456.789e3, 1000000.0]
+    vals = np.concatenate([special, rng.normal(size=3000) * 10.0 ** rng.integers(-30, 30, 3000),
+                           rng.integers(-1000, 1000, 500).astype(float), rng.random(472)])
+    feat = vals.reshape(-1, 10)
+    n = feat.shape[0]
+    names = ["/data/nan_dir/cand_%d_inf.phcx.gz" % i for i in range(n)]
+    skip = np.zeros(n, np.int8)
+    skip[[3, n - 1]] = 1
+    for py2 in (True, False):
+        for mode in ("csv", "arff", "bare"):
+            got = phcx_io.format_rows(feat, names, skip, mode, py2, threads=3)
+            exp = []
+            for i in range(n):
+                if skip[i]:
+                    continue
+                if mode == "bare":
+                    exp.append(",".join(O.fmt_float(v, py2) for v in feat[i]).replace("nan", "0").replace("inf", "0"))
+                else:
+                    exp.append(O.format_row(names[i], feat[i], arff=(mode == "arff"), py2=py2))
+            assert got == "\n".join(exp) + "\n", (py2, mode)
