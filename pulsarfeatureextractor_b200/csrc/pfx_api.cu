@@ -103,6 +103,20 @@ static int check_shape(pfx_ctx* ctx, const pfx_shape* s, int64_t n) {
     return PFX_OK;
 }
 
+// Everything the Bates kernels refuse, checked before anything is launched: an error in the middle
+// of pfx_score_dev would leave kernels of the side streams in flight on buffers the caller may free.
+static int check_bates_shape(pfx_ctx* ctx, const pfx_shape* s) {
+    if (s->nbin < 8 || s->nbin > 65535)
+        return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin = %d: the Bates scores need 8 <= nbin <= 65535", s->nbin);
+    if (s->nsub < 1) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nsub < 1");
+    if (s->n_dm < 4) return set_err(ctx, PFX_ERR_UNSUPPORTED, "n_dm < 4");
+    const size_t sub_bytes = (size_t)align_up(sub_work_doubles(s->nbin, s->nsub), 2) * 8;
+    if (sub_bytes > (size_t)ctx->smem_optin)
+        return set_err(ctx, PFX_ERR_UNSUPPORTED, "sub-bands %d x %d need %zu bytes of shared memory per candidate, limit %d",
+                       s->nsub, s->nbin, sub_bytes, ctx->smem_optin);
+    return PFX_OK;
+}
+
 static void rotate_counters(pfx_ctx* ctx) { ctx->counter_slot = (ctx->counter_slot + 1) % COUNTER_SLOTS; }
 
 // =============================================================================================
@@ -195,6 +209,10 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
     if (!profile || !feat || feat_ld < ncol) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
     if (bates && (!subbands || !dmcurve || !params || !status)) return set_err(ctx, PFX_ERR_INVALID, "Bates scores need subbands, dmcurve, params and status");
     if (lyon && !dmstat) return set_err(ctx, PFX_ERR_INVALID, "Lyon statistics need dmstat");
+    if (bates) {
+        const int rcs = check_bates_shape(ctx, shape);
+        if (rcs) return rcs;
+    }
     rotate_counters(ctx);
     int launches = 0;
     int e = 0;
@@ -228,24 +246,23 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
             // side stream first: the DM and sinusoid kernels have a short body and a long tail of
             // slow candidates (a few lingering blocks); launched ahead of the histogram/Gaussian
             // chain their tails hide behind its body instead of adding to the step
+            // whatever happens, the side streams are joined again before this function returns:
+            // the caller's stream must cover every kernel that touches the caller's buffers
             rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, 3);
+            if (!rc && trace) cudaEventRecord(ctx->ev[5], sd);
+            if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, 0);
+            if (!rc && trace) cudaEventRecord(ctx->ev[2], sd2);
+            if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, 4);
+            if (!rc) rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
+            if (!rc && trace) cudaEventRecord(ctx->ev[3], st);
+            if (!rc) rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
+            if (!rc && trace) cudaEventRecord(ctx->ev[4], st);
+            cudaEventRecord(ctx->join_ev[par], sd);
+            cudaStreamWaitEvent(st, ctx->join_ev[par], 0);
+            cudaEventRecord(ctx->join2_ev[par], sd2);
+            cudaStreamWaitEvent(st, ctx->join2_ev[par], 0);
             if (rc) return rc;
-            if (trace) cudaEventRecord(ctx->ev[5], sd);
-            rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, 0);
-            if (rc) return rc;
-            if (trace) cudaEventRecord(ctx->ev[2], sd2);
-            rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, 4);
-            if (rc) return rc;
-            rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
-            if (rc) return rc;
-            if (trace) cudaEventRecord(ctx->ev[3], st);
-            rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
-            if (rc) return rc;
-            if (trace) cudaEventRecord(ctx->ev[4], st);
-            PFX_CUDA(ctx, cudaEventRecord(ctx->join_ev[par], sd));
-            PFX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join_ev[par], 0));
-            PFX_CUDA(ctx, cudaEventRecord(ctx->join2_ev[par], sd2));
-            PFX_CUDA(ctx, cudaStreamWaitEvent(st, ctx->join2_ev[par], 0));
+            PFX_CUDA(ctx, cudaGetLastError());
         } else {
             rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, 0);
             if (rc) return rc;
@@ -401,7 +418,11 @@ extern "C" int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, u
         rc = score_dev_impl(ctx, shape, cn, features, base + L.profile, base + L.subbands, base + L.dmcurve,
                             base + L.dmstat, (const double*)(base + L.params), (double*)(base + L.feat), ncol,
                             bates && ier ? (int8_t*)(base + L.ier) : nullptr, (int32_t*)(base + L.status), st, 0);
-        if (rc) return rc;
+        if (rc) {       // nothing may still be copying into the caller's arrays when we return
+            cudaStreamSynchronize(ctx->streams[0]);
+            cudaStreamSynchronize(ctx->streams[1]);
+            return rc;
+        }
         launches += ctx->last_launches;
         if (feat_ld == ncol) {
             PFX_CUDA(ctx, cudaMemcpyAsync(feat + (size_t)done * feat_ld, base + L.feat, (size_t)cn * ncol * 8,

@@ -276,6 +276,45 @@ def test_survey_shape_1024_bins(eng):
     assert np.array_equal(h.status, status) and np.array_equal(h.ier, ier)
 
 
+def test_edge_sizes_and_errors(eng, batch_and_oracle):
+    """Empty and ragged batches (sizes that are no multiple of a warp, a lane group or a block),
+    one candidate, and the error behaviour of the ABI."""
+    import torch
+    from pulsarfeatureextractor_b200.engine import PfxError
+    b, feat, status, ier, rows = batch_and_oracle
+    # a candidate's row does not depend on what else is in the batch
+    for n in (1, 2, 31, 33, 97):
+        f, s, i = _dev(eng, b.slice(0, n))
+        assert np.array_equal(f, feat[:n], equal_nan=True) and np.array_equal(s, status[:n]) and np.array_equal(i, ier[:n])
+        h = eng.score_host(b.profile[:n], b.subbands[:n], b.dmcurve[:n], b.dmstat[:n], b.params[:n], features="all", chunk=7)
+        assert np.array_equal(h.features, feat[:n], equal_nan=True) and np.array_equal(h.status, status[:n])
+    # empty batch: accepted, nothing launched, empty outputs
+    e = b.slice(0, 0)
+    f, s, i = _dev(eng, e)
+    assert f.shape == (0, 30) and s.shape == (0,)
+    h = eng.score_host(e.profile, e.subbands, e.dmcurve, e.dmstat, e.params, features="all")
+    assert h.features.shape == (0, 30)
+    # Lyon-only needs no Bates inputs; Bates without sub-bands is refused
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ly = eng.score_device(t(b.profile[:5]), None, None, t(b.dmstat[:5]), None, features="lyon")
+    torch.cuda.synchronize()
+    assert np.array_equal(ly.features.cpu().numpy(), feat[:5, 22:30], equal_nan=True)
+    with pytest.raises(PfxError):
+        eng.score_device(t(b.profile[:5]), None, t(b.dmcurve[:5]), t(b.dmstat[:5]), t(b.params[:5]), features="all")
+    # profiles shorter than the reference's procedures can handle are refused, not mis-scored
+    with pytest.raises(PfxError):
+        eng.score_device(t(b.profile[:5, :4]), t(b.subbands[:5, :, :4]), t(b.dmcurve[:5]), t(b.dmstat[:5]), t(b.params[:5]),
+                         features="all")
+    # non-contiguous input
+    with pytest.raises(PfxError):
+        eng.score_device(t(b.profile[:8])[::2], t(b.subbands[:4]), t(b.dmcurve[:4]), t(b.dmstat[:4]), t(b.params[:4]),
+                         features="all")
+    # the context is still usable after errors
+    f, s, i = _dev(eng, b.slice(0, 3))
+    assert np.array_equal(f, feat[:3], equal_nan=True)
+
+
 def test_pfd_params_on_device(eng):
     """S/N (3-sigma clipped) and half-maximum width derived from the profile, PFDOperations.py:130-231.
     The S/N cancels to rounding noise when nothing is clipped and its sign picks 0.1 or ~1e-15, so the
