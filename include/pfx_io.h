@@ -58,6 +58,31 @@ int pfx_phcx_gather(const pfx_scan* scan, const int64_t* idx, int64_t count, uin
 
 void pfx_phcx_free(pfx_scan* scan);
 
+/* ---- PRESTO .pfd files (PFDFile.py:96-456, PFDOperations.py:242-252,474-525) --------------------
+ * Per file: header and fold cube profs[npart][nsub][proflen]; avgprof (numpy's pairwise sum of
+ * profs / proflen) and varprof before any rotation; de-dispersion at the best DM by whole-bin left
+ * rotations; profile = (sumprof - min) / mean scaled to [0, 255] with the reference's formula;
+ * sub-bands = profs.sum(0); the reduced chi-square versus DM curve on 100 trial DMs between dms[0]
+ * and dms[-1] with rotations accumulated from trial to trial, rounded to float32.
+ * Outputs per file: profile f64[proflen], subbands f64[nsub][proflen], dmcurve f32[100] (also the
+ * array of the Lyon DM statistics), params = 0 (S/N: pfx_pfd_params_dev), best DM, bary_p1 (s),
+ * 0 (width: pfx_pfd_params_dev), DMs[1], DMs[99], 100, 0.
+ * ok = 0: unreadable or truncated file, impossible dimensions, fewer than two DMs in the header. */
+typedef struct pfx_pfd_info {
+    int32_t ok;
+    int32_t nbin;      /* proflen */
+    int32_t nsub;
+    int32_t n_dm;      /* 100 */
+    int32_t reserved0, reserved1;
+    double params[8];
+} pfx_pfd_info;
+
+int pfx_pfd_scan(const char* const* paths, int64_t n, int threads, pfx_pfd_info* info, pfx_scan** out);
+/* rows of files idx[0..count) (same nbin, nsub): profile f64, subbands f64, dmcurve f32, params f64 */
+int pfx_pfd_gather(const pfx_scan* scan, const int64_t* idx, int64_t count, double* profile,
+                   double* subbands, float* dmcurve, double* params);
+void pfx_pfd_free(pfx_scan* scan);
+
 /* Output rows (DataProcessor.storeScore / storeScoreARFF, DataProcessor.py:305-325,405-425).
  * Formats rows i < count with skip[i] == 0 (skip may be NULL) of feat[count][ld] (first ncol columns):
  *   mode 0  CSV   "<name>,s1,...,sN\n"

@@ -191,6 +191,23 @@ def lyon4(values):
                     float(_stats.skew(bins)), float(_stats.kurtosis(bins))]
 
 
+def lyon4_asis(values):
+    """The same four statistics on the array AS IT IS: for .pfd candidates the reference passes the
+    float32 chi-square curve straight to numpy / scipy (PFDFile.py:567-574), so mean, std, skew and
+    kurtosis are evaluated in float32 arithmetic there."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with np.errstate(all="ignore"):
+            return [float(np.mean(values)), float(np.std(values)),
+                    float(_stats.skew(values)), float(_stats.kurtosis(values))]
+
+
+def lyon8_pfd(profile, chis):
+    """PFD family: profile statistics on Python floats (PFDFile.py:531-541), DM-curve statistics on
+    the float32 array as is."""
+    return np.array(lyon4(profile) + lyon4_asis(np.asarray(chis)), dtype=np.float64)
+
+
 def lyon8(profile, dm_data):
     """Profile statistics followed by DM-curve statistics (column order DP:884-886,918-926)."""
     return np.array(lyon4(profile) + lyon4(dm_data), dtype=np.float64)

@@ -14,6 +14,8 @@ in-memory source transformation and executes the result:
                ``0L``          -> ``0``                    (syntax only, PFDOperations.py:60)
                ``Num.float``   -> ``float``                (removed numpy alias, PFDOperations.py:498)
                ``d.has_key(k)``-> ``(k in d)``             (PFDFile.py:266)
+               ``test[ii] not in '...'`` -> ``chr(test[ii]) ...``, ``test.find('\\0')`` -> ``find(b'\\0')``
+                                                           (bytes read from the binary .pfd, PFDFile.py:130-139)
   AST level    ``a / b``       -> ``_py2div(a, b)``        classic division: floor for int/int
                                                            (Python ints *and* numpy integer scalars /
                                                            integer arrays), true division otherwise
@@ -134,6 +136,10 @@ def _text_fix(src):
         line = re.sub(r"\b0L\b", "0", line)
         line = line.replace("Num.float", "float")
         line = re.sub(r"(\w+(?:\.\w+)*)\.has_key\(([^)]*)\)", r"(\2 in \1)", line)
+        # Python 2 ``str`` read from a binary file is ``bytes`` in Python 3 (PFDFile.py:130-139):
+        # indexing gives an int, and ``find`` wants a bytes needle
+        line = line.replace("if test[ii] not in '0123456789:.-\\0':", "if chr(test[ii]) not in '0123456789:.-\\0':")
+        line = line.replace("test.find('\\0')", "test.find(b'\\0')")
         out.append(line)
     return "\n".join(out) + "\n"
 

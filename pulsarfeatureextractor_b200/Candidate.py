@@ -9,7 +9,7 @@ through DataProcessor, which packs many candidates into one structure-of-arrays 
 """
 import numpy as np
 
-from . import phcx_io
+from . import pfd_io, phcx_io
 
 
 class Candidate(object):
@@ -31,12 +31,18 @@ class Candidate(object):
     def load(self):
         fam = self.family()
         if fam == "pfd":
-            raise NotImplementedError("PFD reader is not part of this build (SURVEY.md 8f2)")
+            return pfd_io.read_pfd(self.candidateName)
         return phcx_io.read_phcx(self.candidateName, section=1 if fam == "phcx" else 0)
 
     # ---- scoring entry points, same names as the reference ----------------------------------------
     def _score(self, engine, features):
         c = self.load()
+        if self.family() == "pfd":
+            out = engine.score_pfd_host(c.profile[None], c.subbands[None], c.dmcurve[None], c.params[None],
+                                        features=features)
+            if features != "lyon" and not out.ok()[0]:
+                raise Exception("candidate scoring failed, status=0x%x" % int(out.status[0]))
+            return [float(v) for v in out.features[0]]
         out = engine.score_host(np.ascontiguousarray(c.profile[None]), np.ascontiguousarray(c.subbands[None]),
                                 np.ascontiguousarray(c.dmcurve[None]), np.ascontiguousarray(c.dmstat[None]),
                                 np.ascontiguousarray(c.params[None]), features=features)

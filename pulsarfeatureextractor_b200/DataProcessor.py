@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-from . import _lib, phcx_io
+from . import _lib, pfd_io, phcx_io
 from .Candidate import Candidate
 
 
@@ -42,6 +42,7 @@ class DataProcessor(object):
         self.phcxRegex = "*.phcx.gz"
         self.superbRegex = "*.phcx"
         self.pfdRegex = "*.pfd"
+        self.pfdScrunchedRegex = "*.pfd.36scrunch"
         self.scoreStore = []
         self.candidateErrorLog = error_log
         self.engine = engine
@@ -133,7 +134,25 @@ class DataProcessor(object):
                 feat[ks] = out.features
                 okm[ks] = ok
 
-            if phcx_io.native_available() and not any(".pfd" in p for p in chunk):
+            if phcx_io.native_available() and all(".pfd" in p for p in chunk):
+                # PRESTO .pfd files: native reader (de-dispersion, profile, sub-bands, chi-square curve),
+                # S/N and width on the device, PFD family constants
+                scan = pfd_io.PfdScan(chunk)
+                groups = {}
+                for k in range(len(chunk)):
+                    if scan.ok(k):
+                        groups.setdefault(scan.shape_key(k), []).append(k)
+                    else:
+                        print("Error reading profile data :\n\t", chunk[k])
+                for _key, ks in groups.items():
+                    prof, sub, dmc, par = scan.gather(ks)
+                    out = eng.score_pfd_host(prof, sub, dmc, par, features=features)
+                    ok = out.ok() if features != "lyon" else np.ones(len(ks), dtype=bool)
+                    ks = np.asarray(ks)
+                    feat[ks] = out.features
+                    okm[ks] = ok
+                scan.close()
+            elif phcx_io.native_available() and not any(".pfd" in p for p in chunk):
                 # bulk path: native scanner, rows gathered per shape into pinned buffers
                 scan = phcx_io.Scan(chunk)
                 groups = {}
@@ -157,6 +176,13 @@ class DataProcessor(object):
                     groups.setdefault(key, []).append((k, c))
                 for _key, items in groups.items():
                     stack = lambda name: np.ascontiguousarray(np.stack([getattr(c, name) for _k, c in items]))
+                    if isinstance(items[0][1], pfd_io.PFDCandidate):
+                        out = eng.score_pfd_host(stack("profile"), stack("subbands"), stack("dmcurve"), stack("params"),
+                                                 features=features)
+                        ks = np.asarray([k for k, _c in items])
+                        feat[ks] = out.features
+                        okm[ks] = out.ok() if features != "lyon" else True
+                        continue
                     score_group([k for k, _c in items], stack("profile"), stack("subbands"), stack("dmcurve"),
                                 stack("dmstat"), stack("params"))
             yield chunk, feat, okm
@@ -262,12 +288,26 @@ class DataProcessor(object):
     def dmprofSUPERB(self, directory, verbose, outPath, arff, processSingleCandidate):
         return self.dmprof(directory, verbose, [self.superbRegex], outPath, arff, processSingleCandidate)
 
-    def _pfd_unsupported(self, *a, **k):
-        sys.stderr.write("PFD candidates: the .pfd reader/dedispersion stage is not part of this build "
-                         "(SURVEY.md 8f2); PFD-shaped arrays can be scored through Engine.score_host "
-                         "with family=PFX_FAMILY_PFD.\n")
-        return 0, 0
+    # ---- PFD entry points (DataProcessor.py:150-227,271-288) ---------------------------------------
+    def processPFDSeparately(self, directory, verbose, processSingleCandidate):
+        self.pfd = True
+        return self.processSeparately(directory, verbose, [self.pfdRegex, self.pfdScrunchedRegex], processSingleCandidate)
 
-    processPFDCollectively = processPFDSeparately = dmprofPFD = _pfd_unsupported
-    processPFDAndPHCXCollectively = processPHCXCollectively
-    processPFDAndPHCXSeparately = processPHCXSeparately
+    def processPFDCollectively(self, directory, verbose, outPath, arff, genProfileData, processSingleCandidate):
+        self.pfd = True
+        return self.processCollectively(directory, verbose, [self.pfdRegex, self.pfdScrunchedRegex], outPath, arff,
+                                        False, processSingleCandidate)
+
+    def processPFDAndPHCXSeparately(self, directory, verbose, processSingleCandidate):
+        self.pfd = self.phcx = True
+        return self.processSeparately(directory, verbose, [self.phcxRegex, self.pfdRegex, self.pfdScrunchedRegex],
+                                      processSingleCandidate)
+
+    def processPFDAndPHCXCollectively(self, directory, verbose, outPath, arff, genProfileData, processSingleCandidate):
+        self.pfd = self.phcx = True
+        return self.processCollectively(directory, verbose, [self.phcxRegex, self.pfdRegex, self.pfdScrunchedRegex],
+                                        outPath, arff, False, processSingleCandidate)
+
+    def dmprofPFD(self, directory, verbose, outPath, arff, processSingleCandidate):
+        return self.dmprof(directory, verbose, [self.pfdRegex, self.pfdScrunchedRegex], outPath, arff,
+                           processSingleCandidate)

@@ -326,6 +326,332 @@ extern "C" int pfx_phcx_gather(const pfx_scan* scan, const int64_t* idx, int64_t
 
 extern "C" void pfx_phcx_free(pfx_scan* scan) { delete scan; }
 
+// ---- PRESTO .pfd files ---------------------------------------------------------------------------
+namespace {
+
+struct PfdCand {
+    std::vector<double> profile, subbands;
+    std::vector<float> chis;
+};
+
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src), which ndarray.sum() and
+// numpy.mean use on contiguous data: the reference's avgprof, mean(normprof) and chi-square sums
+double np_pairwise(const double* a, size_t n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (size_t i = 0; i < n; ++i) r += a[i];
+        return r;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        size_t i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; ++k) r[k] += a[i + k];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += a[i];
+        return res;
+    }
+    size_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise(a, n2) + np_pairwise(a + n2, n - n2);
+}
+
+struct Reader {
+    const unsigned char* p;
+    size_t n, pos;
+    bool swap, bad;
+    void get(void* dst, size_t size, size_t count) {
+        if (bad || pos + size * count > n) {
+            bad = true;
+            memset(dst, 0, size * count);
+            return;
+        }
+        memcpy(dst, p + pos, size * count);
+        pos += size * count;
+        if (swap && size > 1) {
+            unsigned char* d = (unsigned char*)dst;
+            for (size_t i = 0; i < count; ++i)
+                for (size_t b = 0; b < size / 2; ++b) {
+                    const unsigned char t = d[i * size + b];
+                    d[i * size + b] = d[i * size + size - 1 - b];
+                    d[i * size + size - 1 - b] = t;
+                }
+        }
+    }
+    int32_t i32() {
+        int32_t v;
+        get(&v, 4, 1);
+        return v;
+    }
+    double f64() {
+        double v;
+        get(&v, 8, 1);
+        return v;
+    }
+    void skip(size_t k) {
+        if (bad || pos + k > n) bad = true;
+        else pos += k;
+    }
+};
+
+inline long pymod(long a, long m) {
+    const long r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+void rotate_left(double* row, int len, long bins, std::vector<double>* tmp) {
+    const long r = pymod(bins, len);
+    if (!r) return;
+    tmp->assign(row, row + len);
+    for (int k = 0; k < len; ++k) row[k] = (*tmp)[(size_t)((k + r) % len)];
+}
+
+bool parse_pfd(const char* path, PfdCand* c, pfx_pfd_info* info) {
+    std::string raw;
+    if (!read_file(path, false, &raw)) return false;
+    Reader rd = {(const unsigned char*)raw.data(), raw.size(), 0, false, false};
+    if (raw.size() < 20) return false;
+    {   // endianness test of PFDFile.py:118-124: none of the first five ints should be large
+        int32_t t[5];
+        memcpy(t, raw.data(), 20);
+        double mx = 0.0;
+        for (int k = 0; k < 5; ++k) mx = std::fmax(mx, std::fabs((double)t[k]));
+        rd.swap = mx > 100000.0;
+    }
+    const int32_t numdms = rd.i32(), numperiods = rd.i32(), numpdots = rd.i32(), nsub = rd.i32(), npart = rd.i32();
+    const int32_t proflen = rd.i32(), numchan = rd.i32();
+    for (int k = 0; k < 5; ++k) rd.i32();
+    for (int k = 0; k < 4; ++k) {
+        const int32_t ln = rd.i32();
+        if (ln < 0) return false;
+        rd.skip((size_t)ln);
+    }
+    if (rd.bad || rd.pos + 16 > rd.n) return false;
+    bool has_posn = true;
+    for (int k = 0; k < 16; ++k) {
+        const char ch = (char)rd.p[rd.pos + k];
+        if (!((ch >= '0' && ch <= '9') || ch == ':' || ch == '.' || ch == '-' || ch == '\0')) {
+            has_posn = false;
+            break;
+        }
+    }
+    if (has_posn) rd.skip(32);
+    rd.f64();                      // dt
+    rd.f64();                      // startT
+    rd.f64();                      // endT
+    rd.f64();                      // tepoch
+    rd.f64();                      // bepoch
+    rd.f64();                      // avgvoverc
+    const double lofreq = rd.f64(), chan_wid = rd.f64(), bestdm = rd.f64();
+    rd.skip(8);
+    for (int k = 0; k < 3; ++k) rd.f64();              // topo
+    rd.skip(8);
+    const double bary_p1 = rd.f64();
+    rd.f64();
+    rd.f64();
+    rd.skip(8);
+    const double fold_p1 = rd.f64();
+    rd.f64();
+    rd.f64();
+    for (int k = 0; k < 7; ++k) rd.f64();              // orbit
+    if (rd.bad || numdms < 2 || numperiods < 0 || numpdots < 0 || nsub <= 0 || npart <= 0 || proflen <= 0 ||
+        nsub > 65536 || npart > 65536 || proflen > 65535)
+        return false;
+    std::vector<double> dms((size_t)numdms);
+    rd.get(dms.data(), 8, (size_t)numdms);
+    rd.skip(8 * (size_t)numperiods);
+    rd.skip(8 * (size_t)numpdots);
+    const size_t ncube = (size_t)npart * nsub * proflen;
+    std::vector<double> profs(ncube), stats((size_t)npart * nsub * 7);
+    rd.get(profs.data(), 8, ncube);
+    rd.get(stats.data(), 8, stats.size());
+    if (rd.bad) return false;
+
+    const double binspersec = fold_p1 * proflen;
+    const long chanpersub = numchan / nsub;            // Python 2 int / int (both positive here or the file is refused below)
+    if (numchan < 0) return false;
+    const double subdeltafreq = chan_wid * (double)chanpersub;
+    const double losubfreq = lofreq + subdeltafreq - chan_wid;
+    std::vector<double> subfreqs((size_t)nsub);
+    for (int j = 0; j < nsub; ++j) subfreqs[(size_t)j] = (double)j * subdeltafreq + losubfreq;
+    // avgprof = (profs / proflen).sum(), varprof = sum of prof_var -- before any rotation
+    double avgprof;
+    {
+        std::vector<double> q(ncube);
+        for (size_t k = 0; k < ncube; ++k) q[k] = profs[k] / (double)proflen;
+        avgprof = np_pairwise(q.data(), ncube);
+    }
+    double varprof = 0.0;
+    for (size_t k = 0; k < (size_t)npart * nsub; ++k) varprof += stats[k * 7 + 5];
+
+    auto delays = [&](double dm, std::vector<double>* out) {
+        out->resize((size_t)nsub);
+        for (int j = 0; j < nsub; ++j) {
+            const double f = subfreqs[(size_t)j];
+            (*out)[(size_t)j] = (f > 0.0) ? dm / ((0.000241 * f) * f) : 0.0;
+        }
+        const double hi = (*out)[(size_t)nsub - 1];
+        for (int j = 0; j < nsub; ++j) (*out)[(size_t)j] -= hi;
+    };
+    std::vector<double> sd, sdb((size_t)nsub, 0.0), tmp;
+    // dedisperse() at the best DM
+    delays(bestdm, &sd);
+    for (int j = 0; j < nsub; ++j) {
+        const double nb = std::floor((sd[(size_t)j] * binspersec - 0.0) + 0.5);
+        if (!(std::fabs(nb) < 9e15)) return false;      // NaN / inf delay: int() raises in the reference
+        for (int i = 0; i < npart; ++i) rotate_left(&profs[((size_t)i * nsub + j) * proflen], proflen, (long)nb, &tmp);
+        sdb[(size_t)j] = 0.0 + nb;
+    }
+    // time-summed sub-bands (profs.sum(0)) and the summed profile (.sum(0) again), both sequential
+    std::vector<double> sub((size_t)nsub * proflen, 0.0);
+    for (int i = 0; i < npart; ++i)
+        for (size_t k = 0; k < (size_t)nsub * proflen; ++k) {
+            const double v = profs[(size_t)i * nsub * proflen + k];
+            sub[k] = (i == 0) ? v : sub[k] + v;
+        }
+    std::vector<double> sumprof((size_t)proflen);
+    for (int j = 0; j < nsub; ++j)
+        for (int k = 0; k < proflen; ++k) {
+            const double v = sub[(size_t)j * proflen + k];
+            sumprof[(size_t)k] = (j == 0) ? v : sumprof[(size_t)k] + v;
+        }
+    // getprofile() + scale(): builtin min / max keep the first of equal values and let a NaN win only
+    // when it comes first
+    double mn = sumprof[0];
+    for (int k = 1; k < proflen; ++k)
+        if (sumprof[(size_t)k] < mn) mn = sumprof[(size_t)k];
+    std::vector<double> s((size_t)proflen);
+    for (int k = 0; k < proflen; ++k) s[(size_t)k] = sumprof[(size_t)k] - mn;
+    const double mean = np_pairwise(s.data(), (size_t)proflen) / (double)proflen;
+    for (int k = 0; k < proflen; ++k) s[(size_t)k] = s[(size_t)k] / mean;
+    double smin = s[0], smax = s[0];
+    for (int k = 1; k < proflen; ++k) {
+        if (s[(size_t)k] < smin) smin = s[(size_t)k];
+        if (s[(size_t)k] > smax) smax = s[(size_t)k];
+    }
+    c->profile.resize((size_t)proflen);
+    for (int k = 0; k < proflen; ++k) {
+        const double t = (s[(size_t)k] - smin) / (smax - smin);
+        c->profile[(size_t)k] = (0.0 * (1.0 - t)) + (255.0 * t);
+    }
+    c->subbands = sub;
+    // plot_chi2_vs_DM(dms[0], dms[-1], 100)
+    const int N = 100;
+    c->chis.assign((size_t)N, 0.0f);
+    const double lo = dms[0], hi = dms[(size_t)numdms - 1];
+    std::vector<double> work = sub, term((size_t)proflen), sp((size_t)proflen);
+    double dm1 = 0.0, dmlast = 0.0;
+    for (int ii = 0; ii < N; ++ii) {
+        const double dm = lo + ((hi - lo) * (double)ii) / (double)(N - 1);
+        if (ii == 1) dm1 = dm;
+        if (ii == N - 1) dmlast = dm;
+        delays(dm, &sd);
+        for (int j = 0; j < nsub; ++j) {
+            const double nb = std::floor((sd[(size_t)j] * binspersec - sdb[(size_t)j]) + 0.5);
+            if (!(std::fabs(nb) < 9e15)) return false;
+            rotate_left(&work[(size_t)j * proflen], proflen, (long)nb, &tmp);
+            sdb[(size_t)j] += nb;
+        }
+        for (int j = 0; j < nsub; ++j)
+            for (int k = 0; k < proflen; ++k) {
+                const double v = work[(size_t)j * proflen + k];
+                sp[(size_t)k] = (j == 0) ? v : sp[(size_t)k] + v;
+            }
+        for (int k = 0; k < proflen; ++k) {
+            const double d = sp[(size_t)k] - avgprof;
+            term[(size_t)k] = (d * d) / varprof;
+        }
+        c->chis[(size_t)ii] = (float)(np_pairwise(term.data(), (size_t)proflen) / ((double)proflen - 1.0));
+    }
+    info->nbin = proflen;
+    info->nsub = nsub;
+    info->n_dm = N;
+    info->params[0] = 0.0;
+    info->params[1] = bestdm;
+    info->params[2] = bary_p1;
+    info->params[3] = 0.0;
+    info->params[4] = dm1;
+    info->params[5] = dmlast;
+    info->params[6] = (double)N;
+    info->params[7] = 0.0;
+    return true;
+}
+
+}  // namespace
+
+struct pfx_pfd_scan_impl {
+    std::vector<PfdCand> cands;
+    std::vector<pfx_pfd_info> info;
+};
+
+extern "C" int pfx_pfd_scan(const char* const* paths, int64_t n, int threads, pfx_pfd_info* info, pfx_scan** out) {
+    if (!paths || n < 0 || !info || !out) return -1;
+    pfx_pfd_scan_impl* h = new (std::nothrow) pfx_pfd_scan_impl;
+    if (!h) return -1;
+    try {
+        h->cands.resize((size_t)n);
+        h->info.resize((size_t)n);
+    } catch (...) {
+        delete h;
+        return -1;
+    }
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if ((int64_t)nt > n) nt = (int)(n > 0 ? n : 1);
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            pfx_pfd_info fi;
+            memset(&fi, 0, sizeof(fi));
+            bool ok = false;
+            try {
+                ok = paths[i] != nullptr && parse_pfd(paths[i], &h->cands[(size_t)i], &fi);
+            } catch (...) {
+                ok = false;
+            }
+            fi.ok = ok ? 1 : 0;
+            if (!ok) h->cands[(size_t)i] = PfdCand();
+            h->info[(size_t)i] = fi;
+            info[i] = fi;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    *out = (pfx_scan*)h;
+    return 0;
+}
+
+extern "C" int pfx_pfd_gather(const pfx_scan* scan, const int64_t* idx, int64_t count, double* profile,
+                              double* subbands, float* dmcurve, double* params) {
+    const pfx_pfd_scan_impl* h = (const pfx_pfd_scan_impl*)scan;
+    if (!h || !idx || count < 0) return -1;
+    if (count == 0) return 0;
+    const int64_t n = (int64_t)h->cands.size();
+    if (idx[0] < 0 || idx[0] >= n) return -1;
+    const pfx_pfd_info& f0 = h->info[(size_t)idx[0]];
+    for (int64_t r = 0; r < count; ++r) {
+        if (idx[r] < 0 || idx[r] >= n) return -1;
+        const pfx_pfd_info& f = h->info[(size_t)idx[r]];
+        if (!f.ok || f.nbin != f0.nbin || f.nsub != f0.nsub || f.n_dm != f0.n_dm) return -2;
+    }
+    for (int64_t r = 0; r < count; ++r) {
+        const PfdCand& c = h->cands[(size_t)idx[r]];
+        const pfx_pfd_info& f = h->info[(size_t)idx[r]];
+        if (profile) memcpy(profile + (size_t)r * f.nbin, c.profile.data(), sizeof(double) * (size_t)f.nbin);
+        if (subbands) memcpy(subbands + (size_t)r * f.nsub * f.nbin, c.subbands.data(), sizeof(double) * (size_t)f.nsub * f.nbin);
+        if (dmcurve) memcpy(dmcurve + (size_t)r * f.n_dm, c.chis.data(), sizeof(float) * (size_t)f.n_dm);
+        if (params) memcpy(params + (size_t)r * 8, f.params, sizeof(double) * 8);
+    }
+    return 0;
+}
+
+extern "C" void pfx_pfd_free(pfx_scan* scan) { delete (pfx_pfd_scan_impl*)scan; }
+
 // ---- output rows ---------------------------------------------------------------------------------
 namespace {
 

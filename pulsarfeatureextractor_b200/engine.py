@@ -218,6 +218,23 @@ class Engine(object):
                                                  _ptr(params), self._stream()))
         return params
 
+    def score_pfd_host(self, profile, subbands, dmcurve, params, features="all"):
+        """PFD family from host arrays (what pfd_io gives): S/N and width are derived on the device
+        (pfx_pfd_params_dev), then all scores; the chi-square curve is also the array of the Lyon
+        DM statistics (PFDFile.py:553-583).  Returns numpy arrays."""
+        torch = self._torch
+        dev = torch.device("cuda", self.device)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        prof, sub, dmc, par = t(profile), t(subbands), t(dmcurve), t(params)
+        if profile.shape[0] == 0:
+            ncol = {"bates": 22, "lyon": 8, "all": 30}[features]
+            return Scores(np.empty((0, ncol)), np.zeros((0,), np.int32), np.zeros((0, _lib.PFX_NIER), np.int8))
+        self.pfd_params(prof, par)
+        out = self.score_device(prof, sub, dmc, dmc, par, features=features, family=_lib.PFX_FAMILY_PFD)
+        torch.cuda.synchronize(dev)
+        return Scores(out.features.cpu().numpy(), out.status.cpu().numpy(),
+                      out.ier.cpu().numpy() if out.ier is not None else None)
+
     def lyon8(self, profile, dmstat):
         torch = self._torch
         n = profile.shape[0]

@@ -399,3 +399,69 @@ def test_cli_output_format(eng, tmp_path):
     ok, bad = dp2.dmprofPHCX(str(d) + "/", False, str(out2), True, False)
     txt = open(out2).read()
     assert ok == 13 and "@attribute Profile_mean numeric" in txt and txt.count("?%") == 13
+
+
+def test_pfd_files_end_to_end(eng, tmp_path):
+    """.pfd files through the native reader, pfx_pfd_params_dev and the PFD family
+    kernels, against the scores of the REFERENCE's PFD.compute() and its Lyon statistics stored in
+    tests/golden/ref_pfd_v1.npz (made by tests/golden/make_golden_pfd.py with the reference's code)."""
+    from pulsarfeatureextractor_b200 import pfd_io
+    from pulsarfeatureextractor_b200.DataProcessor import DataProcessor
+    warnings.simplefilter("ignore")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_pfd_v1.npz"))
+    d = tmp_path / "pfd"
+    d.mkdir()
+    paths = []
+    for k, (seed, npart, nsub, proflen, posn, big) in enumerate(g["cases"]):
+        p = str(d / ("cand_%02d.pfd" % k))
+        pfd_io.write_pfd(p, with_position=bool(posn), big_endian=bool(big),
+                         **pfd_io.synth_pfd(int(seed), npart=int(npart), nsub=int(nsub), proflen=int(proflen)))
+        paths.append(p)
+    scan = pfd_io.PfdScan(paths)
+    det = [2, 3, 11, 12, 13, 14, 15, 19, 20, 21]
+    nok = 0
+    errs = []
+    for k, p in enumerate(paths):
+        assert scan.ok(k)
+        prof, sub, dmc, par = scan.gather([k])
+        out = eng.score_pfd_host(prof, sub, dmc, par, features="all")
+        ref = g["bates_%d" % k]
+        failed = ("fail_%d" % k) in g.files
+        assert failed == bool(out.status[0] & O.ST_FAIL_MASK), (k, hex(int(out.status[0])))
+        gl = g["lyon_%d" % k]
+        ly = out.features[0, 22:30]
+        # profile statistics in float64 as the reference; the DM-curve statistics are float32 arithmetic
+        # in the reference (PFDFile.py:567-574), float64 here: float32 rounding / cancellation apart
+        assert np.allclose(ly[:4], gl[:4], rtol=1e-9, atol=0)
+        assert np.allclose(ly[4:6], gl[4:6], rtol=2e-6, atol=0) and np.allclose(ly[6:], gl[6:], rtol=0, atol=5e-3)
+        if failed:
+            continue
+        nok += 1
+        f = out.features[0, :22]
+        for c in det:
+            assert _det_ok(ref[c], f[c]), (k, c + 1, ref[c], f[c])
+        # scores 17 and 18 (Prop, Shift of the 4-parameter DM fit) are left out of the point-wise
+        # comparison: on these chi-square curves the fit is chaotic -- scipy itself moves them by
+        # O(1) when the model expression is merely re-associated (measured: |1 - Prop| 0.957 -> 0.607,
+        # ier 5 -> 2, ...; SURVEY appendix B) -- while score 19 and the other fits are reproducible
+        e = _rel(ref, f)
+        assert np.isfinite(f[16]) and np.isfinite(f[17])
+        # the well-conditioned fits agree point-wise: both sinusoid chi-squares, the chi-square of the
+        # Gaussian + background fit, the chi-square of the theoretical DM curve
+        for c in (0, 1, 8, 18):
+            assert e[c] <= 1e-6, (k, c + 1, ref[c], f[c])
+        errs.append(e)
+    scan.close()
+    assert nok >= 6
+    # the histogram / double-Gaussian scores (5-8, 10, 11) sit on the usual noise floor of ill
+    # conditioned fits: judged by the median over the candidates
+    med = np.median(np.array(errs), axis=0)
+    for c in (4, 5, 6, 7, 9, 10):
+        assert med[c] <= 1e-4, (c + 1, med[c])
+    # the CLI classes on the same directory: one row per scored candidate, failures logged
+    outp = tmp_path / "pfd_scores.csv"
+    dp = DataProcessor(False, engine=eng, error_log=str(tmp_path / "pfd_err.txt"))
+    ok, bad = dp.processPFDCollectively(str(d) + "/", False, str(outp), False, False, False)
+    assert ok == nok and bad == len(paths) - nok
+    rows = open(outp).read().strip().split("\n")
+    assert len(rows) == nok and all(r.split(",")[0].endswith(".pfd") and len(r.split(",")) == 23 for r in rows)
