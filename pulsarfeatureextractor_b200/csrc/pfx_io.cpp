@@ -1,4 +1,4 @@
-// pfx_phcx.cpp -- libpfxio.so: streaming PHCX scanner (include/pfx_io.h).
+// pfx_io.cpp -- libpfxio.so: PHCX scanner, PRESTO .pfd reader and output-row formatter (include/pfx_io.h).
 //
 // One pass per file: inflate (zlib) -> tag scan -> hex decode -> arrays.  The scan follows the
 // document-order, n-th-occurrence rule the reference gets from minidom's getElementsByTagName

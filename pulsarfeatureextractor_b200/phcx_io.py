@@ -27,7 +27,7 @@ import re
 
 import numpy as np
 
-# ---- native scanner (include/pfx_io.h, csrc/pfx_phcx.cpp) ------------------------------------
+# ---- native scanner (include/pfx_io.h, csrc/pfx_io.cpp) ------------------------------------
 _IO_PATH = os.environ.get("PFX_IO_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpfxio.so")
 IO_EXPORTS = ["pfx_phcx_scan", "pfx_phcx_gather", "pfx_phcx_free", "pfx_pfd_scan", "pfx_pfd_gather", "pfx_pfd_free",
               "pfx_format_rows", "pfx_io_free", "pfx_io_version"]
