@@ -9,7 +9,9 @@
 // quickly simply takes more candidates (the spread in function evaluations is ~100x).
 // The rows of a candidate are dealt to the C lanes of its group (LaneGroup, pfx_lane_lm.cuh): the
 // data vector (float64 values + uint16 bin numbers) is stored once per group in shared memory with
-// the group index fastest; each lane has its own n x n workspace.
+// the group index fastest; each lane has its own n x n workspace in k_gauss_rounds, the two lanes of
+// a group share one in k_gauss_final (lane 0 runs the n x n steps and broadcasts their results), which
+// lets 96 instead of 64 candidates reside per SM.
 #include "pfx_internal.cuh"
 #include "pfx_lane_gauss.cuh"
 
@@ -59,7 +61,8 @@ constexpr int ROUNDS_LANES = PFX_ROUNDS_LANES;      // lanes per candidate in k_
 constexpr int FINAL_LANES = PFX_FINAL_LANES;        // and in k_gauss_final
 // largest block considered (bounded by 64K registers per SM)
 constexpr int ROUNDS_MAXT = ROUNDS_LANES == 1 ? 128 : (ROUNDS_LANES == 2 ? 224 : 320);
-constexpr int FINAL_MAXT = FINAL_LANES == 1 ? 128 : 192;
+constexpr int FINAL_MAXT = FINAL_LANES == 1 ? 128 : 256;
+constexpr int FINAL_WS_PER_GROUP = 1;          // the lanes of a group share the n x n workspace
 
 __global__ void __launch_bounds__(ROUNDS_MAXT, 1)
 k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
@@ -145,8 +148,19 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
               unsigned short* gxs) {
     extern __shared__ double smem[];
     typedef LaneGroup<FINAL_LANES> G;
-    const LaneBuf b = gdat ? lane_buf<FINAL_LANES>(gdat, gxs) : lane_buf_smem<FINAL_LANES>(smem, m, lane_ws_doubles(8));
-    const LaneWs ws = lane_ws(smem, 8);
+    // one n x n workspace per group: [element][group of the block]
+    const int groups = blockDim.x / FINAL_LANES;
+    LaneBuf b;
+    if (gdat) {
+        b = lane_buf<FINAL_LANES>(gdat, gxs);
+    } else {
+        double* dat = smem + (size_t)lane_ws_doubles(8) * groups;
+        b.stride = groups;
+        b.dat = dat + threadIdx.x / FINAL_LANES;
+        b.xs = (unsigned short*)(dat + (size_t)m * groups) + threadIdx.x / FINAL_LANES;
+    }
+    LaneWs ws;
+    ws.carve(smem + threadIdx.x / FINAL_LANES, groups, 8);
     Gauss8LaneT<FINAL_LANES> g;
     g.phase = GP_IDLE;
     g.cand = -1;
@@ -185,10 +199,10 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
 // block (multiple of 32 lanes, at most max_threads) whose groups fit with their data vectors in
 // shared memory.  Returns false when not even two warps fit (long profiles): the data vectors then
 // go to the global scratch and only the n x n workspaces stay in shared memory.
-static bool lane_layout(pfx_ctx* ctx, int m, int np, int lanes_per_cand, int max_threads, int extra_doubles,
+static bool lane_layout(pfx_ctx* ctx, int m, int np, int lanes_per_cand, int max_threads, int ws_per_group,
                         int* threads, size_t* smem) {
-    const size_t ws = (size_t)lane_ws_doubles(np) * 8 + (size_t)extra_doubles * 8;
-    const size_t per_group = ws * lanes_per_cand + (size_t)m * 10;
+    const size_t ws = (size_t)lane_ws_doubles(np) * 8;
+    const size_t per_group = ws * ws_per_group + (size_t)m * 10;
     const size_t budget = (size_t)ctx->smem_optin;
     for (int t = max_threads; t >= 64; t -= 32) {
         if (per_group * (t / lanes_per_cand) + 64 <= budget) {
@@ -248,7 +262,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     {
         int threads;
         size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, 0, &threads, &smem);
+        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
         if (rc) return rc;
         const int per_block = threads / ROUNDS_LANES;
@@ -266,7 +280,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     {
         int threads;
         size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, 0, &threads, &smem);
+        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
         if (rc) return rc;
         const int per_block = threads / FINAL_LANES;

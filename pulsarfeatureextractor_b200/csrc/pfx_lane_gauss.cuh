@@ -540,12 +540,12 @@ struct Gauss8LaneT {
             lm.template jac_block<B>(A, bv);
         }
         lm.template jac_combine<C>();
-        const int r = lm.jac_end(ws, m);
+        const int r = lm.template jac_end_shared<C>(ws, m);      // one n x n workspace per group
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
     }
 
     PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
-        lm.trial_begin(ws);
+        lm.template trial_begin_shared<C>(ws);
         double s = 0.0;
         for (int i = G::rank(); i < m; i += C) {
             const double f = PFX_SUB(b.d(i), value(lm.xnew, (double)i));

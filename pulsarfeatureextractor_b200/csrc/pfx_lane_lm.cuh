@@ -107,6 +107,7 @@ struct LaneGroup {
     PFX_HD static double xchg(double v, int s) { return (C == 1) ? v : __shfl_xor_sync(mask(), v, s); }
     PFX_HD static double bcast(double v) { return (C == 1) ? v : __shfl_sync(mask(), v, 0, C); }
     PFX_HD static long long bcast(long long v) { return (C == 1) ? v : __shfl_sync(mask(), v, 0, C); }
+    PFX_HD static int bcast(int v) { return (C == 1) ? v : __shfl_sync(mask(), v, 0, C); }
     PFX_HD static void sync() { if (C > 1) __syncwarp(mask()); }
 #else
     // host build (logic check): groups of one lane only; nvcc's host pass merely has to parse this
@@ -114,6 +115,7 @@ struct LaneGroup {
     PFX_HD static double xchg(double v, int) { return v; }
     PFX_HD static double bcast(double v) { return v; }
     PFX_HD static long long bcast(long long v) { return v; }
+    PFX_HD static int bcast(int v) { return v; }
     PFX_HD static void sync() {}
 #endif
     // IEEE addition and max are commutative, so both partners of an exchange get the same bits
@@ -772,6 +774,42 @@ struct LaneLM {
         }
         pnorm = sqrt(sq);
         if (iter == 1) delta = fmin(delta, pnorm);
+    }
+
+    // ---- one n x n workspace per group --------------------------------------------------------------
+    // With the workspace shared by the C lanes of a group (it is the larger part of the shared memory
+    // a fit with n = 8 needs), lane 0 runs the n x n steps and hands the state they change to the
+    // others; everything else stays redundant and bit-identical.
+    template <int C>
+    PFX_HD int jac_end_shared(const LaneWs& s, int m) {
+        typedef LaneGroup<C> G;
+        int r = 0;
+        if (G::rank() == 0) r = jac_end(s, m);
+        if (C > 1) {
+            r = G::bcast(r);
+#pragma unroll
+            for (int j = 0; j < N; ++j) diag[j] = G::bcast(diag[j]);
+            xnorm = G::bcast(xnorm);
+            delta = G::bcast(delta);
+            fnorm = G::bcast(fnorm);
+            gnorm = G::bcast(gnorm);
+            info = G::bcast(info);
+            nfev = G::bcast(nfev);
+        }
+        return r;
+    }
+    template <int C>
+    PFX_HD void trial_begin_shared(const LaneWs& s) {
+        typedef LaneGroup<C> G;
+        if (G::rank() == 0) trial_begin(s);
+        if (C > 1) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) xnew[j] = G::bcast(xnew[j]);
+            pnorm = G::bcast(pnorm);
+            rpnorm = G::bcast(rpnorm);
+            par = G::bcast(par);
+            delta = G::bcast(delta);
+        }
     }
 
     // fnorm1 = |f(xnew)|.  Returns LANE_JAC (step accepted), LANE_TRIAL (retry with a smaller
