@@ -157,7 +157,7 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
         double* dat = smem + (size_t)lane_ws_doubles(8) * groups;
         b.stride = groups;
         b.dat = dat + threadIdx.x / FINAL_LANES;
-        b.xs = (unsigned short*)(dat + (size_t)m * groups) + threadIdx.x / FINAL_LANES;
+        b.xs = nullptr;         // the 8-parameter fit runs on all bins in order: no bin numbers needed
     }
     LaneWs ws;
     ws.carve(smem + threadIdx.x / FINAL_LANES, groups, 8);
@@ -200,9 +200,9 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
 // shared memory.  Returns false when not even two warps fit (long profiles): the data vectors then
 // go to the global scratch and only the n x n workspaces stay in shared memory.
 static bool lane_layout(pfx_ctx* ctx, int m, int np, int lanes_per_cand, int max_threads, int ws_per_group,
-                        int* threads, size_t* smem) {
+                        int bytes_per_bin, int* threads, size_t* smem) {
     const size_t ws = (size_t)lane_ws_doubles(np) * 8;
-    const size_t per_group = ws * ws_per_group + (size_t)m * 10;
+    const size_t per_group = ws * ws_per_group + (size_t)m * bytes_per_bin;
     const size_t budget = (size_t)ctx->smem_optin;
     for (int t = max_threads; t >= 64; t -= 32) {
         if (per_group * (t / lanes_per_cand) + 64 <= budget) {
@@ -262,7 +262,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     {
         int threads;
         size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, &threads, &smem);
+        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, 10, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
         if (rc) return rc;
         const int per_block = threads / ROUNDS_LANES;
@@ -280,7 +280,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     {
         int threads;
         size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, &threads, &smem);
+        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, 8, &threads, &smem);
         rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
         if (rc) return rc;
         const int per_block = threads / FINAL_LANES;
