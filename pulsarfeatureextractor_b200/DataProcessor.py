@@ -36,7 +36,7 @@ def fmt_float(v, py2=True):
 
 
 class DataProcessor(object):
-    def __init__(self, debugFlag=False, engine=None, batch=4096, features=None, py2_format=True,
+    def __init__(self, debugFlag=False, engine=None, batch=32768, features=None, py2_format=True,
                  error_log="CandidateErrorLog.txt"):
         self.debug = debugFlag
         self.phcxRegex = "*.phcx.gz"

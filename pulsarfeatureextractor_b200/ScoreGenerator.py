@@ -40,7 +40,8 @@ class ScoreGenerator(object):
         parser.add_option("--features", action="store", dest="features", default=None,
                           help="bates (default), lyon or all (22 Bates followed by 8 Lyon columns)")
         parser.add_option("--gpu", action="store", dest="gpu", type="int", default=0)
-        parser.add_option("--batch", action="store", dest="batch", type="int", default=4096)
+        parser.add_option("--batch", action="store", dest="batch", type="int", default=32768,
+                          help="candidates per GPU batch (the kernels end in a tail of slow candidates, so few large batches win)")
         parser.add_option("--repr", action="store_true", dest="repr", default=False)
         args, _ = parser.parse_args(argv)
 
