@@ -163,7 +163,9 @@ int pfx::launch_hist(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* pr
         PFX_CUDA(ctx, cudaGetLastError());
         // pass 2: the few candidates whose histogram has more bins go through the warp-form kernel
         // (4096-bin scratch slot per warp); the launch is tiny when the list is empty
-        int wgrid = grid < 64 ? grid : 64;
+        // a few per cent of a synthetic batch end up here (1-2 k candidates of 100 k): one warp each, so
+        // the whole persistent grid is launched; blocks without work leave at once
+        int wgrid = grid;
         k_hist<<<wgrid, BLOCK_THREADS, smem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
                                                     take_counter(ctx, 6, st), wd, cap_smem, ctx->hist_scratch,
                                                     HIST_CAP_GLOBAL, ctx->ovf_list[par], ovf_count);
