@@ -2,20 +2,38 @@
 """
 bench.py -- throughput of the per-candidate scoring path (22 Bates + 8 Lyon) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n CANDS] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME] [--n CANDS] [--impl reference]
 
-Workload (BASELINE.json configs[1], the configuration the metric is quoted on): HTRU-shaped PHCX
-candidates -- profile u8[128], sub-bands u8[16][128], DM curve u8[256], DataBlock[0] u8[256],
-8 float64 parameters -- 100 000 per GPU, all 30 features.  A "step" is one pass of the whole
-scoring path over that batch.  Under torchrun every rank scores its own shard of the seeded
-stream (weak scaling, no collective: candidates are independent) and rank 0 prints one JSON line.
+Configurations (BASELINE.json `configs`; data are seeded, synthetic and UNTILED: every candidate of a
+batch is a different draw of pulsarfeatureextractor_b200/synth.py, generated in worker processes):
+
+  htru100k   (default; configs[1], the configuration the metric is quoted on) HTRU-shaped PHCX
+             candidates -- profile u8[128], sub-bands u8[16][128], DM curve u8[256], DataBlock[0]
+             u8[256], 8 float64 parameters -- 100 000 per GPU, all 30 features.  Weak scaling.
+  target10m  BASELINE north_star: the same shape, 10 000 000 candidates IN TOTAL (split over the
+             ranks: strong scaling), all 30 features.
+  lyon10m    configs[2]: the 8 Lyon statistics over 10 000 000 candidates in total, streamed from
+             pinned host memory (e2e) and device resident (value).
+  pfd        configs[3]: Bates 22 on PFD-shaped candidates (float64 64-bin profile, 64 x 64 float64
+             sub-bands, float32 256-trial curve, PFD constants), 100 000 per GPU.
+  survey     configs[4] shape: all 30 features on 1024-bin uint8 profiles (16 x 1024 sub-bands),
+             50 000 per GPU (the 100 M of the config do not fit one run of a few minutes).
+  --total T  with htru100k: T candidates in total split over the ranks (strong scaling).
+
+A "step" is one pass of the scoring path over the batch.  Under torchrun every rank scores its own
+shard of the seeded stream (no collective: candidates are independent) and rank 0 prints one JSON line.
 
 value   candidates/s with the batch resident in HBM (device pointers through pfx_score_dev)
 e2e     candidates/s through pfx_score_host: pinned host buffers in, feature rows out, H2D and D2H
         copies inside the timed region
-roofline  the dominant kernel (k_gauss, scores 8-11) against measured HBM bandwidth, as the metric
-        demands, plus its share of the step; the kernel is FP64/latency bound, see DESIGN.md
-cpu_baseline  the oracle (reference-faithful Python/SciPy port) on this box's host cores
+roofline       the dominant kernel pair (k_gauss_*, scores 8-11) against measured HBM bandwidth, as the
+               metric demands, plus its share of the step; the pair is FP64/latency bound, see DESIGN.md
+roofline_fp64  the same kernels against the FP64 pipe: flops per candidate counted by ncu
+               (profiles/r02_fp64_flops.json) over the live kernel time, against the DFMA peak measured
+               on this pool (profiles/r01_fp64_microbench.txt)
+roofline_lyon  the HBM-bound kernel of the path (Lyon statistics), measured live
+cpu_baseline   the oracle (reference-faithful Python/SciPy port) on this box's host cores, a bounded
+               SAMPLE of the same stream
 """
 import argparse
 import json
@@ -28,15 +46,43 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NBIN, NSUB, NDM, NDMSTAT = 128, 16, 256, 256
-CONFIG_ID = 2
-# algorithmic bytes per candidate: every input array once in its storage dtype, the
-# parameters, and the outputs (30 float64 features, 18 int8 ier, int32 status)
-BYTES_IN = NBIN + NSUB * NBIN + NDM + NDMSTAT + 8 * 8
-BYTES_OUT = 30 * 8 + 18 + 4
-BYTES_PER_CAND = BYTES_IN + BYTES_OUT
+CONFIGS = {
+    # name: stream id, nbin, nsub, n_dm, n_dmstat, per-GPU default, total (strong) default, features, family
+    "htru100k": dict(stream=2, nbin=128, nsub=16, n_dm=256, n_dmstat=256, per_gpu=100000, total=None,
+                     features="all", family="phcx", es=1, es_dm=1,
+                     workload="BASELINE configs[1]: HTRU PHCX shape, profile u8[128], sub-bands u8[16x128], "
+                              "DM curve u8[256], DataBlock0 u8[256]; all 30 features (22 Bates + 8 Lyon)"),
+    "target10m": dict(stream=2, nbin=128, nsub=16, n_dm=256, n_dmstat=256, per_gpu=None, total=10_000_000,
+                      features="all", family="phcx", es=1, es_dm=1,
+                      workload="BASELINE north_star target: 10M HTRU-shaped candidates in total, all 30 features"),
+    "lyon10m": dict(stream=3, nbin=128, nsub=16, n_dm=256, n_dmstat=256, per_gpu=None, total=10_000_000,
+                    features="lyon", family="phcx", es=1, es_dm=1,
+                    workload="BASELINE configs[2]: Lyon 8 statistics, 10M candidates in total, profile u8[128] + "
+                             "DataBlock0 u8[256], streamed from pinned host memory"),
+    "pfd": dict(stream=4, nbin=64, nsub=64, n_dm=256, n_dmstat=256, per_gpu=100000, total=None,
+                features="bates", family="pfd", es=8, es_dm=4,
+                workload="BASELINE configs[3]: Bates 22 on PFD-shaped candidates, profile f64[64], sub-bands "
+                         "f64[64x64], chi-square curve f32[256], 4-parameter DM model"),
+    "survey": dict(stream=5, nbin=1024, nsub=16, n_dm=256, n_dmstat=256, per_gpu=50000, total=None,
+                   features="all", family="phcx", es=1, es_dm=1,
+                   workload="BASELINE configs[4] shape: all 30 features, profile u8[1024], sub-bands u8[16x1024]"),
+}
+NCOL = {"all": 30, "bates": 22, "lyon": 8}
 LYON_N = 4_000_000            # candidates of the secondary, HBM-bound roofline entry
-LYON_BYTES_PER_CAND = NBIN + NDMSTAT + 64
+FP64_PEAK_TFLOPS = 34.0       # DFMA peak measured on this pool (profiles/r01_fp64_microbench.txt)
+
+
+def bytes_per_cand(c):
+    """Algorithmic bytes per candidate: every input array once in its storage dtype, the
+    parameters, and the outputs (float64 features, 18 int8 ier, int32 status)."""
+    f = c["features"]
+    b_in = c["es"] * c["nbin"]
+    if f != "lyon":
+        b_in += c["es"] * c["nsub"] * c["nbin"] + c["es_dm"] * c["n_dm"] + 8 * 8
+    if f != "bates":
+        b_in += (c["es_dm"] if c["family"] == "pfd" else 1) * c["n_dmstat"]
+    b_out = NCOL[f] * 8 + (18 + 4 if f != "lyon" else 0)
+    return b_in, b_out
 
 
 def read_peaks():
@@ -45,6 +91,14 @@ def read_peaks():
         with open(p) as fh:
             return json.load(fh).get("hbm_gbs", 6650.0), "measured"
     return 6650.0, "fallback"
+
+
+def read_json(rel):
+    p = os.path.join(ROOT, rel)
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return json.load(fh)
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -81,29 +135,72 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(n_sample, workers):
-    """Oracle (Python/SciPy port of the reference) on host cores over the first n_sample
-    candidates of the same seeded stream."""
+# ---- synthetic data (worker processes) ---------------------------------------------------------
+def _gen_part(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from pulsarfeatureextractor_b200 import synth
+    name, lo, hi = args
+    c = CONFIGS[name]
+    if c["family"] == "pfd":
+        b = synth.generate_pfd_shaped(c["stream"], lo, hi - lo, nbin=c["nbin"], nsub=c["nsub"], n_dm=c["n_dm"])
+    else:
+        lyon = c["features"] == "lyon"
+        b = synth.generate(c["stream"], lo, hi - lo, c["nbin"], c["nsub"], c["n_dm"], c["n_dmstat"],
+                           want_subbands=not lyon, want_dm=True)
+    return b.profile, b.subbands, b.dmcurve, b.dmstat, b.params
+
+
+def make_batch(name, start, n, workers):
+    """Candidates [start, start+n) of the config's seeded stream in PINNED host tensors, generated in
+    `workers` processes (4 096-candidate chunks of the stream: identical bytes however it is split)."""
+    import numpy as np
+    import torch
     import multiprocessing as mp
-    t0 = time.time()
-    with mp.Pool(workers) as pool:
-        parts = [(CONFIG_ID, i * n_sample // workers, (i + 1) * n_sample // workers) for i in range(workers)]
-        pool.map(_cpu_worker_warm, parts)          # import + generate outside the timed region
-        t0 = time.time()
-        done = sum(pool.map(_cpu_worker, parts))
-        dt = time.time() - t0
-    return done / dt, dt
+    c = CONFIGS[name]
+    step = 4096 * 4
+    first = (start // 4096) * 4096
+    parts = [(name, max(lo, start), min(lo + step, start + n)) for lo in range(first, start + n, step)]
+    parts = [p for p in parts if p[2] > p[1]]
+    pdt = torch.float64 if c["family"] == "pfd" else torch.uint8
+    ddt = torch.float32 if c["family"] == "pfd" else torch.uint8
+    lyon = c["features"] == "lyon"
+    pin = torch.cuda.is_available()
+    prof = torch.empty((n, c["nbin"]), dtype=pdt, pin_memory=pin)
+    sub = None if lyon else torch.empty((n, c["nsub"], c["nbin"]), dtype=pdt, pin_memory=pin)
+    dmc = None if lyon else torch.empty((n, c["n_dm"]), dtype=ddt, pin_memory=pin)
+    dms = torch.empty((n, c["n_dmstat"]), dtype=torch.uint8, pin_memory=pin)
+    par = torch.empty((n, 8), dtype=torch.float64, pin_memory=pin)
+
+    def place(p, res):
+        lo, hi = p[1] - start, p[2] - start
+        prof[lo:hi] = torch.from_numpy(res[0])
+        if not lyon:
+            sub[lo:hi] = torch.from_numpy(res[1])
+            dmc[lo:hi] = torch.from_numpy(res[2])
+        dms[lo:hi] = torch.from_numpy(res[3])
+        par[lo:hi] = torch.from_numpy(res[4])
+
+    if workers > 1 and len(parts) > 1:
+        with mp.get_context("fork").Pool(min(workers, len(parts))) as pool:
+            for p, res in zip(parts, pool.imap(_gen_part, parts)):
+                place(p, res)
+    else:
+        for p in parts:
+            place(p, _gen_part(p))
+    if c["family"] == "pfd":
+        dms = dmc          # PFD family: the chi-square curve is also the array of the Lyon DM statistics
+    return prof, sub, dmc, dms, par
 
 
+# ---- CPU arm -----------------------------------------------------------------------------------
 _CPU_CACHE = {}
 
 
 def _cpu_worker_warm(args):
     os.environ["OMP_NUM_THREADS"] = "1"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    from pulsarfeatureextractor_b200 import synth
-    cfg, lo, hi = args
-    _CPU_CACHE[(cfg, lo, hi)] = synth.generate(cfg, lo, hi - lo, NBIN, NSUB, NDM, NDMSTAT)
+    import pfx_oracle  # noqa: F401  (import cost outside the timed region)
+    _CPU_CACHE[args] = _gen_part(args)
     return 0
 
 
@@ -112,52 +209,89 @@ def _cpu_worker(args):
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pfx_oracle as O
-    from pulsarfeatureextractor_b200 import synth
     warnings.simplefilter("ignore")
-    cfg, lo, hi = args
-    b = _CPU_CACHE.get((cfg, lo, hi))
-    if b is None:
-        b = synth.generate(cfg, lo, hi - lo, NBIN, NSUB, NDM, NDMSTAT)
+    name, lo, hi = args
+    c = CONFIGS[name]
+    prof, sub, dmc, dms, par = _CPU_CACHE.get(args) or _gen_part(args)
+    O.FAST_CORR = False
     for i in range(hi - lo):
-        O.bates22_phcx(b.profile[i].astype(np.int64), b.subbands[i].astype(np.int64),
-                       b.dmcurve[i].astype(np.int64), b.params[i])
-        O.lyon8(b.profile[i], b.dmstat[i])
+        if c["features"] != "lyon":
+            if c["family"] == "pfd":
+                O.bates22_pfd_arrays(prof[i], sub[i], dmc[i], par[i])
+            else:
+                O.bates22_phcx(prof[i].astype(np.int64), sub[i].astype(np.int64), dmc[i].astype(np.int64), par[i])
+        if c["features"] != "bates":
+            O.lyon8(prof[i], dms[i])
     return hi - lo
+
+
+def cpu_baseline(name, n_sample, workers):
+    """Oracle (Python/SciPy port of the reference) on host cores over the first n_sample candidates of
+    the same seeded stream; data generation and imports outside the timed region."""
+    import multiprocessing as mp
+    with mp.Pool(workers) as pool:
+        parts = [(name, i * n_sample // workers, (i + 1) * n_sample // workers) for i in range(workers)]
+        parts = [p for p in parts if p[2] > p[1]]
+        pool.map(_cpu_worker_warm, parts)
+        t0 = time.time()
+        done = sum(pool.map(_cpu_worker, parts))
+        dt = time.time() - t0
+    return done / dt, dt
+
+
+def cpu_sample_size(name, workers, asked):
+    per = {"htru100k": 512, "target10m": 512, "lyon10m": 40000, "pfd": 128, "survey": 128}[name]
+    return max(workers * 8, asked or per)
+
+
+def port_note():
+    d = read_json("profiles/r02_ref_vs_port_speed.json")
+    if not d:
+        return None
+    return {"measured_in": "build container (the reference cannot travel to the GPU box)", **d}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is
     Python 2 source that cannot run on this image's Python 3, so the oracle -- its
     line-faithful Python 3 / SciPy restatement, pinned against the reference through
-    oracle/refshim.py -- is timed, on all host cores."""
+    oracle/refshim.py -- is timed, on all host cores, on a bounded SAMPLE of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    name = args.config
     workers = os.cpu_count() or 1
-    n_sample = max(workers * 8, args.cpu_sample)
+    n_sample = cpu_sample_size(name, workers, args.cpu_sample)
     vals = []
     for _ in range(max(1, args.steps)):
-        v, dt = cpu_baseline(n_sample, workers)
+        v, dt = cpu_baseline(name, n_sample, workers)
         vals.append(v)
     value = sum(vals) / len(vals)
+    cfg = workload_config(name, n_sample, 1)
+    cfg["sample_note"] = ("the CPU arm times a %d-candidate SAMPLE of the stream per step (the GPU arm scores the whole "
+                          "batch); candidates/s is size independent" % n_sample)
     line = {
         "impl": "reference", "metric": "candidates/sec (22 Bates + 8 Lyon)", "value": value,
         "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * n_sample / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n_sample),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": workers, "kind": "port",
-                         "sample": "%d candidates of the bench stream per step, all 30 features" % n_sample},
+                         "sample": "first %d candidates of the bench stream per step, features: %s"
+                                   % (n_sample, CONFIGS[name]["features"]),
+                         "port_vs_shimmed_reference": port_note()},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(n):
-    return {"workload": "BASELINE configs[1]: HTRU PHCX shape, profile u8[128], sub-bands u8[16x128], "
-                        "DM curve u8[256], DataBlock0 u8[256]; all 30 features (22 Bates + 8 Lyon)",
-            "candidates_per_gpu": n, "l2": "inputs+outputs %.0f MB per step > 126 MB L2" % (n * BYTES_PER_CAND / 1e6)}
+def workload_config(name, n, world):
+    c = CONFIGS[name]
+    b_in, b_out = bytes_per_cand(c)
+    return {"workload": c["workload"], "name": name, "candidates_per_gpu": n, "candidates_total": n * world,
+            "features": c["features"], "data_generation": "seeded, untiled (every candidate a separate draw)",
+            "l2": "inputs+outputs %.0f MB per step per GPU > 126 MB L2" % (n * (b_in + b_out) / 1e6)}
 
 
 def main():
@@ -165,10 +299,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=100000, help="candidates per GPU")
+    ap.add_argument("--config", default="htru100k", choices=sorted(CONFIGS))
+    ap.add_argument("--n", type=int, default=0, help="candidates per GPU (overrides the config)")
+    ap.add_argument("--total", type=int, default=0, help="candidates in total, split over the ranks (strong scaling)")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-sample", type=int, default=512)
+    ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--subbatches", type=int, default=-1, help="pfx_set_subbatches (development)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -176,7 +313,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from pulsarfeatureextractor_b200 import synth
+    from pulsarfeatureextractor_b200 import _lib
     from pulsarfeatureextractor_b200.engine import Engine, Scores
 
     rank = int(os.environ.get("RANK", "0"))
@@ -186,20 +323,43 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n = args.n
+    name = args.config
+    c = CONFIGS[name]
+    total = args.total or (c["total"] if not args.n else 0)
+    if total:
+        lo, hi = total * rank // world, total * (rank + 1) // world
+        n, start, scaling = hi - lo, lo, "strong"
+    else:
+        n = args.n or c["per_gpu"]
+        start, scaling = rank * n, "weak"
+    features, ncol = c["features"], NCOL[c["features"]]
+    family = _lib.PFX_FAMILY_PFD if c["family"] == "pfd" else _lib.PFX_FAMILY_PHCX
+    b_in, b_out = bytes_per_cand(c)
 
     # this rank's shard of the seeded stream, in pinned host memory
-    b = synth.generate(CONFIG_ID, rank * n, n, NBIN, NSUB, NDM, NDMSTAT)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_prof, h_sub, h_dm, h_ds, h_par = pin(b.profile), pin(b.subbands), pin(b.dmcurve), pin(b.dmstat), pin(b.params)
-    d_prof, d_sub, d_dm, d_ds, d_par = (x.to(dev) for x in (h_prof, h_sub, h_dm, h_ds, h_par))
+    workers = max(1, (os.cpu_count() or 1) // world)
+    t_gen = time.time()
+    h_prof, h_sub, h_dm, h_ds, h_par = make_batch(name, start, n, workers)
+    t_gen = time.time() - t_gen
+    to_dev = lambda x: None if x is None else x.to(dev)
+    d_prof, d_sub, d_dm, d_par = to_dev(h_prof), to_dev(h_sub), to_dev(h_dm), to_dev(h_par)
+    d_ds = d_dm if c["family"] == "pfd" else to_dev(h_ds)
     eng = Engine(local)
-    out_dev = Scores(torch.empty((n, 30), dtype=torch.float64, device=dev),
-                     torch.zeros((n,), dtype=torch.int32, device=dev),
-                     torch.zeros((n, 18), dtype=torch.int8, device=dev))
-    out_host = Scores(torch.empty((n, 30), dtype=torch.float64).pin_memory(),
-                      torch.zeros((n,), dtype=torch.int32).pin_memory(),
-                      torch.zeros((n, 18), dtype=torch.int8).pin_memory())
+    if args.subbatches >= 0:
+        eng.set_subbatches(args.subbatches)
+    bates = features != "lyon"
+    if bates:
+        eng.reserve(eng.make_shape(d_prof, d_sub, d_dm, d_ds, family), n)
+        if c["family"] == "pfd":
+            eng.pfd_params(d_prof, d_par)       # S/N and width from the profile (PFDOperations.py:130-231)
+            torch.cuda.synchronize()
+            h_par.copy_(d_par)
+    out_dev = Scores(torch.empty((n, ncol), dtype=torch.float64, device=dev),
+                     torch.zeros((n,), dtype=torch.int32, device=dev) if bates else None,
+                     torch.zeros((n, 18), dtype=torch.int8, device=dev) if bates else None)
+    out_host = Scores(torch.empty((n, ncol), dtype=torch.float64).pin_memory(),
+                      torch.zeros((n,), dtype=torch.int32).pin_memory() if bates else None,
+                      torch.zeros((n, 18), dtype=torch.int8).pin_memory() if bates else None)
 
     def barrier():
         if world > 1:
@@ -207,13 +367,22 @@ def main():
         torch.cuda.synchronize()
 
     def step_dev():
-        eng.score_device(d_prof, d_sub, d_dm, d_ds, d_par, features="all", out=out_dev)
+        eng.score_device(d_prof, d_sub, d_dm, d_ds, d_par, features=features, family=family, out=out_dev)
 
     def step_host():
-        eng.score_host(h_prof, h_sub, h_dm, h_ds, h_par, features="all", out=out_host)
+        eng.score_host(h_prof, h_sub, h_dm, h_ds, h_par, features=features, family=family, out=out_host)
 
-    for _ in range(args.warmup):
-        step_dev()
+    # warm-up: at least three passes; for the multi-second configurations on a 100 000-candidate slice
+    long_step = n > 400000 and bates
+    if long_step:
+        wn = 100000
+        w_out = Scores(out_dev.features[:wn], out_dev.status[:wn], out_dev.ier[:wn])
+        for _ in range(max(3, args.warmup)):
+            eng.score_device(d_prof[:wn], d_sub[:wn], d_dm[:wn], d_ds[:wn], d_par[:wn], features=features,
+                             family=family, out=w_out)
+    else:
+        for _ in range(max(3, args.warmup)):
+            step_dev()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
@@ -227,21 +396,27 @@ def main():
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    # one more step with the score groups serialised and timed individually (CUDA events inside
-    # libpfx): kernel durations for the roofline entry and the per-stage table
-    eng.set_stage_timing(True)
-    step_dev()
-    stage = eng.last_timing()
-    # and one with the production stream layout, recording when each group completed
-    eng.set_stage_timing(2)
-    step_dev()
-    trace = eng.last_timing()
-    eng.set_stage_timing(False)
-    launches = int(stage.get("launches", 0)) * args.steps
+    stage, trace, launches = {}, {}, 0
+    if bates:
+        launches = int(eng.last_timing().get("launches", 0)) * args.steps
+        if not long_step:
+            # one more step with the score groups serialised and timed individually (CUDA events inside
+            # libpfx): kernel durations for the roofline entries and the per-stage table
+            eng.set_stage_timing(True)
+            step_dev()
+            stage = eng.last_timing()
+            # and one with the production stream layout, recording when each group completed
+            eng.set_stage_timing(2)
+            step_dev()
+            trace = eng.last_timing()
+            eng.set_stage_timing(False)
+    else:
+        launches = args.steps
 
     # ---- end to end through the host-buffer call ---------------------------------------------
-    for _ in range(min(2, args.warmup)):
-        step_host()
+    if not long_step:
+        for _ in range(min(2, args.warmup)):
+            step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -254,8 +429,8 @@ def main():
     if rank == 0:
         gen = torch.Generator(device=dev)
         gen.manual_seed(7)
-        lp = torch.randint(0, 256, (LYON_N, NBIN), dtype=torch.uint8, device=dev, generator=gen)
-        ld_ = torch.randint(0, 256, (LYON_N, NDMSTAT), dtype=torch.uint8, device=dev, generator=gen)
+        lp = torch.randint(0, 256, (LYON_N, 128), dtype=torch.uint8, device=dev, generator=gen)
+        ld_ = torch.randint(0, 256, (LYON_N, 256), dtype=torch.uint8, device=dev, generator=gen)
         for _ in range(3):
             eng.lyon8(lp, ld_)
         torch.cuda.synchronize()
@@ -267,13 +442,15 @@ def main():
         torch.cuda.synchronize()
         lyon_ms = l0.elapsed_time(l1) / 5
         peak_l, kind_l = read_peaks()
-        ach = LYON_N * LYON_BYTES_PER_CAND / (lyon_ms / 1000.0) / 1e9
+        lyon_bytes = 128 + 256 + 64
+        ach = LYON_N * lyon_bytes / (lyon_ms / 1000.0) / 1e9
+        prof_l = read_json("profiles/r02_lyon_summary.json") or {}
         lyon_roof = {"bound": "hbm", "kernel": "k_lyon8_u8<1,2> (8 Lyon statistics, uint8 rows)",
                      "achieved": ach, "peak": peak_l, "peak_kind": kind_l, "unit": "GB/s", "frac": ach / peak_l,
-                     "traffic": LYON_N * 446.0, "candidates": LYON_N, "kernel_ms": lyon_ms,
-                     "candidates_per_s": LYON_N / (lyon_ms / 1000.0),
-                     "note": "traffic: ncu dram read+write of the 10M-candidate capture, 446 B/candidate "
-                             "(profiles/r01_lyon_r1_summary.csv) against 448 B algorithmic"}
+                     "traffic": LYON_N * prof_l.get("dram_bytes_per_candidate", 446.0), "candidates": LYON_N,
+                     "kernel_ms": lyon_ms, "candidates_per_s": LYON_N / (lyon_ms / 1000.0),
+                     "note": "traffic: ncu dram read+write per candidate (%s) against %d B algorithmic"
+                             % (prof_l.get("source", "profiles/r01_lyon_r1_summary.csv"), lyon_bytes)}
         del lp, ld_
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -282,7 +459,7 @@ def main():
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = float(times[0]), float(times[1])
-    ok = int(((out_host.status.numpy() & 0x3df) == 0).sum())
+    ok = int(((out_host.status.numpy() & 0x3df) == 0).sum()) if bates else n
     fd, fh = out_dev.features.cpu(), out_host.features
     diff = ~((fd == fh) | (torch.isnan(fd) & torch.isnan(fh)))
     same = not bool(diff.any())
@@ -292,47 +469,67 @@ def main():
 
     if rank == 0:
         peak, peak_kind = read_peaks()
-        total = n * world
-        value = total * args.steps / (ms_dev / 1000.0)
-        e2e = total * args.steps / (ms_e2e / 1000.0)
-        gauss_ms = stage.get("gauss", 0.0)
-        # algorithmic bytes per candidate of the path x candidates per launch, over the
-        # duration of the dominant kernel pair
-        achieved = n * BYTES_PER_CAND / (gauss_ms / 1000.0) / 1e9 if gauss_ms > 0 else 0.0
-        step_gbs = n * BYTES_PER_CAND / (ms_dev / args.steps / 1000.0) / 1e9
+        total_n = n * world if not total else total
+        value = total_n * args.steps / (ms_dev / 1000.0)
+        e2e = total_n * args.steps / (ms_e2e / 1000.0)
         line = {
             "metric": "candidates/sec (22 Bates + 8 Lyon)", "value": value, "unit": "candidates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(n),
-            "e2e": {"value": e2e, "unit": "candidates/s", "h2d_bytes_per_step": n * BYTES_IN,
-                    "d2h_bytes_per_step": n * BYTES_OUT, "ms_per_step": ms_e2e / args.steps},
+            "config": workload_config(name, n, world),
+            "e2e": {"value": e2e, "unit": "candidates/s", "h2d_bytes_per_step": n * b_in,
+                    "d2h_bytes_per_step": n * b_out, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "k_gauss_rounds + k_gauss_final (scores 8-11, 10 LM solves per candidate)",
-                         "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": n * 337.7,
-                         "kernel_ms": gauss_ms, "kernel_share_of_step": gauss_ms / (ms_dev / args.steps),
-                         "whole_step_gbs": step_gbs, "whole_step_frac": step_gbs / peak,
-                         "note": "the Bates path is FP64/latency bound (~1e3 flop per input byte, 10 Levenberg-"
-                                 "Marquardt solves per candidate in this kernel pair), so its HBM fraction is "
-                                 "tiny by construction; the HBM-bound kernel of the path is reported in roofline_lyon. "
-                                 "traffic: ncu dram read+write of k_gauss_rounds at 100k candidates, 337.7 B/candidate "
-                                 "(profiles/r01_gauss_final_build_summary.csv: profile row in, carry record and scores "
-                                 "out; no re-reads); same capture: issue slots 25.7% busy, FP64 pipe 19.8%, 14.9 of 32 "
-                                 "lanes active per instruction, top stall = fixed-latency dependency (wait)"},
             "roofline_lyon": lyon_roof,
-            "stage_ms_serialised": {k: v for k, v in stage.items() if k != "launches"},
-            "stage_done_ms_overlapped": {k: v for k, v in trace.items() if k not in ("launches", "subband")},
             "clocks": sampler.summary(),
-            "rows_valid": ok, "host_equals_device": same,
+            "rows_valid": ok, "host_equals_device": same, "data_generation_s": t_gen,
         }
+        step_gbs = n * (b_in + b_out) / (ms_dev / args.steps / 1000.0) / 1e9
+        if bates:
+            gauss_ms = stage.get("gauss", 0.0)
+            prof_g = read_json("profiles/r02_gauss_summary.json") or {}
+            traffic = prof_g.get("dram_bytes_per_candidate", 337.7)
+            # algorithmic bytes per candidate of the path x candidates per launch, over the
+            # duration of the dominant kernel pair
+            achieved = n * (b_in + b_out) / (gauss_ms / 1000.0) / 1e9 if gauss_ms > 0 else step_gbs
+            line["roofline"] = {
+                "bound": "hbm", "kernel": "k_gauss_rounds + k_gauss_final (scores 8-11, 10 LM solves per candidate)",
+                "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": n * traffic,
+                "kernel_ms": gauss_ms, "kernel_share_of_step": gauss_ms / (ms_dev / args.steps) if gauss_ms else None,
+                "whole_step_gbs": step_gbs, "whole_step_frac": step_gbs / peak,
+                "note": "the Bates path is FP64/latency bound (~1e3 flop per input byte, 10 Levenberg-Marquardt solves "
+                        "per candidate in this kernel pair), so its HBM fraction is tiny by construction: see "
+                        "roofline_fp64 for the pipe that bounds it and roofline_lyon for the HBM-bound kernel of the "
+                        "path.  traffic: ncu dram read+write per candidate (%s)"
+                        % prof_g.get("source", "profiles/r01_gauss_final_build_summary.csv")}
+            flops = read_json("profiles/r02_fp64_flops.json")
+            if flops and gauss_ms > 0 and name in ("htru100k", "target10m"):
+                per_cand = flops["gauss_pair_fp64_flop_per_candidate"]
+                ach = n * per_cand / (gauss_ms / 1000.0) / 1e12
+                line["roofline_fp64"] = {
+                    "bound": "fp64", "kernel": "k_gauss_rounds + k_gauss_final", "achieved": ach,
+                    "peak": FP64_PEAK_TFLOPS, "peak_kind": "measured DFMA micro-benchmark (profiles/r01_fp64_microbench.txt)",
+                    "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "flop_per_candidate": per_cand,
+                    "kernel_ms": gauss_ms,
+                    "note": "flops = 2 x DFMA + DADD + DMUL thread instructions counted by ncu (%s), "
+                            "x candidates of this step / live kernel time" % flops.get("source", "profiles/")}
+            line["stage_ms_serialised"] = {k: v for k, v in stage.items() if k != "launches"}
+            line["stage_done_ms_overlapped"] = {k: v for k, v in trace.items() if k not in ("launches", "subband")}
+        else:
+            line["roofline"] = {"bound": "hbm", "kernel": "k_lyon8_u8 (the whole step is this kernel)",
+                                "achieved": step_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                                "frac": step_gbs / peak, "traffic": n * 446.0, "kernel_ms": ms_dev / args.steps,
+                                "note": "e2e is bound by the host link (PCIe), value by HBM"}
         if not args.no_cpu and world == 1:
             workers = os.cpu_count() or 1
-            ns = max(workers * 8, args.cpu_sample)
-            v, dt = cpu_baseline(ns, workers)
+            ns = cpu_sample_size(name, workers, args.cpu_sample)
+            v, dt = cpu_baseline(name, ns, workers)
             line["cpu_baseline"] = {"value": v, "unit": "candidates/s", "cores": workers, "kind": "port",
-                                    "sample": "first %d candidates of the same stream, all 30 features, %.1f s" % (ns, dt)}
+                                    "sample": "first %d candidates of the same stream, features %s, %.1f s"
+                                              % (ns, features, dt),
+                                    "port_vs_shimmed_reference": port_note()}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

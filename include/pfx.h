@@ -11,7 +11,14 @@
  *     reference keeps on its operator object (self.snr/dm/period/width, PHCXOperations.py:107-110)
  *     travel in the batch (`params`).
  *   - `*_dev` entry points take DEVICE pointers, enqueue work on `stream` (a cudaStream_t
- *     passed as void*) and return without synchronising.  `pfx_score_host` takes HOST pointers,
+ *     passed as void*) and return without synchronising, provided the context's scratch is large
+ *     enough: it grows on demand (a device allocation, and a device synchronisation when an older
+ *     block has to be freed), so call pfx_reserve() once with the largest batch to keep every later
+ *     call free of allocations and host synchronisation.  Any number of calls may be in flight on
+ *     any streams of one context: scratch is handed out in sets whose reuse is ordered on the device
+ *     by events (more calls in flight than sets serialise, they never share scratch).  The host-side
+ *     entry points of one context are not re-entrant: one host thread per context.
+ *     `pfx_score_host` takes HOST pointers,
  *     streams chunks through context-owned device staging buffers (H2D copy, kernels, D2H
  *     copy) and returns when the results are in the caller's host arrays.
  *   - All data buffers are caller-owned.  The context owns only scratch.
@@ -137,6 +144,17 @@ void pfx_destroy(pfx_ctx* ctx);
 const char* pfx_last_error(const pfx_ctx* ctx);
 /* SM count, shared memory per block and scratch bytes held by the context. */
 int pfx_device_info(const pfx_ctx* ctx, int* sm_count, int* smem_per_block, size_t* scratch_bytes);
+
+/* Size the context's scratch for batches of up to n_max candidates of this shape (work-queue
+ * counters, the records passed between the two Gaussian kernels, histogram buffers; staging of
+ * pfx_score_host is sized by its first call).  After it no *_dev call with n <= n_max and this shape
+ * allocates or synchronises.  Optional: without it scratch grows lazily inside the calls. */
+int pfx_reserve(pfx_ctx* ctx, const pfx_shape* shape, int64_t n_max);
+/* The histogram -> Gaussian chain of pfx_score_dev (the long pole, a persistent kernel pair that ends
+ * in a tail of slow candidates) is cut into `nsub` sub-batches on separate streams so that the tail
+ * of one overlaps the body of the next; 0 = default (4 for batches of 64 Ki candidates and more),
+ * 1 = off.  Results do not depend on it: a candidate's row is a function of the candidate alone. */
+int pfx_set_subbatches(pfx_ctx* ctx, int nsub);
 
 /* ---- Lyon statistics -------------------------------------------------------------------
  * Replaces PHCX.computeProfileStatScores / computeDMCurveStatScores (PHCXFile.py:320-379,

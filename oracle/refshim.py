@@ -22,8 +22,14 @@ in-memory source transformation and executes the result:
                ``x == []``     -> ``_eq_emptylist(x)``     2014-era numpy returned False for
                                                            ``ndarray == []``; numpy 2 raises
                ``range(...)``  -> ``list(range(...))``     Python 2 ``range`` is a list
-  environment  stub ``matplotlib`` / ``matplotlib.pyplot`` / ``PIL`` modules (debug plotting only),
-               ``scipy.std = numpy.std`` (the alias the reference imports, ProfileOperations.py:153)
+  environment  stub ``matplotlib`` / ``matplotlib.pyplot`` / ``matplotlib.image`` / ``PIL`` modules
+               (debug plotting only),
+               ``scipy.std = numpy.std`` (the alias the reference imports, ProfileOperations.py:153),
+               ``str(x)`` of a float (Python float or numpy.float64) -> Python 2's ``float.__str__``:
+               ``'%.12g'`` plus ``'.0'`` when the result has neither ``'.'`` nor an exponent
+               (CPython 2.7 ``float_str``: ``PyOS_double_to_string(v, 'g', 12, Py_DTSF_ADD_DOT_0)``;
+               numpy < 1.14 printed ``float64`` the same way).  Only the writer uses it
+               (``",".join(map(str, scores))``, DataProcessor.py:321,421,442).
 
 It is used (a) by ``tests/golden/make_golden.py`` to generate the committed golden
 vectors and (b) by ``tests/test_oracle_vs_reference.py`` (skipped when
@@ -52,6 +58,7 @@ _MODULE_ORDER = [
     "SUPERBPHCXFile",
     "PFDFile",
     "Candidate",
+    "DataProcessor",
 ]
 
 
@@ -77,6 +84,21 @@ def _py2div(a, b):
     if _is_intlike(a) and _is_intlike(b):
         return a // b
     return a / b
+
+
+def _py2str(*args, **kwargs):
+    """Python 2 ``str``: floats print with 12 significant digits (see the module docstring)."""
+    if len(args) == 1 and not kwargs and isinstance(args[0], float):
+        v = float(args[0])
+        if v != v:
+            return "nan"
+        if v in (float("inf"), float("-inf")):
+            return "inf" if v > 0 else "-inf"
+        t = "%.12g" % v
+        if "." not in t and "e" not in t:
+            t += ".0"
+        return t
+    return builtins.str(*args, **kwargs)
 
 
 def _eq_emptylist(x):
@@ -146,7 +168,7 @@ def _text_fix(src):
 
 def _install_stubs():
     created = []
-    for name in ("matplotlib", "matplotlib.pyplot", "PIL", "PIL.Image", "Image"):
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.image", "PIL", "PIL.Image", "Image"):
         if name not in sys.modules:
             try:
                 __import__(name)
@@ -182,6 +204,7 @@ def load_reference(src=REF_SRC, quiet=True):
             mod.__file__ = path
             mod.__dict__["_py2div"] = _py2div
             mod.__dict__["_eq_emptylist"] = _eq_emptylist
+            mod.__dict__["str"] = _py2str
             if quiet:
                 mod.__dict__["print"] = lambda *a, **k: None
             sys.modules[name] = mod

@@ -22,9 +22,13 @@ class Candidate(object):
 
     # ---- reader dispatch (Candidate.py:136-150) ------------------------------------------------
     def family(self):
-        if ".pfd" in self.candidateName:
+        # the reference tests the whole path for the substrings (Candidate.py:136-150); the file name
+        # is what is meant, and a directory called 'x.pfd' must not re-route PHCX files
+        import os
+        name = os.path.basename(self.candidateName)
+        if ".pfd" in name:
             return "pfd"
-        if ".gz" in self.candidateName:
+        if ".gz" in name:
             return "phcx"
         return "superb"
 

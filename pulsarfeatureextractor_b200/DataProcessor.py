@@ -134,7 +134,7 @@ class DataProcessor(object):
                 feat[ks] = out.features
                 okm[ks] = ok
 
-            if phcx_io.native_available() and all(".pfd" in p for p in chunk):
+            if phcx_io.native_available() and all(".pfd" in os.path.basename(p) for p in chunk):
                 # PRESTO .pfd files: native reader (de-dispersion, profile, sub-bands, chi-square curve),
                 # S/N and width on the device, PFD family constants
                 scan = pfd_io.PfdScan(chunk)
@@ -152,7 +152,7 @@ class DataProcessor(object):
                     feat[ks] = out.features
                     okm[ks] = ok
                 scan.close()
-            elif phcx_io.native_available() and not any(".pfd" in p for p in chunk):
+            elif phcx_io.native_available() and not any(".pfd" in os.path.basename(p) for p in chunk):
                 # bulk path: native scanner, rows gathered per shape into pinned buffers
                 scan = phcx_io.Scan(chunk)
                 groups = {}

@@ -12,8 +12,10 @@ ScoreGenerator -- command line of the reference (ScoreGenerator.py:99-292), flag
   --label     (reference: interactive labelling; not part of the scoring path)
   --dmprof    the 8 Lyon statistics instead of the 22 Bates scores
 
-Additive options of this build: --features {bates,lyon,all}, --gpu N, --batch N, --repr
-(shortest round-trip float formatting instead of Python 2's 12 significant digits).
+Additive options of this build: --features {bates,lyon,all}, --gpu N (first device), --gpus G (score
+on G devices of this box: candidates are dealt to one context and host thread per device, rows come
+back in input order), --batch N, --repr (shortest round-trip float formatting instead of Python 2's
+12 significant digits).
 """
 import os
 import sys
@@ -40,6 +42,8 @@ class ScoreGenerator(object):
         parser.add_option("--features", action="store", dest="features", default=None,
                           help="bates (default), lyon or all (22 Bates followed by 8 Lyon columns)")
         parser.add_option("--gpu", action="store", dest="gpu", type="int", default=0)
+        parser.add_option("--gpus", action="store", dest="gpus", type="int", default=1,
+                          help="number of GPUs of this box to shard the candidates over (no collective)")
         parser.add_option("--batch", action="store", dest="batch", type="int", default=32768,
                           help="candidates per GPU batch (the kernels end in a tail of slow candidates, so few large batches win)")
         parser.add_option("--repr", action="store_true", dest="repr", default=False)
@@ -67,8 +71,9 @@ class ScoreGenerator(object):
         print("\tOutput path:", args.outputPath, "\n\tCandidate directory:", args.candDir,
               "\n\tWrite to single file:", single_file, "\n\tProcess single candidate:", process_single, "\n")
 
-        from .engine import Engine
-        dp = DataProcessor(args.verbose, engine=Engine(args.gpu), batch=args.batch, features=args.features,
+        from .engine import make_engine
+        batch = args.batch * max(1, args.gpus)
+        dp = DataProcessor(args.verbose, engine=make_engine(args.gpus, args.gpu), batch=batch, features=args.features,
                            py2_format=not args.repr)
         if args.label:
             print("Labelling is interactive and outside the scoring path; nothing to do.")
@@ -85,7 +90,10 @@ class ScoreGenerator(object):
             else:
                 dp.processPHCXCollectively(search, args.verbose, args.outputPath, args.arff, args.profile, process_single)
         elif args.pfd and not args.phcx and not args.superb:
-            dp.processPFDCollectively(search, args.verbose, args.outputPath, args.arff, args.profile, process_single)
+            if not single_file:         # ScoreGenerator.py:205-211 of the reference
+                dp.processPFDSeparately(search, args.verbose, process_single)
+            else:
+                dp.processPFDCollectively(search, args.verbose, args.outputPath, args.arff, args.profile, process_single)
         elif args.superb and not args.pfd and not args.phcx:
             dp.processSUPERBCollectively(search, args.verbose, args.outputPath, args.arff, args.profile, process_single)
         elif not args.superb:

@@ -33,6 +33,7 @@ EXPORTS = [
     "pfx_version", "pfx_create", "pfx_destroy", "pfx_last_error", "pfx_device_info",
     "pfx_lyon8_dev", "pfx_pfd_params_dev", "pfx_sinusoid_dev", "pfx_gaussian_dev", "pfx_dmfit_dev", "pfx_subband_dev",
     "pfx_score_dev", "pfx_score_host", "pfx_last_timing", "pfx_set_stage_timing",
+    "pfx_reserve", "pfx_set_subbatches",
 ]
 
 
@@ -79,6 +80,8 @@ def load():
     lib.pfx_score_host.argtypes = [vp, sp, i64, ctypes.c_uint32, vp, vp, vp, vp, vp, dp, i64, vp, vp, i64]
     lib.pfx_last_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.pfx_set_stage_timing.argtypes = [vp, ctypes.c_int]
+    lib.pfx_reserve.argtypes = [vp, sp, i64]
+    lib.pfx_set_subbatches.argtypes = [vp, ctypes.c_int]
     for name in EXPORTS:
         getattr(lib, name)
     return lib

@@ -36,11 +36,15 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (cudaMalloc(&ctx->counters, sizeof(u64) * COUNTER_SLOTS * COUNTERS_PER_SLOT) != cudaSuccess) {
+    if (cudaMalloc(&ctx->counters, sizeof(u64) * N_SETS * COUNTERS_PER_SET) != cudaSuccess) {
         free(ctx);
         return PFX_ERR_NOMEM;
     }
-    ctx->scratch_bytes = sizeof(u64) * COUNTER_SLOTS * COUNTERS_PER_SLOT;
+    ctx->scratch_bytes = sizeof(u64) * N_SETS * COUNTERS_PER_SET;
+    for (int i = 0; i < N_SETS; ++i) {
+        ctx->sets[i].counters = ctx->counters + (size_t)i * COUNTERS_PER_SET;
+        cudaEventCreateWithFlags(&ctx->sets[i].done, cudaEventDisableTiming);
+    }
     for (int i = 0; i < N_EVENTS; ++i) cudaEventCreate(&ctx->ev[i]);
     for (int i = 0; i < 2; ++i) {
         cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking);
@@ -49,7 +53,16 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
         cudaEventCreateWithFlags(&ctx->join2_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->hist_ev[i], cudaEventDisableTiming);
     }
+    for (int i = 0; i < MAX_SUB; ++i) {
+        cudaStreamCreateWithFlags(&ctx->sub[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&ctx->sub_ev[i], cudaEventDisableTiming);
+    }
+    // sub-batches of the histogram -> Gaussian chain per call (see score_dev_impl); PFX_SUBBATCH
+    // overrides the default for experiments
+    ctx->subbatch = 0;
+    if (const char* e = getenv("PFX_SUBBATCH")) ctx->subbatch = atoi(e);
     *out = ctx;
     return PFX_OK;
 }
@@ -59,13 +72,12 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     cudaFree(ctx->counters);
-    if (ctx->hist_scratch) cudaFree(ctx->hist_scratch);
-    if (ctx->carry) cudaFree(ctx->carry);
-    for (int i = 0; i < 4; ++i)
-        if (ctx->lane_buf[i]) cudaFree(ctx->lane_buf[i]);
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->hist_lane_buf[i]) cudaFree(ctx->hist_lane_buf[i]);
-        if (ctx->ovf_list[i]) cudaFree(ctx->ovf_list[i]);
+    for (int i = 0; i < N_SETS; ++i) {
+        pfx_scratch_set& t = ctx->sets[i];
+        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp};
+        for (pfx_buf* b : bufs)
+            if (b->p) cudaFree(b->p);
+        cudaEventDestroy(t.done);
     }
     for (int i = 0; i < 2; ++i) {
         if (ctx->stage[i]) cudaFree(ctx->stage[i]);
@@ -75,6 +87,11 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
         cudaEventDestroy(ctx->join2_ev[i]);
         cudaEventDestroy(ctx->fork_ev[i]);
         cudaEventDestroy(ctx->join_ev[i]);
+        cudaEventDestroy(ctx->hist_ev[i]);
+    }
+    for (int i = 0; i < MAX_SUB; ++i) {
+        cudaStreamDestroy(ctx->sub[i]);
+        cudaEventDestroy(ctx->sub_ev[i]);
     }
     for (int i = 0; i < N_EVENTS; ++i) cudaEventDestroy(ctx->ev[i]);
     free(ctx);
@@ -117,7 +134,74 @@ static int check_bates_shape(pfx_ctx* ctx, const pfx_shape* s) {
     return PFX_OK;
 }
 
-static void rotate_counters(pfx_ctx* ctx) { ctx->counter_slot = (ctx->counter_slot + 1) % COUNTER_SLOTS; }
+pfx_scratch_set* pfx::take_set(pfx_ctx* ctx, cudaStream_t st) {
+    pfx_scratch_set* set = &ctx->sets[ctx->set_rr];
+    ctx->set_rr = (ctx->set_rr + 1) % N_SETS;
+    if (set->used) cudaStreamWaitEvent(st, set->done, 0);      // behind the set's previous user, on the device
+    set->used = true;
+    return set;
+}
+
+void pfx::release_set(pfx_ctx*, pfx_scratch_set* set, cudaStream_t st) { cudaEventRecord(set->done, st); }
+
+int pfx::ensure_buf(pfx_ctx* ctx, pfx_buf* b, size_t need) {
+    if (b->bytes >= need) return PFX_OK;
+    if (b->p) {
+        // the old block may be in use by a call in flight: freeing it waits for the device
+        cudaDeviceSynchronize();
+        cudaFree(b->p);
+        ctx->scratch_bytes -= b->bytes;
+        b->p = nullptr;
+        b->bytes = 0;
+    }
+    need = (need + 255) / 256 * 256;
+    PFX_CUDA(ctx, cudaMalloc(&b->p, need));
+    b->bytes = need;
+    ctx->scratch_bytes += need;
+    return PFX_OK;
+}
+
+int pfx::persistent_grid_impl(pfx_ctx* ctx, const void* fn, int threads, size_t smem, int* grid) {
+    for (int i = 0; i < ctx->n_grid_cache; ++i) {
+        const pfx_grid_cache_entry& e = ctx->grid_cache[i];
+        if (e.fn == fn && e.threads == threads && e.smem == smem) {
+            *grid = e.grid;
+            return PFX_OK;
+        }
+    }
+    PFX_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    PFX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    if (per_sm < 1)
+        return set_err(ctx, PFX_ERR_UNSUPPORTED,
+                       "kernel needs %zu bytes of shared memory per block, limit %d", smem, ctx->smem_optin);
+    *grid = per_sm * ctx->sm_count;
+    // the attribute is per function, not per launch: the cache keeps the last shared-memory size
+    // set for a function valid by dropping entries of the same function with another size
+    int w = 0;
+    for (int i = 0; i < ctx->n_grid_cache; ++i)
+        if (ctx->grid_cache[i].fn != fn) ctx->grid_cache[w++] = ctx->grid_cache[i];
+    ctx->n_grid_cache = w;
+    if (ctx->n_grid_cache < (int)(sizeof(ctx->grid_cache) / sizeof(ctx->grid_cache[0]))) {
+        pfx_grid_cache_entry& e = ctx->grid_cache[ctx->n_grid_cache++];
+        e.fn = fn;
+        e.threads = threads;
+        e.smem = smem;
+        e.grid = *grid;
+    }
+    return PFX_OK;
+}
+
+// Number of sub-batches the Gaussian chain of a call is cut into.  The persistent lane kernels end
+// in a tail set by the slowest candidates (one candidate can take as long as six average ones);
+// with S sub-batches on S streams the blocks freed by the tail of one sub-batch are taken by the
+// body of the next, and the final-fit kernel of sub-batch k runs next to the rounds of k + 1.
+static int pick_subbatches(const pfx_ctx* ctx, int64_t n) {
+    int s = ctx->subbatch > 0 ? ctx->subbatch : 4;
+    if (s > MAX_SUB) s = MAX_SUB;
+    while (s > 1 && n / s < 16384) --s;
+    return s;
+}
 
 // =============================================================================================
 // device-pointer entry points
@@ -140,8 +224,11 @@ extern "C" int pfx_sinusoid_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n,
     if (n == 0) return PFX_OK;
     if (!profile || !feat || feat_ld < 4) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
-    rotate_counters(ctx);
-    return launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, (cudaStream_t)stream, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    pfx_scratch_set* set = take_set(ctx, st);
+    rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, set, 0);
+    release_set(ctx, set, st);
+    return rc;
 }
 
 extern "C" int pfx_gaussian_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
@@ -151,13 +238,12 @@ extern "C" int pfx_gaussian_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n,
     if (n == 0) return PFX_OK;
     if (!profile || !feat || !status || feat_ld < 11) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
-    rotate_counters(ctx);
-    {
-        cudaStream_t st = (cudaStream_t)stream;
-        rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 0);
-        if (rc) return rc;
-        return launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
-    }
+    cudaStream_t st = (cudaStream_t)stream;
+    pfx_scratch_set* set = take_set(ctx, st);
+    rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, set, 0);
+    if (!rc) rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, set, 1);
+    release_set(ctx, set, st);
+    return rc;
 }
 
 extern "C" int pfx_dmfit_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
@@ -169,8 +255,11 @@ extern "C" int pfx_dmfit_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, co
     if (n == 0) return PFX_OK;
     if (!dmcurve || !params || !feat || !status || feat_ld < 19) return set_err(ctx, PFX_ERR_INVALID, "bad argument");
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
-    rotate_counters(ctx);
-    return launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, (cudaStream_t)stream, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    pfx_scratch_set* set = take_set(ctx, st);
+    rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, st, set, 0);
+    release_set(ctx, set, st);
+    return rc;
 }
 
 extern "C" int pfx_pfd_params_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile,
@@ -192,8 +281,45 @@ extern "C" int pfx_subband_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, 
     if (!profile || !subbands || !params || !feat || !status || feat_ld < 22)
         return set_err(ctx, PFX_ERR_INVALID, "bad argument");
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
-    rotate_counters(ctx);
-    return launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, (cudaStream_t)stream, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    pfx_scratch_set* set = take_set(ctx, st);
+    rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, st, set, 0);
+    release_set(ctx, set, st);
+    return rc;
+}
+
+// The histogram -> Gaussian chain of one call: the histogram stage over the whole batch on `st`,
+// then the two Gaussian kernels per sub-batch, each sub-batch on its own stream with its own scratch
+// set, joined back into `st`.  Returns the first error; the streams are joined in any case.
+static int launch_hist_gauss(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, const void* profile, double* feat,
+                             int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set,
+                             cudaEvent_t after_hist, int* launches) {
+    int rc = launch_hist(ctx, shape, n, profile, feat, ld, ier, status, st, set, 1);
+    if (rc) return rc;
+    *launches += 2;
+    if (after_hist) cudaEventRecord(after_hist, st);
+    const int nsub = pick_subbatches(ctx, n);
+    if (nsub <= 1) {
+        *launches += 2;
+        return launch_gauss(ctx, shape, n, profile, feat, ld, ier, status, st, set, 2);
+    }
+    const int par = ctx->fork_rr & 1;
+    cudaEventRecord(ctx->hist_ev[par], st);
+    const size_t es = elem_size(shape->dtype);
+    for (int k = 0; k < nsub; ++k) {
+        const int64_t lo = n * k / nsub, hi = n * (k + 1) / nsub;
+        cudaStream_t sk = ctx->sub[k];
+        cudaStreamWaitEvent(sk, ctx->hist_ev[par], 0);
+        pfx_scratch_set* sset = take_set(ctx, sk);
+        if (!rc)
+            rc = launch_gauss(ctx, shape, hi - lo, (const char*)profile + (size_t)lo * shape->nbin * es,
+                              feat + lo * ld, ld, ier ? ier + lo * PFX_NIER : nullptr, status + lo, sk, sset, 2);
+        release_set(ctx, sset, sk);
+        cudaEventRecord(ctx->sub_ev[k], sk);
+        cudaStreamWaitEvent(st, ctx->sub_ev[k], 0);
+        *launches += 2;
+    }
+    return rc;
 }
 
 static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint32_t features,
@@ -213,7 +339,6 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
         const int rcs = check_bates_shape(ctx, shape);
         if (rcs) return rcs;
     }
-    rotate_counters(ctx);
     int launches = 0;
     int e = 0;
     if (timed || trace) cudaEventRecord(ctx->ev[e++], st);
@@ -230,57 +355,51 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
         rc = launch_fill_nan(ctx, feat, n, feat_ld, PFX_NBATES, st);
         if (rc) return rc;
         ++launches;
-        // The histogram -> Gaussian chain is the long pole and ends in a tail of slow candidates;
-        // scores 1-4, 12-19 and 20-22 do not depend on it and run on a side stream next to it.
-        // (Timed calls keep everything on one stream so that the per-stage events mean something.)
-        cudaStream_t sd = st, sd2 = st;
-        const int par = ctx->counter_slot & 1;
+        pfx_scratch_set* set = take_set(ctx, st);
+        ctx->fork_rr++;
+        const int par = ctx->fork_rr & 1;
         if (!timed) {
-            sd = ctx->side[par];
-            sd2 = ctx->side2[par];
-            PFX_CUDA(ctx, cudaEventRecord(ctx->fork_ev[par], st));
-            PFX_CUDA(ctx, cudaStreamWaitEvent(sd, ctx->fork_ev[par], 0));
-            PFX_CUDA(ctx, cudaStreamWaitEvent(sd2, ctx->fork_ev[par], 0));
-        }
-        if (!timed) {
-            // side stream first: the DM and sinusoid kernels have a short body and a long tail of
-            // slow candidates (a few lingering blocks); launched ahead of the histogram/Gaussian
-            // chain their tails hide behind its body instead of adding to the step
-            // whatever happens, the side streams are joined again before this function returns:
-            // the caller's stream must cover every kernel that touches the caller's buffers
-            rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, 3);
+            // The histogram -> Gaussian chain is the long pole and ends in a tail of slow candidates;
+            // scores 1-4, 12-19 and 20-22 do not depend on it and run on side streams next to it,
+            // launched first: the DM and sinusoid kernels have a short body and a long tail of slow
+            // candidates (a few lingering blocks) that hides behind the body of the chain.
+            // Whatever happens, the side streams are joined again before this function returns: the
+            // caller's stream must cover every kernel that touches the caller's buffers.
+            cudaStream_t sd = ctx->side[par], sd2 = ctx->side2[par];
+            rc = PFX_OK;
+            if (cudaEventRecord(ctx->fork_ev[par], st) != cudaSuccess ||
+                cudaStreamWaitEvent(sd, ctx->fork_ev[par], 0) != cudaSuccess ||
+                cudaStreamWaitEvent(sd2, ctx->fork_ev[par], 0) != cudaSuccess)
+                rc = set_err(ctx, PFX_ERR_CUDA, "fork of the side streams failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (!rc) rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, set, 3);
             if (!rc && trace) cudaEventRecord(ctx->ev[5], sd);
-            if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, 0);
+            if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0);
             if (!rc && trace) cudaEventRecord(ctx->ev[2], sd2);
-            if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, 4);
-            if (!rc) rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
-            if (!rc && trace) cudaEventRecord(ctx->ev[3], st);
-            if (!rc) rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
+            if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, set, 4);
+            if (!rc) rc = launch_hist_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, set,
+                                            trace ? ctx->ev[3] : nullptr, &launches);
             if (!rc && trace) cudaEventRecord(ctx->ev[4], st);
             cudaEventRecord(ctx->join_ev[par], sd);
             cudaStreamWaitEvent(st, ctx->join_ev[par], 0);
             cudaEventRecord(ctx->join2_ev[par], sd2);
             cudaStreamWaitEvent(st, ctx->join2_ev[par], 0);
+            release_set(ctx, set, st);
             if (rc) return rc;
             PFX_CUDA(ctx, cudaGetLastError());
+            launches += 3;
         } else {
-            rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, 0);
+            rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, st, set, 0);
+            if (!rc) cudaEventRecord(ctx->ev[e++], st);
+            if (!rc) rc = launch_hist_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, set, ctx->ev[e++], &launches);
+            if (!rc) cudaEventRecord(ctx->ev[e++], st);
+            if (!rc) rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, st, set, 3);
+            if (!rc) cudaEventRecord(ctx->ev[e++], st);
+            if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, st, set, 4);
+            if (!rc) cudaEventRecord(ctx->ev[e++], st);
+            release_set(ctx, set, st);
             if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
-            rc = launch_hist(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 1);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
-            rc = launch_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, 2);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
-            rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, st, 3);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
-            rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, st, 4);
-            if (rc) return rc;
-            cudaEventRecord(ctx->ev[e++], st);
+            launches += 3;
         }
-        launches += 7;
     }
     ctx->last_launches = launches;
     if (trace && bates) cudaEventRecord(ctx->ev[6], st);
@@ -299,6 +418,30 @@ extern "C" int pfx_score_dev(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, ui
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
     return score_dev_impl(ctx, shape, n, features, profile, subbands, dmcurve, dmstat, params, feat, feat_ld,
                           ier, status, (cudaStream_t)stream, ctx->stage_timing);
+}
+
+extern "C" int pfx_reserve(pfx_ctx* ctx, const pfx_shape* shape, int64_t n_max) {
+    int rc = check_shape(ctx, shape, n_max);
+    if (rc) return rc;
+    if (n_max == 0) return PFX_OK;
+    PFX_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = check_bates_shape(ctx, shape);
+    if (rc) return rc;
+    // every set is sized for a whole call of n_max candidates, so whichever set a call or one of
+    // its sub-batches draws is large enough
+    for (int i = 0; i < N_SETS; ++i) {
+        rc = reserve_hist(ctx, &ctx->sets[i], shape, n_max);
+        if (!rc) rc = reserve_gauss(ctx, &ctx->sets[i], shape, n_max);
+        if (rc) return rc;
+    }
+    ctx->reserved = true;
+    return PFX_OK;
+}
+
+extern "C" int pfx_set_subbatches(pfx_ctx* ctx, int nsub) {
+    if (!ctx || nsub < 0) return PFX_ERR_INVALID;
+    ctx->subbatch = nsub;
+    return PFX_OK;
 }
 
 extern "C" int pfx_set_stage_timing(pfx_ctx* ctx, int on) {
@@ -380,69 +523,74 @@ extern "C" int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, u
     if (chunk > n) chunk = n;
     const StageLayout L = stage_layout(shape, chunk, bates, lyon, ncol);
     for (int b = 0; b < 2; ++b) {
-        if (ctx->stage_bytes[b] < L.total) {
-            if (ctx->stage[b]) {
-                cudaDeviceSynchronize();
-                cudaFree(ctx->stage[b]);
-                ctx->scratch_bytes -= ctx->stage_bytes[b];
-                ctx->stage[b] = nullptr;
-                ctx->stage_bytes[b] = 0;
-            }
-            PFX_CUDA(ctx, cudaMalloc(&ctx->stage[b], L.total));
-            ctx->stage_bytes[b] = L.total;
-            ctx->scratch_bytes += L.total;
-        }
+        pfx_buf sb = {ctx->stage[b], ctx->stage_bytes[b]};
+        rc = ensure_buf(ctx, &sb, L.total);
+        ctx->stage[b] = sb.p;
+        ctx->stage_bytes[b] = sb.bytes;
+        if (rc) return rc;
     }
     const size_t es = elem_size(shape->dtype), eds = elem_size(shape->dm_dtype), ess = elem_size(shape->dmstat_dtype);
     int launches = 0;
     int64_t done = 0;
     int b = 0;
+    // every exit of the loop goes through the two synchronisations below: nothing may still be
+    // copying into the caller's arrays when this function returns, error or not
+#define PFX_TRY(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            rc = set_err(ctx, PFX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                         __FILE__, __LINE__);                                                          \
+            goto out;                                                                                  \
+        }                                                                                              \
+    } while (0)
     while (done < n) {
         const int64_t cn = (n - done < chunk) ? n - done : chunk;
         cudaStream_t st = ctx->streams[b];
         char* base = (char*)ctx->stage[b];
-        PFX_CUDA(ctx, cudaMemcpyAsync(base + L.profile, (const char*)profile + (size_t)done * shape->nbin * es,
-                                      (size_t)cn * shape->nbin * es, cudaMemcpyHostToDevice, st));
+        PFX_TRY(cudaMemcpyAsync(base + L.profile, (const char*)profile + (size_t)done * shape->nbin * es,
+                                (size_t)cn * shape->nbin * es, cudaMemcpyHostToDevice, st));
         if (bates) {
-            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.subbands,
-                                          (const char*)subbands + (size_t)done * shape->nsub * shape->nbin * es,
-                                          (size_t)cn * shape->nsub * shape->nbin * es, cudaMemcpyHostToDevice, st));
-            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.dmcurve, (const char*)dmcurve + (size_t)done * shape->n_dm * eds,
-                                          (size_t)cn * shape->n_dm * eds, cudaMemcpyHostToDevice, st));
-            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.params, (const char*)(params + (size_t)done * PFX_NPARAM),
-                                          (size_t)cn * PFX_NPARAM * 8, cudaMemcpyHostToDevice, st));
+            PFX_TRY(cudaMemcpyAsync(base + L.subbands,
+                                    (const char*)subbands + (size_t)done * shape->nsub * shape->nbin * es,
+                                    (size_t)cn * shape->nsub * shape->nbin * es, cudaMemcpyHostToDevice, st));
+            PFX_TRY(cudaMemcpyAsync(base + L.dmcurve, (const char*)dmcurve + (size_t)done * shape->n_dm * eds,
+                                    (size_t)cn * shape->n_dm * eds, cudaMemcpyHostToDevice, st));
+            PFX_TRY(cudaMemcpyAsync(base + L.params, (const char*)(params + (size_t)done * PFX_NPARAM),
+                                    (size_t)cn * PFX_NPARAM * 8, cudaMemcpyHostToDevice, st));
         }
         if (lyon)
-            PFX_CUDA(ctx, cudaMemcpyAsync(base + L.dmstat, (const char*)dmstat + (size_t)done * shape->n_dmstat * ess,
-                                          (size_t)cn * shape->n_dmstat * ess, cudaMemcpyHostToDevice, st));
+            PFX_TRY(cudaMemcpyAsync(base + L.dmstat, (const char*)dmstat + (size_t)done * shape->n_dmstat * ess,
+                                    (size_t)cn * shape->n_dmstat * ess, cudaMemcpyHostToDevice, st));
         rc = score_dev_impl(ctx, shape, cn, features, base + L.profile, base + L.subbands, base + L.dmcurve,
                             base + L.dmstat, (const double*)(base + L.params), (double*)(base + L.feat), ncol,
                             bates && ier ? (int8_t*)(base + L.ier) : nullptr, (int32_t*)(base + L.status), st, 0);
-        if (rc) {       // nothing may still be copying into the caller's arrays when we return
-            cudaStreamSynchronize(ctx->streams[0]);
-            cudaStreamSynchronize(ctx->streams[1]);
-            return rc;
-        }
+        if (rc) goto out;
         launches += ctx->last_launches;
         if (feat_ld == ncol) {
-            PFX_CUDA(ctx, cudaMemcpyAsync(feat + (size_t)done * feat_ld, base + L.feat, (size_t)cn * ncol * 8,
-                                          cudaMemcpyDeviceToHost, st));
+            PFX_TRY(cudaMemcpyAsync(feat + (size_t)done * feat_ld, base + L.feat, (size_t)cn * ncol * 8,
+                                    cudaMemcpyDeviceToHost, st));
         } else {
-            PFX_CUDA(ctx, cudaMemcpy2DAsync(feat + (size_t)done * feat_ld, (size_t)feat_ld * 8, base + L.feat,
-                                            (size_t)ncol * 8, (size_t)ncol * 8, (size_t)cn,
-                                            cudaMemcpyDeviceToHost, st));
+            PFX_TRY(cudaMemcpy2DAsync(feat + (size_t)done * feat_ld, (size_t)feat_ld * 8, base + L.feat,
+                                      (size_t)ncol * 8, (size_t)ncol * 8, (size_t)cn, cudaMemcpyDeviceToHost, st));
         }
         if (bates) {
             if (ier)
-                PFX_CUDA(ctx, cudaMemcpyAsync(ier + (size_t)done * PFX_NIER, base + L.ier, (size_t)cn * PFX_NIER,
-                                              cudaMemcpyDeviceToHost, st));
-            PFX_CUDA(ctx, cudaMemcpyAsync(status + done, base + L.status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
+                PFX_TRY(cudaMemcpyAsync(ier + (size_t)done * PFX_NIER, base + L.ier, (size_t)cn * PFX_NIER,
+                                        cudaMemcpyDeviceToHost, st));
+            PFX_TRY(cudaMemcpyAsync(status + done, base + L.status, (size_t)cn * 4, cudaMemcpyDeviceToHost, st));
         }
         done += cn;
         b ^= 1;
     }
-    PFX_CUDA(ctx, cudaStreamSynchronize(ctx->streams[0]));
-    PFX_CUDA(ctx, cudaStreamSynchronize(ctx->streams[1]));
+#undef PFX_TRY
+out:
+    {
+        const cudaError_t e0 = cudaStreamSynchronize(ctx->streams[0]), e1 = cudaStreamSynchronize(ctx->streams[1]);
+        if (rc) return rc;
+        if (e0 != cudaSuccess || e1 != cudaSuccess)
+            return set_err(ctx, PFX_ERR_CUDA, "pfx_score_host: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    }
     ctx->last_launches = launches;
     ctx->ev_valid = false;
     return PFX_OK;

@@ -16,35 +16,60 @@ constexpr int GROUPS_PER_BLOCK = BLOCK_THREADS / WARP;
 constexpr int LYON_W = 8;                     // lanes per candidate in the Lyon kernel
 constexpr int LYON_THREADS = 256;
 constexpr int HIST_CAP_GLOBAL = 4096;         // bins a global scratch slot can hold
-constexpr int COUNTER_SLOTS = 64;             // ring of work-queue counter sets
-constexpr int COUNTERS_PER_SLOT = 8;
+constexpr int N_SETS = 10;                    // scratch sets: launches in flight per context (see ScratchSet)
+constexpr int COUNTERS_PER_SET = 16;
 constexpr int N_EVENTS = 8;
+constexpr int MAX_SUB = 4;                    // sub-batches of one pfx_score_dev call (own stream + set each)
 
 typedef unsigned long long u64;
 
 }  // namespace pfx
+
+// Scratch of one launch group (one *_dev call, or one sub-batch of pfx_score_dev): work-queue
+// counters, the carry records between the two Gaussian kernels, per-lane data vectors, histogram
+// buffers.  A context owns N_SETS of them and hands them out round robin; `done` is recorded on
+// the stream of the call after its last kernel, and the next user of the set makes its stream wait
+// for that event first.  So any number of calls may be in flight on any streams of one context:
+// more than N_SETS of them serialise on the device instead of sharing scratch (no host
+// synchronisation either way).
+struct pfx_buf {
+    void* p;
+    size_t bytes;
+};
+struct pfx_scratch_set {
+    pfx::u64* counters;       // COUNTERS_PER_SET
+    pfx_buf carry;            // per-candidate records passed between the two Gaussian kernels
+    pfx_buf lane[2];          // per-lane data vectors of the Gaussian lane kernels (long profiles)
+    pfx_buf hist_lane;        // per-lane arrays of k_hist_lane
+    pfx_buf ovf;              // candidates whose histogram overflowed the per-lane capacity
+    pfx_buf hist_warp;        // global histogram slots of the warp-form kernel
+    cudaEvent_t done;
+    bool used;
+};
+struct pfx_grid_cache_entry {
+    const void* fn;
+    int threads;
+    size_t smem;
+    int grid;
+};
 
 struct pfx_ctx {
     int device;
     int sm_count;
     int smem_optin;
     char err[512];
-    pfx::u64* counters;       // COUNTER_SLOTS * COUNTERS_PER_SLOT
-    int counter_slot;
-    double* hist_scratch;
-    size_t hist_scratch_bytes;
-    void* carry;              // per-candidate records passed between the two Gaussian kernels
-    size_t carry_bytes;
-    void* lane_buf[4];        // per-lane data vectors of the lane-per-candidate kernels
-    size_t lane_bytes[4];
-    void* hist_lane_buf[2];   // per-lane arrays of k_hist_lane
-    size_t hist_lane_bytes[2];
-    int* ovf_list[2];         // candidates whose histogram overflowed the per-lane capacity
-    size_t ovf_bytes[2];
+    pfx::u64* counters;       // N_SETS * COUNTERS_PER_SET
+    pfx_scratch_set sets[pfx::N_SETS];
+    int set_rr;
+    pfx_grid_cache_entry grid_cache[32];
+    int n_grid_cache;
+    int subbatch;             // sub-batches of the histogram/Gaussian chain per pfx_score_dev call
+    bool reserved;            // pfx_reserve was called: growing scratch inside a call is reported
     cudaEvent_t ev[pfx::N_EVENTS];
-    // fork/join: the independent score groups of one call run on a side stream
-    cudaStream_t side[2], side2[2];
-    cudaEvent_t fork_ev[2], join_ev[2], join2_ev[2];
+    // fork/join: the independent score groups of one call run on side streams
+    cudaStream_t side[2], side2[2], sub[pfx::MAX_SUB];
+    cudaEvent_t fork_ev[2], join_ev[2], join2_ev[2], hist_ev[2], sub_ev[pfx::MAX_SUB];
+    int fork_rr;
     bool ev_valid, ev_trace;
     int stage_timing;         // 1: serialise the stages of pfx_score_dev and time each (pfx_last_timing)
     int last_launches;
@@ -67,25 +92,28 @@ int set_err(pfx_ctx* ctx, int code, const char* fmt, ...);
                                 cudaGetErrorString(e_), __FILE__, __LINE__);                     \
     } while (0)
 
-// k-th counter of the current slot; slots rotate per call so that calls in flight on different
-// streams never share a counter
-inline u64* take_counter(pfx_ctx* ctx, int k, cudaStream_t st) {
-    u64* c = ctx->counters + (size_t)ctx->counter_slot * COUNTERS_PER_SLOT + k;
+// Next scratch set of the context, ordered behind its previous user on the device (see
+// pfx_scratch_set).  release_set records the completion event on the stream that covers every
+// kernel of the launch group.
+pfx_scratch_set* take_set(pfx_ctx* ctx, cudaStream_t st);
+void release_set(pfx_ctx* ctx, pfx_scratch_set* set, cudaStream_t st);
+// grow-only scratch buffer.  Growing inside a call frees the old block, which synchronises the
+// device: pfx_reserve() sizes every set up front so that this never happens on the hot path.
+int ensure_buf(pfx_ctx* ctx, pfx_buf* b, size_t need);
+
+// k-th work-queue counter of a set, zeroed on the launching stream
+inline u64* take_counter(pfx_scratch_set* set, int k, cudaStream_t st) {
+    u64* c = set->counters + k;
     cudaMemsetAsync(c, 0, sizeof(u64), st);
     return c;
 }
 
-// persistent launch: grid = resident blocks per SM x SM count
+// persistent launch: grid = resident blocks per SM x SM count.  The attribute call and the
+// occupancy query run once per (kernel, block size, shared memory) and are cached in the context.
+int persistent_grid_impl(pfx_ctx* ctx, const void* fn, int threads, size_t smem, int* grid);
 template <class K>
 inline int persistent_grid(pfx_ctx* ctx, K kernel, int threads, size_t smem, int* grid) {
-    PFX_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    PFX_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
-    if (per_sm < 1)
-        return set_err(ctx, PFX_ERR_UNSUPPORTED,
-                       "kernel needs %zu bytes of shared memory per block, limit %d", smem, ctx->smem_optin);
-    *grid = per_sm * ctx->sm_count;
-    return PFX_OK;
+    return persistent_grid_impl(ctx, (const void*)kernel, threads, smem, grid);
 }
 
 #if defined(__CUDACC__)
@@ -99,19 +127,22 @@ __device__ __forceinline__ long long next_candidate(const G& g, u64* counter) {
 
 // launchers, one per translation unit
 int launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                    int64_t ld, int8_t* ier, cudaStream_t st, int ck);
+                    int64_t ld, int8_t* ier, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_hist(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck);
+                int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                 int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck);
+                 int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_dmfit(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
-                 double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck);
+                 double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, const void* subbands,
-                   const double* params, double* feat, int64_t ld, int32_t* status, cudaStream_t st, int ck);
+                   const double* params, double* feat, int64_t ld, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_lyon(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, const void* dmstat,
                 double* feat, int64_t ld, cudaStream_t st);
 int launch_pfd_params(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* params,
                       cudaStream_t st);
+// size the scratch of a set for n candidates of this shape (what the launchers would grow lazily)
+int reserve_hist(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, int64_t n);
+int reserve_gauss(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, int64_t n);
 int launch_fill_nan(pfx_ctx* ctx, double* feat, int64_t n, int64_t ld, int ncol, cudaStream_t st);
 
 }  // namespace pfx

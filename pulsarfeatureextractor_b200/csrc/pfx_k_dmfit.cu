@@ -58,7 +58,7 @@ k_dmfit(const void* __restrict__ dmcurve, int dm_dtype, long long n, int n_dm, i
 
 template <int N>
 int launch_n(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
-             double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
+             double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
     // one warp per block: a block leaves when its 32 lanes are done, so the tail of slow candidates
     // holds little shared memory and the Gaussian kernels' blocks fit next to it
     const int threads = 32;
@@ -69,7 +69,7 @@ int launch_n(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, c
     const long long groups = (long long)grid * threads / DM_LANES;
     if (groups > n) grid = (int)((n * DM_LANES + threads - 1) / threads);
     k_dmfit<N><<<grid, threads, smem, st>>>(dmcurve, s->dm_dtype, n, s->n_dm, s->family, params, feat, ld, ier,
-                                             status, take_counter(ctx, ck, st));
+                                             status, take_counter(set, ck, st));
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }
@@ -94,9 +94,9 @@ int pfx::launch_pfd_params(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const vo
 }
 
 int pfx::launch_dmfit(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
-                      double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
+                      double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
     if (s->n_dm < 4) return set_err(ctx, PFX_ERR_UNSUPPORTED, "n_dm < 4");
     if (s->family == PFX_FAMILY_PFD)
-        return launch_n<4>(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, ck);
-    return launch_n<3>(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, ck);
+        return launch_n<4>(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, set, ck);
+    return launch_n<3>(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, set, ck);
 }

@@ -79,7 +79,16 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
     g.cand = -1;
     bool more = true;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    PFX_PROF_T0(pk0);
+#if defined(PFX_PROFILE)
+    long long ptail = 0;
+#endif
     for (;;) {
+        PFX_PROF_T0(pq0);
+#if defined(PFX_PROFILE)
+        // the tail of a warp starts when its first lane finds the queue empty
+        if (!ptail && __any_sync(0xffffffffu, !more)) ptail = clock64();
+#endif
         if (g.phase == GP_IDLE) {
             if (g.cand >= 0 && G::rank() != 0) g.cand = -1;
             if (g.cand >= 0) {
@@ -137,9 +146,16 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
                 }
             }
         }
+        __syncwarp();
+        PFX_PROF_ADD(PROF_QUEUE, pq0);
         if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
         g.step(b, ws);
     }
+    __syncwarp();
+    PFX_PROF_ADD(PROF_TOTAL, pk0);
+#if defined(PFX_PROFILE)
+    if (ptail) PFX_PROF_ADD(PROF_TAIL, ptail);
+#endif
 }
 
 __global__ void __launch_bounds__(FINAL_MAXT, 1)
@@ -217,83 +233,89 @@ static bool lane_layout(pfx_ctx* ctx, int m, int np, int lanes_per_cand, int max
 }
 
 // scratch for the data vectors of one launch: groups x m x (8 + 2) bytes
-static int lane_scratch(pfx_ctx* ctx, size_t lanes, int m, int slot, double** gdat, unsigned short** gxs) {
+static int lane_scratch(pfx_ctx* ctx, pfx_buf* buf, size_t lanes, int m, double** gdat, unsigned short** gxs) {
     const size_t need = ((lanes * (size_t)m * 10) + 255) / 256 * 256;
-    if (ctx->lane_bytes[slot] < need) {
-        if (ctx->lane_buf[slot]) {
-            cudaDeviceSynchronize();
-            cudaFree(ctx->lane_buf[slot]);
-            ctx->scratch_bytes -= ctx->lane_bytes[slot];
-            ctx->lane_buf[slot] = nullptr;
-            ctx->lane_bytes[slot] = 0;
-        }
-        PFX_CUDA(ctx, cudaMalloc(&ctx->lane_buf[slot], need));
-        ctx->lane_bytes[slot] = need;
-        ctx->scratch_bytes += need;
-    }
-    *gdat = (double*)ctx->lane_buf[slot];
-    *gxs = (unsigned short*)((char*)ctx->lane_buf[slot] + lanes * (size_t)m * 8);
+    const int rc = ensure_buf(ctx, buf, need);
+    if (rc) return rc;
+    *gdat = (double*)buf->p;
+    *gxs = (unsigned short*)((char*)buf->p + lanes * (size_t)m * 8);
     return PFX_OK;
 }
 
-int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                      int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
-    const int m = s->nbin;
-    if (m < 8 || m > 65535) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin out of range");
-    const int par = ctx->counter_slot & 1;      // calls in flight alternate between two scratch sets
-    // carry records
-    const size_t need = (size_t)n * sizeof(GaussCarry);
-    if (ctx->carry_bytes < need) {
-        if (ctx->carry) {
-            cudaDeviceSynchronize();
-            cudaFree(ctx->carry);
-            ctx->scratch_bytes -= 2 * ctx->carry_bytes;
-            ctx->carry = nullptr;
-            ctx->carry_bytes = 0;
-        }
-        PFX_CUDA(ctx, cudaMalloc(&ctx->carry, need * 2));
-        ctx->carry_bytes = need;
-        ctx->scratch_bytes += need * 2;
-    }
-    GaussCarry* carry = (GaussCarry*)((char*)ctx->carry + (size_t)par * ctx->carry_bytes);
-    double* gdat;
-    unsigned short* gxs;
-    int grid, rc;
-    {
-        int threads;
-        size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, 10, &threads, &smem);
-        rc = persistent_grid(ctx, k_gauss_rounds, threads, smem, &grid);
-        if (rc) return rc;
-        const int per_block = threads / ROUNDS_LANES;
-        if ((long long)grid * per_block > n) grid = (int)((n + per_block - 1) / per_block);
-        gdat = nullptr;
-        gxs = nullptr;
-        if (!in_smem) {
-            rc = lane_scratch(ctx, (size_t)grid * per_block, m, par * 2 + 0, &gdat, &gxs);
+namespace {
+struct GaussPlan {
+    int threads[2], grid[2];
+    size_t smem[2];
+    bool in_smem[2];
+};
+}  // namespace
+
+// launch geometry of the two kernels for n candidates of m bins, and the scratch they need
+static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, GaussPlan* p) {
+    int rc = ensure_buf(ctx, &set->carry, (size_t)n * sizeof(GaussCarry));
+    if (rc) return rc;
+    p->in_smem[0] = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, 10, &p->threads[0], &p->smem[0]);
+    rc = persistent_grid(ctx, k_gauss_rounds, p->threads[0], p->smem[0], &p->grid[0]);
+    if (rc) return rc;
+    p->in_smem[1] = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, 8, &p->threads[1], &p->smem[1]);
+    rc = persistent_grid(ctx, k_gauss_final, p->threads[1], p->smem[1], &p->grid[1]);
+    if (rc) return rc;
+    const int lanes[2] = {ROUNDS_LANES, FINAL_LANES};
+    for (int k = 0; k < 2; ++k) {
+        const int per_block = p->threads[k] / lanes[k];
+        if ((long long)p->grid[k] * per_block > n) p->grid[k] = (int)((n + per_block - 1) / per_block);
+        if (!p->in_smem[k]) {
+            double* gdat;
+            unsigned short* gxs;
+            rc = lane_scratch(ctx, &set->lane[k], (size_t)p->grid[k] * per_block, m, &gdat, &gxs);
             if (rc) return rc;
         }
-        k_gauss_rounds<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
-                                                     take_counter(ctx, ck, st), carry, gdat, gxs);
-        PFX_CUDA(ctx, cudaGetLastError());
-    }
-    {
-        int threads;
-        size_t smem;
-        const bool in_smem = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, 8, &threads, &smem);
-        rc = persistent_grid(ctx, k_gauss_final, threads, smem, &grid);
-        if (rc) return rc;
-        const int per_block = threads / FINAL_LANES;
-        if ((long long)grid * per_block > n) grid = (int)((n + per_block - 1) / per_block);
-        gdat = nullptr;
-        gxs = nullptr;
-        if (!in_smem) {
-            rc = lane_scratch(ctx, (size_t)grid * per_block, m, par * 2 + 1, &gdat, &gxs);
-            if (rc) return rc;
-        }
-        k_gauss_final<<<grid, threads, smem, st>>>(profile, s->dtype, n, m, feat, ld, ier,
-                                                    take_counter(ctx, ck + 4, st), carry, gdat, gxs);
-        PFX_CUDA(ctx, cudaGetLastError());
     }
     return PFX_OK;
 }
+
+int pfx::reserve_gauss(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, int64_t n) {
+    GaussPlan p;
+    return gauss_plan(ctx, set, s->nbin, n, &p);
+}
+
+int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
+                      int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
+    const int m = s->nbin;
+    if (m < 8 || m > 65535) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin out of range");
+    GaussPlan p;
+    int rc = gauss_plan(ctx, set, m, n, &p);
+    if (rc) return rc;
+    GaussCarry* carry = (GaussCarry*)set->carry.p;
+    double* gdat = nullptr;
+    unsigned short* gxs = nullptr;
+    if (!p.in_smem[0]) {
+        rc = lane_scratch(ctx, &set->lane[0], (size_t)p.grid[0] * (p.threads[0] / ROUNDS_LANES), m, &gdat, &gxs);
+        if (rc) return rc;
+    }
+    k_gauss_rounds<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
+                                                                take_counter(set, ck, st), carry, gdat, gxs);
+    PFX_CUDA(ctx, cudaGetLastError());
+    gdat = nullptr;
+    gxs = nullptr;
+    if (!p.in_smem[1]) {
+        rc = lane_scratch(ctx, &set->lane[1], (size_t)p.grid[1] * (p.threads[1] / FINAL_LANES), m, &gdat, &gxs);
+        if (rc) return rc;
+    }
+    k_gauss_final<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
+                                                               take_counter(set, ck + 4, st), carry, gdat, gxs);
+    PFX_CUDA(ctx, cudaGetLastError());
+    return PFX_OK;
+}
+
+#if defined(PFX_PROFILE)
+// development builds only (not part of include/pfx.h): per-phase counters of k_gauss_rounds
+extern "C" int pfx_debug_profile(unsigned long long* out32, int reset) {
+    if (out32 && cudaMemcpyFromSymbol(out32, g_pfx_prof, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        if (cudaMemcpyToSymbol(g_pfx_prof, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

@@ -92,84 +92,63 @@ k_hist_lane(const void* __restrict__ profile, int dtype, long long n, int m, dou
 
 }  // namespace
 
+namespace {
+struct HistPlan {
+    int grid, lgrid, wd, cap_smem;
+    size_t smem, lsmem;
+};
+}  // namespace
+
+static int hist_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, HistPlan* p) {
+    p->cap_smem = 192;                              // typical histograms have 6..110 bins
+    while (3 * p->cap_smem < m) p->cap_smem += 64;  // the derivative is staged in the Jacobian area
+    p->wd = align_up(hist_work_doubles(m, p->cap_smem), 2);
+    p->smem = (size_t)p->wd * 8 * GROUPS_PER_BLOCK;
+    int rc = persistent_grid(ctx, k_hist, BLOCK_THREADS, p->smem, &p->grid);
+    if (rc) return rc;
+    // global histogram slots of the warp-form kernel: one per warp of its grid, per scratch set
+    rc = ensure_buf(ctx, &set->hist_warp, (size_t)p->grid * GROUPS_PER_BLOCK * hist_scratch_doubles(HIST_CAP_GLOBAL) * 8);
+    if (rc) return rc;
+    const int threads = 128;
+    p->lsmem = (size_t)lane_ws_doubles(3) * 8 * threads;
+    rc = persistent_grid(ctx, k_hist_lane, threads, p->lsmem, &p->lgrid);
+    if (rc) return rc;
+#if defined(PFX_HIST_BLOCKS_PER_SM)
+    if (p->lgrid > PFX_HIST_BLOCKS_PER_SM * ctx->sm_count) p->lgrid = PFX_HIST_BLOCKS_PER_SM * ctx->sm_count;
+#endif
+    if ((long long)p->lgrid * threads > n) p->lgrid = (int)((n + threads - 1) / threads);
+    rc = ensure_buf(ctx, &set->hist_lane, (size_t)p->lgrid * threads * (size_t)hist_lane_doubles(m) * 8);
+    if (rc) return rc;
+    return ensure_buf(ctx, &set->ovf, (size_t)n * sizeof(int));
+}
+
+int pfx::reserve_hist(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, int64_t n) {
+    HistPlan p;
+    return hist_plan(ctx, set, s->nbin, n, &p);
+}
+
 int pfx::launch_hist(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                     int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, int ck) {
+                     int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
     const int m = s->nbin;
     if (m < 8) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin < 8");
-    int cap_smem = 192;                       // typical histograms have 6..110 bins
-    while (3 * cap_smem < m) cap_smem += 64;  // the derivative is staged in the Jacobian area
-    const int wd = align_up(hist_work_doubles(m, cap_smem), 2);
-    const size_t smem = (size_t)wd * 8 * GROUPS_PER_BLOCK;
-    int grid;
-    int rc = persistent_grid(ctx, k_hist, BLOCK_THREADS, smem, &grid);
+    HistPlan p;
+    int rc = hist_plan(ctx, set, m, n, &p);
     if (rc) return rc;
-    const int groups = grid * GROUPS_PER_BLOCK;
-    const size_t need = (size_t)groups * hist_scratch_doubles(HIST_CAP_GLOBAL) * 8;
-    if (ctx->hist_scratch_bytes < need) {
-        if (ctx->hist_scratch) {
-            cudaDeviceSynchronize();
-            cudaFree(ctx->hist_scratch);
-            ctx->scratch_bytes -= ctx->hist_scratch_bytes;
-            ctx->hist_scratch = nullptr;
-            ctx->hist_scratch_bytes = 0;
-        }
-        PFX_CUDA(ctx, cudaMalloc(&ctx->hist_scratch, need));
-        ctx->hist_scratch_bytes = need;
-        ctx->scratch_bytes += need;
-    }
     const double pow_m = pow((double)m, -0.3333333);        // POI:151, evaluated by the C library
     const double pow_m1 = pow((double)(m - 1), -0.3333333);
     // pass 1: one lane per candidate, histograms up to HIST_LANE_CAP bins
-    {
-        const int threads = 128;
-        const size_t lsmem = (size_t)lane_ws_doubles(3) * 8 * threads;
-        int lgrid;
-        rc = persistent_grid(ctx, k_hist_lane, threads, lsmem, &lgrid);
-        if (rc) return rc;
-#if defined(PFX_HIST_BLOCKS_PER_SM)
-        if (lgrid > PFX_HIST_BLOCKS_PER_SM * ctx->sm_count) lgrid = PFX_HIST_BLOCKS_PER_SM * ctx->sm_count;
-#endif
-        if ((long long)lgrid * threads > n) lgrid = (int)((n + threads - 1) / threads);
-        const size_t lanes = (size_t)lgrid * threads;
-        const int par = ctx->counter_slot & 1;
-        const size_t lneed = lanes * (size_t)hist_lane_doubles(m) * 8;
-        if (ctx->hist_lane_bytes[par] < lneed) {
-            if (ctx->hist_lane_buf[par]) {
-                cudaDeviceSynchronize();
-                cudaFree(ctx->hist_lane_buf[par]);
-                ctx->scratch_bytes -= ctx->hist_lane_bytes[par];
-                ctx->hist_lane_buf[par] = nullptr;
-                ctx->hist_lane_bytes[par] = 0;
-            }
-            PFX_CUDA(ctx, cudaMalloc(&ctx->hist_lane_buf[par], lneed));
-            ctx->hist_lane_bytes[par] = lneed;
-            ctx->scratch_bytes += lneed;
-        }
-        const size_t oneed = (size_t)n * sizeof(int);
-        if (ctx->ovf_bytes[par] < oneed) {
-            if (ctx->ovf_list[par]) {
-                cudaDeviceSynchronize();
-                cudaFree(ctx->ovf_list[par]);
-                ctx->scratch_bytes -= ctx->ovf_bytes[par];
-            }
-            PFX_CUDA(ctx, cudaMalloc(&ctx->ovf_list[par], oneed));
-            ctx->ovf_bytes[par] = oneed;
-            ctx->scratch_bytes += oneed;
-        }
-        u64* ovf_count = take_counter(ctx, 7, st);
-        k_hist_lane<<<lgrid, threads, lsmem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
-                                                    take_counter(ctx, ck, st), (double*)ctx->hist_lane_buf[par],
-                                                    ctx->ovf_list[par], ovf_count);
-        PFX_CUDA(ctx, cudaGetLastError());
-        // pass 2: the few candidates whose histogram has more bins go through the warp-form kernel
-        // (4096-bin scratch slot per warp); the launch is tiny when the list is empty
-        // a few per cent of a synthetic batch end up here (1-2 k candidates of 100 k): one warp each, so
-        // the whole persistent grid is launched; blocks without work leave at once
-        int wgrid = grid;
-        k_hist<<<wgrid, BLOCK_THREADS, smem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
-                                                    take_counter(ctx, 6, st), wd, cap_smem, ctx->hist_scratch,
-                                                    HIST_CAP_GLOBAL, ctx->ovf_list[par], ovf_count);
-        PFX_CUDA(ctx, cudaGetLastError());
-    }
+    u64* ovf_count = take_counter(set, 7, st);
+    k_hist_lane<<<p.lgrid, 128, p.lsmem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
+                                                take_counter(set, ck, st), (double*)set->hist_lane.p,
+                                                (int*)set->ovf.p, ovf_count);
+    PFX_CUDA(ctx, cudaGetLastError());
+    // pass 2: the few candidates whose histogram has more bins go through the warp-form kernel
+    // (4096-bin scratch slot per warp); a few per cent of a synthetic batch end up here (1-2 k
+    // candidates of 100 k): one warp each, so the whole persistent grid is launched; blocks without
+    // work leave at once
+    k_hist<<<p.grid, BLOCK_THREADS, p.smem, st>>>(profile, s->dtype, n, m, pow_m, pow_m1, feat, ld, ier, status,
+                                                   take_counter(set, 6, st), p.wd, p.cap_smem,
+                                                   (double*)set->hist_warp.p, HIST_CAP_GLOBAL, (int*)set->ovf.p, ovf_count);
+    PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }

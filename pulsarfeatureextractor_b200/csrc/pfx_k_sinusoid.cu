@@ -52,7 +52,7 @@ k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, doub
 }  // namespace
 
 int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                         int64_t ld, int8_t* ier, cudaStream_t st, int ck) {
+                         int64_t ld, int8_t* ier, cudaStream_t st, pfx_scratch_set* set, int ck) {
     if (s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin < 2");
     // one warp per block: a block leaves when its 32 lanes are done, so the tail of slow candidates
     // holds little shared memory and the Gaussian kernels' blocks fit next to it
@@ -64,7 +64,7 @@ int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void
     const int per_block = threads / SIN_LANES;
     if ((long long)grid * per_block > n) grid = (int)((n + per_block - 1) / per_block);
     k_sinusoid<<<grid, threads, smem, st>>>(profile, s->dtype, n, s->nbin, feat, ld, ier,
-                                             take_counter(ctx, ck, st));
+                                             take_counter(set, ck, st));
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }

@@ -25,7 +25,7 @@ k_subband(const void* __restrict__ profile, const void* __restrict__ subbands, i
 
 int pfx::launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile,
                           const void* subbands, const double* params, double* feat, int64_t ld,
-                          int32_t* status, cudaStream_t st, int ck) {
+                          int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
     if (s->nsub < 1 || s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "bad sub-band shape");
     const int wd = align_up(sub_work_doubles(s->nbin, s->nsub), 2);
     // the box-car sums of one candidate (nsub x nbin float64) live in shared memory; as many warps
@@ -41,7 +41,7 @@ int pfx::launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void*
     int rc = persistent_grid(ctx, k_subband, threads, smem, &grid);
     if (rc) return rc;
     k_subband<<<grid, threads, smem, st>>>(profile, subbands, s->dtype, n, s->nbin, s->nsub, params, feat,
-                                                  ld, status, take_counter(ctx, ck, st), wd);
+                                                  ld, status, take_counter(set, ck, st), wd);
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }

@@ -17,6 +17,30 @@
 #include "pfx_driver.cuh"
 #include "pfx_lane_lm.cuh"
 
+// -DPFX_PROFILE: per-phase cycle and active-lane accounting of the lane kernels (development
+// builds only; read back with pfx_debug_profile, scripts/gpu_phase_profile.py).  Slot k holds
+// [2k] warp cycles spent in the phase and [2k+1] the same weighted by the lanes that executed it.
+#if defined(PFX_PROFILE) && defined(__CUDACC__)
+static __device__ unsigned long long g_pfx_prof[32];
+#endif
+#if defined(PFX_PROFILE) && defined(__CUDA_ARCH__)
+#define PFX_PROF_T0(v) const long long v = clock64()
+#define PFX_PROF_ADD(slot, v)                                                            \
+    do {                                                                                 \
+        const unsigned am_ = __activemask();                                             \
+        const long long dt_ = clock64() - (v);                                           \
+        if ((int)(threadIdx.x & 31) == __ffs(am_) - 1) {                                 \
+            atomicAdd(&g_pfx_prof[2 * (slot)], (unsigned long long)dt_);                 \
+            atomicAdd(&g_pfx_prof[2 * (slot) + 1], (unsigned long long)dt_ * __popc(am_)); \
+        }                                                                                \
+    } while (0)
+#else
+#define PFX_PROF_T0(v)
+#define PFX_PROF_ADD(slot, v)
+#endif
+enum { PROF_SETUP = 0, PROF_JAC_ROWS = 1, PROF_JAC_END = 2, PROF_LMPAR = 3, PROF_TRIAL_ROWS = 4, PROF_TRIAL_END = 5,
+       PROF_FINISH = 6, PROF_QUEUE = 7, PROF_TOTAL = 8, PROF_TAIL = 9 };
+
 namespace pfx {
 
 struct LaneBuf {
@@ -342,6 +366,7 @@ struct GaussLaneT {
 
     // one Jacobian pass; rows are produced into the staged block and eliminated eight at a time
     PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
+        PFX_PROF_T0(pt0);
         lm.jac_begin();
         G4Jac J;
         J.set(lm.x, lm.h, fl);
@@ -367,12 +392,18 @@ struct GaussLaneT {
             lm.template jac_block_staged<B>(ws.blk, rows);
         }
         lm.template jac_combine<C>();
+        PFX_PROF_ADD(PROF_JAC_ROWS, pt0);
+        PFX_PROF_T0(pt1);
         const int r = lm.jac_end(ws, nrows);
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+        PFX_PROF_ADD(PROF_JAC_END, pt1);
     }
 
     PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
+        PFX_PROF_T0(pt0);
         lm.trial_begin(ws);
+        PFX_PROF_ADD(PROF_LMPAR, pt0);
+        PFX_PROF_T0(pt1);
         G4Eval ev;
         ev.set(lm.xnew, fl);
         double s = 0.0;
@@ -382,8 +413,11 @@ struct GaussLaneT {
             s = PFX_FMA(f, f, s);
         }
         s = G::sum(s);
+        PFX_PROF_ADD(PROF_TRIAL_ROWS, pt1);
+        PFX_PROF_T0(pt2);
         const int r = lm.trial_end(sqrt(s));
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+        PFX_PROF_ADD(PROF_TRIAL_END, pt2);
     }
 
     PFX_HD void finish(const LaneBuf& b) {
@@ -439,10 +473,18 @@ struct GaussLaneT {
 
     // one trip of the kernel loop
     PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {
-        if (phase == GP_SETUP) setup(b);
+        if (phase == GP_SETUP) {
+            PFX_PROF_T0(pt);
+            setup(b);
+            PFX_PROF_ADD(PROF_SETUP, pt);
+        }
         if (phase == GP_JAC) jac_pass(b, ws);
         if (phase == GP_TRIAL) trial_pass(b, ws);
-        if (phase == GP_FIN) finish(b);
+        if (phase == GP_FIN) {
+            PFX_PROF_T0(pt);
+            finish(b);
+            PFX_PROF_ADD(PROF_FINISH, pt);
+        }
     }
 
 };

@@ -88,6 +88,15 @@ class Engine(object):
         self._check(self._lib.pfx_device_info(self._h, ctypes.byref(sm), ctypes.byref(smem), ctypes.byref(scratch)))
         return {"sm_count": sm.value, "smem_per_block": smem.value, "scratch_bytes": scratch.value}
 
+    def reserve(self, shape, n_max):
+        """Size the context's scratch for batches of up to n_max candidates of this shape
+        (pfx_reserve): later score_device calls neither allocate nor synchronise."""
+        self._check(self._lib.pfx_reserve(self._h, ctypes.byref(shape), int(n_max)))
+
+    def set_subbatches(self, nsub):
+        """Sub-batches of the histogram/Gaussian chain per call (0 = default, 1 = off)."""
+        self._check(self._lib.pfx_set_subbatches(self._h, int(nsub)))
+
     def set_stage_timing(self, on):
         """Serialise and time the score groups of score_device (see pfx_set_stage_timing)."""
         self._check(self._lib.pfx_set_stage_timing(self._h, int(on)))
@@ -172,7 +181,7 @@ class Engine(object):
         return Scores(feat, status, ier)
 
     # ---- one entry per operator-API method (ProfileOperationsInterface.py:69-130) ---------
-    def _group(self, fn, n, ncol_needed, args, want_ier=True):
+    def _group(self, n):
         torch = self._torch
         dev = torch.device("cuda", self.device)
         feat = torch.full((n, 22), float("nan"), dtype=torch.float64, device=dev)
@@ -181,21 +190,21 @@ class Engine(object):
         return feat, status, ier
 
     def sinusoid(self, profile):
-        feat, status, ier = self._group(None, profile.shape[0], 4, None)
+        feat, status, ier = self._group(profile.shape[0])
         shape = self.make_shape(profile)
         self._check(self._lib.pfx_sinusoid_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
                                                _ptr(feat), 22, _ptr(ier), _ptr(status), self._stream()))
         return Scores(feat[:, 0:4], status, ier)
 
     def gaussian(self, profile):
-        feat, status, ier = self._group(None, profile.shape[0], 11, None)
+        feat, status, ier = self._group(profile.shape[0])
         shape = self.make_shape(profile)
         self._check(self._lib.pfx_gaussian_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
                                                _ptr(feat), 22, _ptr(ier), _ptr(status), self._stream()))
         return Scores(feat[:, 4:11], status, ier)
 
     def dmfit(self, profile, dmcurve, params, family=_lib.PFX_FAMILY_PHCX):
-        feat, status, ier = self._group(None, profile.shape[0], 19, None)
+        feat, status, ier = self._group(profile.shape[0])
         shape = self.make_shape(profile, None, dmcurve, None, family)
         self._check(self._lib.pfx_dmfit_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
                                             _ptr(dmcurve), _ptr(params), _ptr(feat), 22, _ptr(ier), _ptr(status),
@@ -203,7 +212,7 @@ class Engine(object):
         return Scores(feat[:, 11:19], status, ier)
 
     def subband(self, profile, subbands, params):
-        feat, status, ier = self._group(None, profile.shape[0], 22, None)
+        feat, status, ier = self._group(profile.shape[0])
         shape = self.make_shape(profile, subbands)
         self._check(self._lib.pfx_subband_dev(self._h, ctypes.byref(shape), profile.shape[0], _ptr(profile),
                                               _ptr(subbands), _ptr(params), _ptr(feat), 22, _ptr(status),
@@ -243,3 +252,103 @@ class Engine(object):
         self._check(self._lib.pfx_lyon8_dev(self._h, ctypes.byref(shape), n, _ptr(profile), _ptr(dmstat),
                                             _ptr(feat), 8, self._stream()))
         return Scores(feat, None, None)
+
+
+def shard_ranges(n, ngpu, chunk=65536):
+    """How a batch of n candidates is dealt to ngpu devices: candidates are independent, so
+    any split gives the same rows.  Small batches: one contiguous range per device.  Streamed batches
+    (at least two chunks per device): chunks of `chunk` candidates dealt round robin, which balances
+    the skew in Levenberg-Marquardt iterations between regions of a survey.  Returns, per device, a
+    list of (lo, hi) ranges in ascending order; together they tile [0, n) exactly once."""
+    ngpu = max(1, int(ngpu))
+    if n <= 0:
+        return [[] for _ in range(ngpu)]
+    if n < 2 * chunk * ngpu:
+        return [[(n * r // ngpu, n * (r + 1) // ngpu)] if n * (r + 1) // ngpu > n * r // ngpu else []
+                for r in range(ngpu)]
+    out = [[] for _ in range(ngpu)]
+    for k, lo in enumerate(range(0, n, chunk)):
+        out[k % ngpu].append((lo, min(n, lo + chunk)))
+    return out
+
+
+class MultiEngine(object):
+    """The same host-array interface as Engine over several GPUs of one box: one context, one host
+    thread and one pair of staging buffers per device, no collective.  Each device scores its ranges
+    of the batch and its device-to-host copies land at the rows' own offsets of ONE shared pinned
+    result matrix, so the caller sees rows in input order whatever the split."""
+
+    def __init__(self, devices):
+        import concurrent.futures
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise PfxError("MultiEngine needs at least one device")
+        self.engines = [Engine(d) for d in self.devices]
+        self._torch = self.engines[0]._torch
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=len(self.engines))
+        self.device = self.devices[0]
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for e in self.engines:
+            e.close()
+
+    def device_info(self):
+        return self.engines[0].device_info()
+
+    def _fan_out(self, n, work):
+        """work(engine, lo, hi) for every range of every device, one thread per device."""
+        plan = shard_ranges(n, len(self.engines))
+
+        def run(r):
+            for lo, hi in plan[r]:
+                work(self.engines[r], lo, hi)
+        futs = [self._pool.submit(run, r) for r in range(len(self.engines)) if plan[r]]
+        for f in futs:
+            f.result()          # re-raises the first PfxError of a device
+
+    def _outputs(self, n, fbits, want_ier):
+        torch = self._torch
+        ncol = (22 if fbits & 1 else 0) + (8 if fbits & 2 else 0)
+        feat = torch.empty((n, ncol), dtype=torch.float64, pin_memory=True).numpy()
+        status = torch.zeros((n,), dtype=torch.int32, pin_memory=True).numpy()
+        ier = (torch.zeros((n, _lib.PFX_NIER), dtype=torch.int8, pin_memory=True).numpy()
+               if (want_ier and fbits & 1) else None)
+        return Scores(feat, status, ier)
+
+    def score_host(self, profile, subbands=None, dmcurve=None, dmstat=None, params=None,
+                   features="all", family=_lib.PFX_FAMILY_PHCX, out=None, chunk=0, want_ier=True):
+        fbits = _FEATURES[features] if isinstance(features, str) else int(features)
+        n = profile.shape[0]
+        if out is None:
+            out = self._outputs(n, fbits, want_ier)
+        cut = lambda a, lo, hi: None if a is None else a[lo:hi]
+
+        def work(eng, lo, hi):
+            part = Scores(out.features[lo:hi], out.status[lo:hi], cut(out.ier, lo, hi))
+            eng.score_host(cut(profile, lo, hi), cut(subbands, lo, hi), cut(dmcurve, lo, hi), cut(dmstat, lo, hi),
+                           cut(params, lo, hi), features=features, family=family, out=part, chunk=chunk)
+        self._fan_out(n, work)
+        return out
+
+    def score_pfd_host(self, profile, subbands, dmcurve, params, features="all"):
+        fbits = _FEATURES[features]
+        n = profile.shape[0]
+        out = self._outputs(n, fbits, True)
+        if out.ier is None:
+            out.ier = np.zeros((n, _lib.PFX_NIER), np.int8)
+
+        def work(eng, lo, hi):
+            r = eng.score_pfd_host(profile[lo:hi], subbands[lo:hi], dmcurve[lo:hi], params[lo:hi], features=features)
+            out.features[lo:hi] = r.features
+            out.status[lo:hi] = r.status
+            if r.ier is not None:
+                out.ier[lo:hi] = r.ier
+        self._fan_out(n, work)
+        return out
+
+
+def make_engine(gpus=1, first=0):
+    """Engine for one device, MultiEngine for several (ScoreGenerator --gpus N)."""
+    gpus = int(gpus)
+    return Engine(first) if gpus <= 1 else MultiEngine(range(first, first + gpus))

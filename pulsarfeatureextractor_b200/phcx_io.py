@@ -264,17 +264,27 @@ def expand_dm_block(curve):
     return blk.reshape(-1)
 
 
-def write_phcx(path, profile, subbands, dmcurve, dmstat, params, gz=True):
+def write_phcx(path, profile, subbands, dmcurve, dmstat, params, gz=True, superb=False):
     """Write a two-section PHCX file.  Section 0 ('FFT') carries ``dmstat`` as its DataBlock
     (Lyon DM statistics read it, PHCXOperations.py:538) and a decoy profile; section 1
-    ('FFT-Pdmpd') carries the candidate the Bates scores read.  With ``gz=False`` a SUPERB-style
-    single-section file is written (section index 0 holds everything)."""
+    ('FFT-Pdmpd') carries the candidate the Bates scores read.  With ``gz=False`` a
+    single-section file is written (section index 0 holds everything).  With ``superb=True`` an
+    uncompressed two-section SUPERB file is written (SUPERBPHCXFile.py:80,102-103): section 0 holds
+    the candidate every score reads -- its DataBlock is both the source of the DM curve (max-of-127
+    reduction) and the array of the Lyon DM statistics, so ``dmstat`` is ignored -- and section 1 is
+    a decoy that only has to pass the validity test (SUPERBPHCXFile.py:212-252)."""
     snr, dm, period_s, width, dm_start, dm_end = [float(v) for v in params[:6]]
     block1 = expand_dm_block(dmcurve)
     n_idx = 64
     dm_index = np.linspace(dm_start, dm_end, n_idx)
     parts = ["<?xml version='1.0'?>\n<phcf>\n <head>\n  <SourceID>SYNTHETIC</SourceID>\n </head>\n"]
-    if gz:
+    if superb:
+        gz = False
+        decoy = (255 - np.asarray(profile, dtype=np.uint8))
+        parts.append(_section("FFT", snr, dm, period_s, width, profile, np.asarray(subbands), dm_index, block1))
+        parts.append(_section("FFT-Pdmpd", snr * 0.5, dm + 1.0, period_s * 1.0001, width * 2, decoy,
+                              np.asarray(subbands)[::-1], dm_index * 0.5, block1[::-1]))
+    elif gz:
         decoy = (255 - np.asarray(profile, dtype=np.uint8))
         parts.append(_section("FFT", snr * 0.5, dm + 1.0, period_s * 1.0001, width * 2, decoy,
                               np.asarray(subbands)[::-1], dm_index * 0.5, dmstat))
