@@ -195,6 +195,18 @@ PFX_HD inline double exp_neg(double a) {
     return (a != a) ? a : res;
 }
 
+// 2^-k with k = floor(log2 a) (clamped): an exact scale factor that brings a > 0 to [1, 2).  Used on
+// the rare paths where a sum of squares would leave the double range (entries below 1e-100: the far
+// tails of a Gaussian model), so that the reflections stay finite where MINPACK's scaled enorm does.
+PFX_HD inline double unit_scale(double a) {
+    int e = 0;
+    (void)frexp(a, &e);
+    int k = 1 - e;
+    if (k > 1000) k = 1000;
+    if (k < -1000) k = -1000;
+    return ldexp(1.0, k);
+}
+
 PFX_HD inline double fast_rsqrt(double x) {
 #if defined(__CUDA_ARCH__)
     return rsqrt(x);
@@ -508,14 +520,22 @@ struct LaneLM {
             const double aj = a[j];
             if (aj != 0.0) {
                 const double rjj = R[ridx(j, j)];
-                const double rr = PFX_FMA(rjj, rjj, aj * aj);
-#if defined(__CUDA_ARCH__)
-                const double inv = rsqrt(rr);
-#else
-                const double inv = 1.0 / sqrt(rr);
-#endif
-                const double c = rjj * inv, sn = aj * inv;
-                R[ridx(j, j)] = rr * inv;
+                double rr = PFX_FMA(rjj, rjj, aj * aj);
+                double c, sn;
+                if (rr > 1e-200 && rr < 1e200) {
+                    const double inv = fast_rsqrt(rr);
+                    c = rjj * inv;
+                    sn = aj * inv;
+                    R[ridx(j, j)] = rr * inv;
+                } else {            // out of range (or NaN): the same rotation from scaled entries
+                    const double sc = unit_scale(fmax(fabs(rjj), fabs(aj)));
+                    const double rs = rjj * sc, as = aj * sc;
+                    rr = PFX_FMA(rs, rs, as * as);
+                    const double inv = 1.0 / sqrt(rr);
+                    c = rs * inv;
+                    sn = as * inv;
+                    R[ridx(j, j)] = (rr * inv) / sc;
+                }
 #pragma unroll
                 for (int k = j + 1; k < N; ++k) {
                     const double rjk = R[ridx(j, k)], ak = a[k];
@@ -582,13 +602,52 @@ struct LaneLM {
             double ss = 0.0;
 #pragma unroll
             for (int r = 0; r < B; ++r) ss = PFX_FMA(A[r][j], A[r][j], ss);
-            if (ss != 0.0) {
-                const double rjj = R[ridx(j, j)];
-                const double nrm = sqrt(PFX_FMA(rjj, rjj, ss));
+            int nnz = B, r0 = 0;
+            if (ss == 0.0 || R[ridx(j, j)] == 0.0) {
+                nnz = 0;
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    if (A[r][j] != 0.0) {
+                        ++nnz;
+                        r0 = r;
+                    }
+            }
+            if (nnz == 1 && R[ridx(j, j)] == 0.0) {
+                // exact case, see jac_block_staged
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    if (r == r0) {
+                        R[ridx(j, j)] = A[r][j];
+#pragma unroll
+                        for (int k = j + 1; k < N; ++k) {
+                            R[ridx(j, k)] = A[r][k];
+                            A[r][k] = 0.0;
+                        }
+                        q[j] = bv[r];
+                        bv[r] = 0.0;
+                    }
+            } else if (nnz != 0) {
+                double rjj = R[ridx(j, j)];
+                double t2 = PFX_FMA(rjj, rjj, ss);
+                double sc = 1.0;
+                if (!(t2 > 1e-200 && t2 < 1e200) && t2 == t2) {       // see jac_block_staged
+                    double amax = fabs(rjj);
+#pragma unroll
+                    for (int r = 0; r < B; ++r) amax = fmax(amax, fabs(A[r][j]));
+                    sc = unit_scale(amax);
+                    rjj *= sc;
+                    t2 = rjj * rjj;
+#pragma unroll
+                    for (int r = 0; r < B; ++r) {
+                        A[r][j] *= sc;
+                        t2 = PFX_FMA(A[r][j], A[r][j], t2);
+                    }
+                }
+                const double nrm = sqrt(t2);
                 const double alpha = (rjj > 0.0) ? -nrm : nrm;
                 const double v0 = rjj - alpha;
                 const double beta = 1.0 / (nrm * fabs(v0));
-                R[ridx(j, j)] = alpha;
+                R[ridx(j, j)] = (sc == 1.0) ? alpha : alpha / sc;
 #pragma unroll
                 for (int k = j + 1; k < N; ++k) {
                     double d = v0 * R[ridx(j, k)];
@@ -625,16 +684,65 @@ struct LaneLM {
                 c0[r] = (r < rows) ? blk[r * (N + 1) + j] : 0.0;
                 ss = PFX_FMA(c0[r], c0[r], ss);
             }
-            acn2[j] += 0.0;   // (column norms are accumulated by the producer loop)
-            if (ss != 0.0) {
-                const double rjj = R[ridx(j, j)];
-                const double t2 = PFX_FMA(rjj, rjj, ss);
+            // (column norms are accumulated by the producer loop)
+            // non-zero entries are only counted where it matters: the first rows that reach an empty
+            // row of the factor, and columns whose squares underflowed
+            int nnz = B, r0 = 0;
+            if (ss == 0.0 || R[ridx(j, j)] == 0.0) {
+                nnz = 0;
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    if (c0[r] != 0.0) {
+                        ++nnz;
+                        r0 = r;
+                    }
+            }
+            if (nnz == 1 && R[ridx(j, j)] == 0.0) {
+                // One non-zero entry meets an empty row j of the factor (R[j][j] == 0 means the row was
+                // never written): the reflection degenerates to moving that row into the factor, which
+                // is done EXACTLY.  MINPACK's qrfac is exact in the same situation -- a Jacobian whose
+                // columns j, k, ... are non-zero in one and the same row only (a model that touches a
+                // single data point: every other DM trial clipped, a Gaussian narrower than a bin)
+                // leaves exact zeros behind and lmpar sees the rank deficiency (r[j][j] == 0.0) --
+                // whereas a rounded reflection would leave 1e-16 residues that turn into a step along
+                // a noise direction.
+                R[ridx(j, j)] = c0[r0];
+#pragma unroll
+                for (int k = j + 1; k <= N; ++k) {
+                    const double v = blk[r0 * (N + 1) + k];
+                    if (k < N) R[ridx(j, k < N ? k : j)] = v;
+                    else q[j] = v;
+                    blk[r0 * (N + 1) + k] = 0.0;
+                }
+            } else if (nnz != 0) {
+                double rjj = R[ridx(j, j)];
+                double t2 = PFX_FMA(rjj, rjj, ss);
+                double sc = 1.0;
+                if (!(t2 > 1e-200 && t2 < 1e200) && t2 == t2) {
+                    // Entries so small (or large) that their squares leave the double range: rows far
+                    // out in the tail of a narrow Gaussian give derivatives of 1e-150 and less, the
+                    // reciprocals below would overflow and poison the factor with NaN (seen as
+                    // "gnorm = 0 -> info 4" on the first pass).  MINPACK's enorm is scaled and keeps
+                    // such columns; the same reflection is formed here from the column scaled by an
+                    // exact power of two (H = I - beta v v^T does not depend on the scale of v).
+                    double amax = fabs(rjj);
+#pragma unroll
+                    for (int r = 0; r < B; ++r) amax = fmax(amax, fabs(c0[r]));
+                    sc = unit_scale(amax);
+                    rjj *= sc;
+                    t2 = rjj * rjj;
+#pragma unroll
+                    for (int r = 0; r < B; ++r) {
+                        c0[r] *= sc;
+                        t2 = PFX_FMA(c0[r], c0[r], t2);
+                    }
+                }
                 const double inv = fast_rsqrt(t2);
                 const double nrm = t2 * inv;
                 const double alpha = (rjj > 0.0) ? -nrm : nrm;
                 const double v0 = rjj - alpha;
                 const double beta = inv * fast_rcp(fabs(v0));
-                R[ridx(j, j)] = alpha;
+                R[ridx(j, j)] = (sc == 1.0) ? alpha : alpha / sc;
 #pragma unroll
                 for (int k = j + 1; k <= N; ++k) {
                     double ck[B];
