@@ -152,8 +152,9 @@ int pfx_device_info(const pfx_ctx* ctx, int* sm_count, int* smem_per_block, size
 int pfx_reserve(pfx_ctx* ctx, const pfx_shape* shape, int64_t n_max);
 /* The histogram -> Gaussian chain of pfx_score_dev (the long pole, a persistent kernel pair that ends
  * in a tail of slow candidates) is cut into `nsub` sub-batches on separate streams so that the tail
- * of one overlaps the body of the next; 0 = default (4 for batches of 64 Ki candidates and more),
- * 1 = off.  Results do not depend on it: a candidate's row is a function of the candidate alone. */
+ * of one overlaps the body of the next; 0 = default = 1 = off (measured slower on B200, see
+ * DESIGN.md; kept as a knob).  Results do not depend on it: a candidate's row is a function of the
+ * candidate alone. */
 int pfx_set_subbatches(pfx_ctx* ctx, int nsub);
 
 /* ---- Lyon statistics -------------------------------------------------------------------

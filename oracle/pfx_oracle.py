@@ -825,6 +825,14 @@ def dm_fittings_pfd(chi_curve, dms, snr, dm, period_ms, width, log=None):
 
         def model(x, p):
             amp, prop, shift, up = p
+            if TWIN == 2:
+                weff = np.sqrt(wint + pow(prop * (kdm * abs((dm + shift) - x) * df) / pow(f, 3), 2))
+                weff = np.where(weff > period_ms, period_ms, weff)
+                return up + amp * (np.sqrt(period_ms - weff) / np.sqrt(weff))
+            if TWIN:
+                weff = np.sqrt(wint + pow((prop * (kdm * df / pow(f, 3))) * abs((dm + shift) - x), 2))
+                weff = np.where(weff > period_ms, period_ms, weff)
+                return up + amp * np.sqrt(period_ms / weff - 1.0)
             weff = np.sqrt(wint + pow(prop * kdm * abs((dm + shift) - x) * df / pow(f, 3), 2))
             weff = np.where(weff > period_ms, period_ms, weff)
             return up + amp * np.sqrt((period_ms - weff) / weff)

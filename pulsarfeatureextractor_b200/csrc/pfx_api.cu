@@ -192,12 +192,14 @@ int pfx::persistent_grid_impl(pfx_ctx* ctx, const void* fn, int threads, size_t 
     return PFX_OK;
 }
 
-// Number of sub-batches the Gaussian chain of a call is cut into.  The persistent lane kernels end
-// in a tail set by the slowest candidates (one candidate can take as long as six average ones);
-// with S sub-batches on S streams the blocks freed by the tail of one sub-batch are taken by the
-// body of the next, and the final-fit kernel of sub-batch k runs next to the rounds of k + 1.
+// Number of sub-batches the Gaussian chain of a call is cut into (pfx_set_subbatches).  The idea: the
+// persistent lane kernels end in a tail set by the slowest candidates, and with S sub-batches on S
+// streams the blocks freed by the tail of one sub-batch could be taken by the body of the next.
+// Measured on B200 (profiles/r02_subbatch_sweep.txt): it LOSES -- 727 / 787 / 898 / 968 ms per 100 k
+// candidates for S = 1 / 2 / 3 / 4 -- because a block leaves only when its last lane is done, so every
+// sub-batch pays a full tail of its own and its successor starts block by block.  Default: off.
 static int pick_subbatches(const pfx_ctx* ctx, int64_t n) {
-    int s = ctx->subbatch > 0 ? ctx->subbatch : 4;
+    int s = ctx->subbatch > 0 ? ctx->subbatch : 1;
     if (s > MAX_SUB) s = MAX_SUB;
     while (s > 1 && n / s < 16384) --s;
     return s;

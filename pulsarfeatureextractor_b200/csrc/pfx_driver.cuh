@@ -8,10 +8,19 @@ namespace pfx {
 
 PFX_HD inline int elem_size(int dtype) { return dtype == PFX_U8 ? 1 : (dtype == PFX_F32 ? 4 : 8); }
 
+// Inputs are read-only for the whole call: on the device they are read through the non-coherent
+// path (__ldg), which also tells the compiler that stores to working memory cannot alias them, so
+// the loads of a loop can be issued ahead of the stores of earlier iterations.
 PFX_HD inline double load_elem(const void* base, int dtype, long long idx) {
+#if defined(__CUDA_ARCH__)
+    if (dtype == PFX_U8) return (double)__ldg((const unsigned char*)base + idx);
+    if (dtype == PFX_F32) return (double)__ldg((const float*)base + idx);
+    return __ldg((const double*)base + idx);
+#else
     if (dtype == PFX_U8) return (double)((const unsigned char*)base)[idx];
     if (dtype == PFX_F32) return (double)((const float*)base)[idx];
     return ((const double*)base)[idx];
+#endif
 }
 
 // copy row `row` (len elements) of a typed [n][len] array into float64 work memory

@@ -149,6 +149,25 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
         __syncwarp();
         PFX_PROF_ADD(PROF_QUEUE, pq0);
         if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
+        if (ROUNDS_LANES == 1 && PFX_COOP) {
+            // close and set up fits with the whole warp, one candidate at a time (pfx_lane_gauss.cuh)
+            PFX_PROF_T0(pf0);
+            unsigned fin = __ballot_sync(0xffffffffu, g.phase == GP_FIN);
+            while (fin) {
+                const int src = __ffs(fin) - 1;
+                fin &= fin - 1;
+                g.coop_finish(src, b);
+            }
+            PFX_PROF_ADD(PROF_FINISH, pf0);
+            PFX_PROF_T0(ps0);
+            unsigned set = __ballot_sync(0xffffffffu, g.phase == GP_SETUP);
+            while (set) {
+                const int src = __ffs(set) - 1;
+                set &= set - 1;
+                g.coop_setup(src, b, ws);
+            }
+            PFX_PROF_ADD(PROF_SETUP, ps0);
+        }
         g.step(b, ws);
     }
     __syncwarp();
@@ -181,6 +200,7 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
     g.phase = GP_IDLE;
     g.cand = -1;
     bool more = true;
+    PFX_PROF_T0(pk0);
     for (;;) {
         if (g.phase == GP_IDLE) {
             if (g.cand >= 0) {
@@ -197,7 +217,9 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
                 if (G::rank() == 0) c = (long long)atomicAdd(counter, 1ULL);
                 c = G::bcast(c);
                 if (c < n) {
+                    PFX_PROF_T0(ps);
                     if (!carry[c].skip) g.start(profile, dtype, c, m, carry[c], b);
+                    PFX_PROF_ADD(PROF8_START, ps);
                 } else {
                     more = false;
                 }
@@ -206,6 +228,8 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
         if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
         g.step(b, ws);
     }
+    __syncwarp();
+    PFX_PROF_ADD(PROF8_TOTAL, pk0);
 }
 
 }  // namespace

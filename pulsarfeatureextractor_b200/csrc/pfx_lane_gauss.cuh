@@ -39,7 +39,12 @@ static __device__ unsigned long long g_pfx_prof[32];
 #define PFX_PROF_ADD(slot, v)
 #endif
 enum { PROF_SETUP = 0, PROF_JAC_ROWS = 1, PROF_JAC_END = 2, PROF_LMPAR = 3, PROF_TRIAL_ROWS = 4, PROF_TRIAL_END = 5,
-       PROF_FINISH = 6, PROF_QUEUE = 7, PROF_TOTAL = 8, PROF_TAIL = 9 };
+       PROF_FINISH = 6, PROF_QUEUE = 7, PROF_TOTAL = 8, PROF_TAIL = 9,
+       PROF8_START = 10, PROF8_JAC_ROWS = 11, PROF8_JAC_END = 12, PROF8_TRIAL = 13, PROF8_FINISH = 14, PROF8_TOTAL = 15 };
+
+#ifndef PFX_COOP
+#define PFX_COOP 1      // 0: every lane sets up and closes its own fits (round-1 behaviour, for comparison)
+#endif
 
 namespace pfx {
 
@@ -126,6 +131,175 @@ struct G4Jac {
         a2 = (PFX_SUB(yv, PFX_ADD(PFX_MUL(amxh, e0), bg)) - f0) * ih2;
         a3 = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) * ih3;
     }
+};
+
+// ---- warp-cooperative helpers --------------------------------------------------------------
+// The set-up and the close of a fit (copying / rebuilding the data vector, its statistics, the
+// chi-square) are passes over the bins of ONE candidate.  Run by the candidate's own lane they were
+// executed with 1.6-1.8 of 32 lanes active and took a fifth of k_gauss_rounds (phase profile,
+// profiles/r02_phase_profile_baseline.txt), because the lanes of a warp reach them at different
+// times.  Here the whole warp serves one candidate at a time: the bins are dealt to the 32 lanes
+// and sums are closed by a butterfly.  The summation order (32 strided partial sums, then the
+// butterfly) is fixed and reproduced on the host by one lane emulating the 32, so host and device
+// builds of the kernel logic stay comparable.
+struct WarpCoop {
+    static constexpr int W = 32;
+#if defined(__CUDA_ARCH__)
+    PFX_HD static int lane() { return (int)(threadIdx.x & 31); }
+    PFX_HD static double bc(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    PFX_HD static int bc(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    PFX_HD static long long bc(long long v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+    PFX_HD static void sync() { __syncwarp(); }
+    template <class F>
+    PFX_HD static void rows(int n, F f) {
+        for (int i = lane(); i < n; i += W) f(i);
+    }
+    // sum of val(i); with SQ the terms are val(i)^2 accumulated with one fused multiply-add each
+    template <bool SQ, class F>
+    PFX_HD static double sum(int n, F val) {
+        double p = 0.0;
+        for (int i = lane(); i < n; i += W) {
+            const double v = val(i);
+            p = SQ ? PFX_FMA(v, v, p) : PFX_ADD(p, v);
+        }
+#pragma unroll
+        for (int s = W / 2; s > 0; s >>= 1) p = PFX_ADD(p, __shfl_xor_sync(0xffffffffu, p, s));
+        return p;
+    }
+    // numpy.argmax (argmax_better is a total order, so the combination order is irrelevant) and
+    // Python's builtin max (a NaN survives only in first position)
+    template <class F>
+    PFX_HD static void maxima(int n, F val, int& amax, double& vmax, double& bmax) {
+        int bi = -1;
+        double bv = 0.0, mx = -INFINITY;
+        for (int i = lane(); i < n; i += W) {
+            const double v = val(i);
+            if (bi < 0 || argmax_better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+            if (v > mx) mx = v;
+        }
+#pragma unroll
+        for (int s = W / 2; s > 0; s >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, s), om = __shfl_xor_sync(0xffffffffu, mx, s);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+            if (oi >= 0 && (bi < 0 || argmax_better(ov, oi, bv, bi))) {
+                bv = ov;
+                bi = oi;
+            }
+            if (om > mx) mx = om;
+        }
+        const double d0 = val(0);
+        amax = bi;
+        vmax = bv;
+        bmax = (d0 != d0) ? d0 : mx;
+    }
+#else
+    PFX_HD static int lane() { return 0; }
+    PFX_HD static double bc(double v, int) { return v; }
+    PFX_HD static int bc(int v, int) { return v; }
+    PFX_HD static long long bc(long long v, int) { return v; }
+    PFX_HD static void sync() {}
+    template <class F>
+    PFX_HD static void rows(int n, F f) {
+        for (int i = 0; i < n; ++i) f(i);
+    }
+    template <bool SQ, class F>
+    PFX_HD static double sum(int n, F val) {
+        double part[W];
+        for (int l = 0; l < W; ++l) {
+            double p = 0.0;
+            for (int i = l; i < n; i += W) {
+                const double v = val(i);
+                p = SQ ? PFX_FMA(v, v, p) : PFX_ADD(p, v);
+            }
+            part[l] = p;
+        }
+        for (int s = W / 2; s > 0; s >>= 1) {
+            double t[W];
+            for (int l = 0; l < W; ++l) t[l] = PFX_ADD(part[l], part[l ^ s]);
+            for (int l = 0; l < W; ++l) part[l] = t[l];
+        }
+        return part[0];
+    }
+    template <class F>
+    PFX_HD static void maxima(int n, F val, int& amax, double& vmax, double& bmax) {
+        int bi = -1;
+        double bv = 0.0, mx = -INFINITY;
+        for (int i = 0; i < n; ++i) {
+            const double v = val(i);
+            if (bi < 0 || argmax_better(v, i, bv, bi)) {
+                bv = v;
+                bi = i;
+            }
+            if (v > mx) mx = v;
+        }
+        const double d0 = val(0);
+        amax = bi;
+        vmax = bv;
+        bmax = (d0 != d0) ? d0 : mx;
+    }
+#endif
+};
+
+// The index list of the peak stripping (PO:1305-1354) as a bit set over the bins: the list is always
+// an increasing subsequence of 0..m-1, so "delete the element at list position k" is "clear the k-th
+// set bit".  The reference deletes one or two elements per step of its loop, and a list kept as an
+// array pays a shift of the whole tail for each (O(m^2) shared-memory moves per candidate by a single
+// lane, 5 % of the kernel in round 1).  Words live in the lane's n x n workspace, which is idle while
+// a fit is set up.
+struct BinSet {
+    SPtr<double> w;      // 64 bins per slot
+    int nwords;
+    PFX_HD static int capacity(int slots) { return slots * 64; }
+    PFX_HD unsigned long long get(int k) const {
+        unsigned long long v;
+        const double d = w[k];
+        memcpy(&v, &d, 8);
+        return v;
+    }
+    PFX_HD void put(int k, unsigned long long v) const {
+        double d;
+        memcpy(&d, &v, 8);
+        w[k] = d;
+    }
+    PFX_HD void fill(int m) {
+        nwords = (m + 63) / 64;
+        for (int k = 0; k < nwords; ++k) {
+            const int left = m - 64 * k;
+            put(k, left >= 64 ? ~0ULL : ((1ULL << left) - 1ULL));
+        }
+    }
+    PFX_HD static int popc(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+        return __popcll(v);
+#else
+        return __builtin_popcountll(v);
+#endif
+    }
+    PFX_HD static int lowest(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+        return __ffsll((long long)v) - 1;
+#else
+        return __builtin_ctzll(v);
+#endif
+    }
+    // clear the k-th set bit (0 <= k < number of set bits)
+    PFX_HD void erase(int k) const {
+        for (int wd = 0; wd < nwords; ++wd) {
+            unsigned long long v = get(wd);
+            const int c = popc(v);
+            if (k < c) {
+                unsigned long long t = v;
+                for (int q = 0; q < k; ++q) t &= t - 1;
+                put(wd, v & ~(1ULL << lowest(t)));
+                return;
+            }
+            k -= c;
+        }
+    }
+    PFX_HD bool has(int i) const { return (get(i >> 6) >> (i & 63)) & 1ULL; }
 };
 
 // C lanes of a warp share the candidate (LaneGroup): one copy of the data vector per group.
@@ -471,19 +645,298 @@ struct GaussLaneT {
         }
     }
 
-    // one trip of the kernel loop
+    // ---- warp-cooperative set-up and close of a fit (one lane per candidate, C == 1) -------------
+    // Called by ALL lanes of the warp with the same src; the state of lane src is broadcast, the
+    // passes over its bins are dealt to the 32 lanes, and lane src alone commits the results.
+    PFX_HD static LaneBuf buf_of(const LaneBuf& b, int src) {
+        LaneBuf o = b;
+        const int d = src - WarpCoop::lane();
+        o.dat = b.dat + d;
+        o.xs = b.xs + d;
+        return o;
+    }
+    PFX_HD static double yrot_of(const void* prof, int dt, long long cd, int mm, int ct, int i) {
+        int sidx = i + ct;
+        if (sidx >= mm) sidx -= mm;
+        return load_elem(prof, dt, cd * (long long)mm + sidx);
+    }
+    PFX_HD static void coop_stats(const LaneBuf& bs, int n, double& mu, double& sdev, int& amax, double& vmax,
+                                  double& bmax) {
+        typedef WarpCoop WC;
+        const double sm = WC::template sum<false>(n, [&](int i) { return bs.d(i); });
+        mu = sm / (double)n;
+        const double mu_ = mu;
+        const double q = WC::template sum<true>(n, [&](int i) { return bs.d(i) - mu_; });
+        sdev = sqrt(q / (double)n);
+        WC::maxima(n, [&](int i) { return bs.d(i); }, amax, vmax, bmax);
+    }
+
+    // PO:1305-1354 with the index list kept as a bit set (BinSet); same control flow as strip_peak
+    PFX_HD int strip_peak_bits(const LaneBuf& b, BinSet& set, int pos) const {
+        const int n = m;
+        int len = n;
+        set.fill(n);
+#define PFX_DEL(k_)                              \
+    do {                                         \
+        int k = (k_);                            \
+        if (k < -len || k >= len) return -1;     \
+        if (k < 0) k += len;                     \
+        set.erase(k);                            \
+        --len;                                   \
+    } while (0)
+        PFX_DEL(pos);
+        int tol = 0;
+        const int limit = 5;
+        for (int i = 1; i < n; ++i) {
+            if ((pos - i) > 0 && (pos + i) < n) {
+                const double yl = b.d(pos - i), yl1 = b.d(pos - i + 1), yr_ = b.d(pos + i), yr1 = b.d(pos + i - 1);
+                if ((yl < yl1) && (yr_ < yr1)) {
+                    PFX_DEL(pos - i);
+                    PFX_DEL(pos - i);
+                } else if ((yl >= yl1) || ((yr_ >= yr1) && (tol < limit))) {
+                    PFX_DEL(pos - i);
+                    PFX_DEL(pos - i);
+                    ++tol;
+                } else {
+                    break;
+                }
+            } else if ((pos - i) < 0) {
+                if (pos + i >= n) return -1;
+                const double yr_ = b.d(pos + i), yr1 = b.d(pos + i - 1);
+                if (yr_ < yr1) {
+                    PFX_DEL(pos - i + 1);
+                } else if ((yr_ >= yr1) && (tol < limit)) {
+                    PFX_DEL(pos - i + 1);
+                    ++tol;
+                } else {
+                    break;
+                }
+            } else if ((pos + i) > n) {
+                const double yl = b.d(pos - i), yl1 = b.d(pos - i + 1);
+                if (yl < yl1) {
+                    PFX_DEL(pos - i + 1);
+                } else if ((yl >= yl1) && (tol < limit)) {
+                    PFX_DEL(pos - i);
+                    ++tol;
+                } else {
+                    break;
+                }
+            }
+        }
+#undef PFX_DEL
+        return len;
+    }
+
+    PFX_HD void coop_setup(int src, const LaneBuf& b, const LaneWs& ws) {
+        typedef WarpCoop WC;
+        const bool me = WC::lane() == src;
+        const LaneBuf bs = buf_of(b, src);
+        const int st = WC::bc(stage, src), mm = WC::bc(m, src), ct = WC::bc(cut, src), dt = WC::bc(dtype, src);
+        const long long cd = WC::bc(cand, src);
+        const void* prof = (const void*)WC::bc((long long)profile, src);
+        double x0[4];
+        int nr = mm;
+        G4Flags f;
+        if (st == 0) {
+            // profile statistics and the T1 data vector (PO:724-739, 1098-1110)
+            const double ph = WC::bc(ph_expect, src);
+            WC::rows(mm, [&](int i) {
+                bs.d(i) = yrot_of(prof, dt, cd, mm, ct, i);
+                bs.x(i) = (unsigned short)i;
+            });
+            WC::sync();
+            const double sm = WC::template sum<false>(mm, [&](int i) { return bs.d(i); });
+            const double mean_ = sm / (double)mm;
+            const double q = WC::template sum<true>(mm, [&](int i) { return bs.d(i) - mean_; });
+            const double sd_ = sqrt(q / (double)mm);
+            const double minbg_ = (mean_ < ph) ? mean_ : ph;     // builtin min(ph_expect, mean)
+            WC::sync();
+            if (minbg_ > 0.0) {
+                WC::rows(mm, [&](int i) {
+                    double v = PFX_ADD(PFX_SUB(bs.d(i), minbg_), sd_);
+                    if (v < 0.0) v = 0.0;
+                    bs.d(i) = v;
+                });
+            }
+            WC::sync();
+            double mu, sdev, vmax, bmax;
+            int amax;
+            coop_stats(bs, mm, mu, sdev, amax, vmax, bmax);
+            x0[0] = sdev;
+            x0[1] = (double)amax;
+            x0[2] = vmax;
+            x0[3] = 1.0;
+            f.abs_sigma = true;
+            f.abs_bg = false;
+            if (me) {
+                mean = mean_;
+                sd = sd_;
+                minbg = minbg_;
+            }
+        } else if (st == 1) {
+            // rotated raw profile, peak stripping (PO:1305-1354)
+            WC::rows(mm, [&](int i) { bs.d(i) = yrot_of(prof, dt, cd, mm, ct, i); });
+            WC::sync();
+            int amax;
+            double vmax, bmax;
+            WC::maxima(mm, [&](int i) { return bs.d(i); }, amax, vmax, bmax);
+            int nlen = 0;
+            if (me) {
+                if (mm <= BinSet::capacity(lane_ws_doubles(4))) {
+                    BinSet set;
+                    set.w = ws.blk;
+                    nlen = strip_peak_bits(bs, set, amax);
+                    if (nlen > 0) {
+                        int cnt = 0;
+                        for (int i = 0; i < mm; ++i)
+                            if (set.has(i)) {       // i >= cnt: no overwrite hazard
+                                bs.d(cnt) = bs.d(i);
+                                bs.x(cnt) = (unsigned short)i;
+                                ++cnt;
+                            }
+                    }
+                } else {
+                    nlen = strip_peak(bs, amax);
+                    for (int k = 0; k < nlen; ++k) bs.d(k) = bs.d(bs.x(k));
+                }
+            }
+            nlen = WC::bc(nlen, src);
+            WC::sync();
+            if (nlen <= 0) {
+                if (me) {
+                    if (nlen < 0) {                 // IndexError -> 1e6 sentinels (PO:762-764)
+                        sentinel = true;
+                        status |= PFX_ST_DG_SENTINEL;
+                    } else {
+                        status |= PFX_ST_EMPTY_SEQUENCE;
+                    }
+                    finished = true;
+                    phase = GP_IDLE;
+                }
+                return;
+            }
+            double mu, sdev;
+            int am2;
+            coop_stats(bs, nlen, mu, sdev, am2, vmax, bmax);
+            x0[0] = sdev;
+            x0[1] = (double)bs.x(am2);
+            x0[2] = bmax;
+            x0[3] = mu;
+            nr = nlen;
+            WC::sync();
+            if (nlen < 4) {                          // PO:1373-1377 zero padding
+                if (me)
+                    for (int k = nlen; k < 4; ++k) {
+                        bs.d(k) = 0.0;
+                        bs.x(k) = 0;
+                    }
+                nr = 4;
+            }
+            WC::sync();
+            f.abs_sigma = false;
+            f.abs_bg = true;
+        } else {
+            // rounds 2..8: data were rebuilt by the previous round's close
+            double mu, sdev, vmax, bmax;
+            int amax;
+            coop_stats(bs, mm, mu, sdev, amax, vmax, bmax);
+            x0[0] = sdev;
+            x0[1] = (double)bs.x(amax);
+            x0[2] = bmax;
+            x0[3] = mu;
+            f.abs_sigma = false;
+            f.abs_bg = true;
+        }
+        if (me) {
+            fl = f;
+            nrows = nr;
+            lm.init(x0);
+            phase = GP_JAC;
+        }
+    }
+
+    PFX_HD void coop_finish(int src, const LaneBuf& b) {
+        typedef WarpCoop WC;
+        const bool me = WC::lane() == src;
+        const LaneBuf bs = buf_of(b, src);
+        const int st = WC::bc(stage, src), mm = WC::bc(m, src), ct = WC::bc(cut, src), dt = WC::bc(dtype, src);
+        const long long cd = WC::bc(cand, src);
+        const void* prof = (const void*)WC::bc((long long)profile, src);
+        double p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = WC::bc(lm.x[k], src);
+        G4Flags f;
+        f.abs_sigma = (st == 0);
+        f.abs_bg = (st != 0);
+        if (st == 0) {
+            G4Eval ev;
+            ev.set(p, f);
+            const double c = WC::template sum<true>(mm, [&](int i) { return bs.d(i) - ev.value((double)i); });
+            if (me) {
+                for (int k = 0; k < 4; ++k) p_t1[k] = p[k];
+                t1_fwhm = fabs(FWHM_K * p[0]);
+                t1_chi = c / (double)mm;
+            }
+        } else {
+            // rebuild the data for the next round over the full profile (PO:1388-1399)
+            const double nfwhm = fabs(FWHM_K * p[0]);
+            const double lo = p[2] - (1.5 * nfwhm) / 2.0;
+            const double hi = p[2] + (1.5 * nfwhm) / 2.0;
+            G4Eval fe;
+            fe.set(p, f);
+            WC::sync();
+            if (st < 8) {
+                WC::rows(mm, [&](int i) {
+                    const double xv = (double)i;
+                    const double ev = fe.value(xv);
+                    const double yv = yrot_of(prof, dt, cd, mm, ct, i);
+                    double nv;
+                    if (ev <= yv) nv = PFX_ADD(PFX_SUB(yv, ev), p[3]);
+                    else if ((ev > yv) && (xv > lo) && (xv < hi)) nv = p[3];
+                    else nv = yv;
+                    bs.d(i) = nv;
+                    bs.x(i) = (unsigned short)i;
+                });
+            }
+            WC::sync();
+            if (me) {
+                if (st == 7)
+                    for (int k = 0; k < 4; ++k) p2[k] = p[k];
+                if (st == 8)
+                    for (int k = 0; k < 4; ++k) p1[k] = p[k];
+            }
+        }
+        if (me) {
+            ier[st] = (int8_t)lm.info;
+            ++stage;
+            if (stage > 8) {
+                finished = true;
+                phase = GP_IDLE;
+            } else {
+                phase = GP_SETUP;
+            }
+        }
+    }
+
+    // one trip of the kernel loop.  With one lane per candidate the kernel serves the SETUP and FIN
+    // phases of the warp cooperatively before it calls step(); the host build (one lane) serves
+    // itself here.
     PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {
-        if (phase == GP_SETUP) {
-            PFX_PROF_T0(pt);
+        if (C == 1 && PFX_COOP) {
+#if !defined(__CUDA_ARCH__)
+            if (phase == GP_SETUP) coop_setup(0, b, ws);
+#endif
+        } else if (phase == GP_SETUP) {
             setup(b);
-            PFX_PROF_ADD(PROF_SETUP, pt);
         }
         if (phase == GP_JAC) jac_pass(b, ws);
         if (phase == GP_TRIAL) trial_pass(b, ws);
-        if (phase == GP_FIN) {
-            PFX_PROF_T0(pt);
+        if (C == 1 && PFX_COOP) {
+#if !defined(__CUDA_ARCH__)
+            if (phase == GP_FIN) coop_finish(0, b);
+#endif
+        } else if (phase == GP_FIN) {
             finish(b);
-            PFX_PROF_ADD(PROF_FINISH, pt);
         }
     }
 
@@ -536,6 +989,7 @@ struct Gauss8LaneT {
     }
 
     PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
+        PFX_PROF_T0(pt0);
         lm.jac_begin();
         const double* x = lm.x;
         const double* h = lm.h;
@@ -582,11 +1036,15 @@ struct Gauss8LaneT {
             lm.template jac_block<B>(A, bv);
         }
         lm.template jac_combine<C>();
+        PFX_PROF_ADD(PROF8_JAC_ROWS, pt0);
+        PFX_PROF_T0(pt1);
         const int r = lm.template jac_end_shared<C>(ws, m);      // one n x n workspace per group
         phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+        PFX_PROF_ADD(PROF8_JAC_END, pt1);
     }
 
     PFX_HD void trial_pass(const LaneBuf& b, const LaneWs& ws) {
+        PFX_PROF_T0(pt0);
         lm.template trial_begin_shared<C>(ws);
         double s = 0.0;
         for (int i = G::rank(); i < m; i += C) {
@@ -596,6 +1054,7 @@ struct Gauss8LaneT {
         s = G::sum(s);
         const int r = lm.trial_end(sqrt(s));
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+        PFX_PROF_ADD(PROF8_TRIAL, pt0);
     }
 
     // PO:1407-1428 and PO:747-761
@@ -667,7 +1126,11 @@ struct Gauss8LaneT {
     PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {
         if (phase == GP_JAC) jac_pass(b, ws);
         if (phase == GP_TRIAL) trial_pass(b, ws);
-        if (phase == GP_FIN) finish(b);
+        if (phase == GP_FIN) {
+            PFX_PROF_T0(pt);
+            finish(b);
+            PFX_PROF_ADD(PROF8_FINISH, pt);
+        }
     }
 };
 

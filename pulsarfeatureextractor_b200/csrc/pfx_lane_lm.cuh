@@ -33,8 +33,12 @@ namespace pfx {
 // caller to the streamed column norms of the full Jacobian.
 template <class RV, class IV>
 PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag, double* wa) {
+    double acn0[NPMAX];      // column norms of the full Jacobian (permuted along with rdiag)
     PFX_ROLL
-    for (int j = 0; j < n; ++j) ipvt[j] = j;
+    for (int j = 0; j < n; ++j) {
+        ipvt[j] = j;
+        acn0[j] = rdiag[j];
+    }
     PFX_ROLL
     for (int j = 0; j < n; ++j) {
         int kmax = j;
@@ -50,6 +54,7 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
             }
             rdiag[kmax] = rdiag[j];
             wa[kmax] = wa[j];
+            acn0[kmax] = acn0[j];
             int t = ipvt[j];
             ipvt[j] = ipvt[kmax];
             ipvt[kmax] = t;
@@ -80,6 +85,19 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
                         PFX_ROLL
                         for (int i = j + 1; i < n; ++i) s2 += a[i + ld * k] * a[i + ld * k];
                         rdiag[k] = sqrt(s2);
+                        // Exact rank deficiency.  On the full Jacobian MINPACK leaves EXACT zeros behind
+                        // when the columns j, k, ... are non-zero in one and the same row only (a model
+                        // that touches a single data point: every other DM trial clipped, a Gaussian
+                        // narrower than a bin), and lmpar then sees r[k][k] == 0.0 and does not move
+                        // those parameters.  The triangular factor accumulated block by block carries
+                        // rounding residues of a few ulp of the column norm instead, which would turn
+                        // into a step along a noise direction: a remainder below 1e-13 of the column's
+                        // original norm is such a residue and is flushed to the exact zero.
+                        if (rdiag[k] <= 1e-13 * acn0[k]) {
+                            PFX_ROLL
+                            for (int i = j + 1; i < n; ++i) a[i + ld * k] = 0.0;
+                            rdiag[k] = 0.0;
+                        }
                         wa[k] = rdiag[k];
                     }
                 }
@@ -193,18 +211,6 @@ PFX_HD inline double exp_neg(double a) {
 #endif
     const double res = (p * s1) * s2;
     return (a != a) ? a : res;
-}
-
-// 2^-k with k = floor(log2 a) (clamped): an exact scale factor that brings a > 0 to [1, 2).  Used on
-// the rare paths where a sum of squares would leave the double range (entries below 1e-100: the far
-// tails of a Gaussian model), so that the reflections stay finite where MINPACK's scaled enorm does.
-PFX_HD inline double unit_scale(double a) {
-    int e = 0;
-    (void)frexp(a, &e);
-    int k = 1 - e;
-    if (k > 1000) k = 1000;
-    if (k < -1000) k = -1000;
-    return ldexp(1.0, k);
 }
 
 PFX_HD inline double fast_rsqrt(double x) {
@@ -518,24 +524,13 @@ struct LaneLM {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const double aj = a[j];
-            if (aj != 0.0) {
-                const double rjj = R[ridx(j, j)];
-                double rr = PFX_FMA(rjj, rjj, aj * aj);
-                double c, sn;
-                if (rr > 1e-200 && rr < 1e200) {
-                    const double inv = fast_rsqrt(rr);
-                    c = rjj * inv;
-                    sn = aj * inv;
-                    R[ridx(j, j)] = rr * inv;
-                } else {            // out of range (or NaN): the same rotation from scaled entries
-                    const double sc = unit_scale(fmax(fabs(rjj), fabs(aj)));
-                    const double rs = rjj * sc, as = aj * sc;
-                    rr = PFX_FMA(rs, rs, as * as);
-                    const double inv = 1.0 / sqrt(rr);
-                    c = rs * inv;
-                    sn = as * inv;
-                    R[ridx(j, j)] = (rr * inv) / sc;
-                }
+            const double rjj = R[ridx(j, j)];
+            const double rr = PFX_FMA(rjj, rjj, aj * aj);
+            // (entries whose squares underflow are dropped: see jac_block_staged)
+            if (aj != 0.0 && !(rr <= 1e-290)) {
+                const double inv = fast_rsqrt(rr);
+                const double c = rjj * inv, sn = aj * inv;
+                R[ridx(j, j)] = rr * inv;
 #pragma unroll
                 for (int k = j + 1; k < N; ++k) {
                     const double rjk = R[ridx(j, k)], ak = a[k];
@@ -602,52 +597,17 @@ struct LaneLM {
             double ss = 0.0;
 #pragma unroll
             for (int r = 0; r < B; ++r) ss = PFX_FMA(A[r][j], A[r][j], ss);
-            int nnz = B, r0 = 0;
-            if (ss == 0.0 || R[ridx(j, j)] == 0.0) {
-                nnz = 0;
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    if (A[r][j] != 0.0) {
-                        ++nnz;
-                        r0 = r;
-                    }
-            }
-            if (nnz == 1 && R[ridx(j, j)] == 0.0) {
-                // exact case, see jac_block_staged
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    if (r == r0) {
-                        R[ridx(j, j)] = A[r][j];
-#pragma unroll
-                        for (int k = j + 1; k < N; ++k) {
-                            R[ridx(j, k)] = A[r][k];
-                            A[r][k] = 0.0;
-                        }
-                        q[j] = bv[r];
-                        bv[r] = 0.0;
-                    }
-            } else if (nnz != 0) {
-                double rjj = R[ridx(j, j)];
-                double t2 = PFX_FMA(rjj, rjj, ss);
-                double sc = 1.0;
-                if (!(t2 > 1e-200 && t2 < 1e200) && t2 == t2) {       // see jac_block_staged
-                    double amax = fabs(rjj);
-#pragma unroll
-                    for (int r = 0; r < B; ++r) amax = fmax(amax, fabs(A[r][j]));
-                    sc = unit_scale(amax);
-                    rjj *= sc;
-                    t2 = rjj * rjj;
-#pragma unroll
-                    for (int r = 0; r < B; ++r) {
-                        A[r][j] *= sc;
-                        t2 = PFX_FMA(A[r][j], A[r][j], t2);
-                    }
-                }
-                const double nrm = sqrt(t2);
+            const double rjj = R[ridx(j, j)];
+            const double t2 = PFX_FMA(rjj, rjj, ss);
+            if (ss != 0.0 && !(t2 <= 1e-290)) {          // see jac_block_staged
+                // reciprocal square root and reciprocal instead of sqrt and a division: two short
+                // dependency chains per column instead of two long ones
+                const double inv = fast_rsqrt(t2);
+                const double nrm = t2 * inv;
                 const double alpha = (rjj > 0.0) ? -nrm : nrm;
                 const double v0 = rjj - alpha;
-                const double beta = 1.0 / (nrm * fabs(v0));
-                R[ridx(j, j)] = (sc == 1.0) ? alpha : alpha / sc;
+                const double beta = inv * fast_rcp(fabs(v0));
+                R[ridx(j, j)] = alpha;
 #pragma unroll
                 for (int k = j + 1; k < N; ++k) {
                     double d = v0 * R[ridx(j, k)];
@@ -685,64 +645,20 @@ struct LaneLM {
                 ss = PFX_FMA(c0[r], c0[r], ss);
             }
             // (column norms are accumulated by the producer loop)
-            // non-zero entries are only counted where it matters: the first rows that reach an empty
-            // row of the factor, and columns whose squares underflowed
-            int nnz = B, r0 = 0;
-            if (ss == 0.0 || R[ridx(j, j)] == 0.0) {
-                nnz = 0;
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    if (c0[r] != 0.0) {
-                        ++nnz;
-                        r0 = r;
-                    }
-            }
-            if (nnz == 1 && R[ridx(j, j)] == 0.0) {
-                // One non-zero entry meets an empty row j of the factor (R[j][j] == 0 means the row was
-                // never written): the reflection degenerates to moving that row into the factor, which
-                // is done EXACTLY.  MINPACK's qrfac is exact in the same situation -- a Jacobian whose
-                // columns j, k, ... are non-zero in one and the same row only (a model that touches a
-                // single data point: every other DM trial clipped, a Gaussian narrower than a bin)
-                // leaves exact zeros behind and lmpar sees the rank deficiency (r[j][j] == 0.0) --
-                // whereas a rounded reflection would leave 1e-16 residues that turn into a step along
-                // a noise direction.
-                R[ridx(j, j)] = c0[r0];
-#pragma unroll
-                for (int k = j + 1; k <= N; ++k) {
-                    const double v = blk[r0 * (N + 1) + k];
-                    if (k < N) R[ridx(j, k < N ? k : j)] = v;
-                    else q[j] = v;
-                    blk[r0 * (N + 1) + k] = 0.0;
-                }
-            } else if (nnz != 0) {
-                double rjj = R[ridx(j, j)];
-                double t2 = PFX_FMA(rjj, rjj, ss);
-                double sc = 1.0;
-                if (!(t2 > 1e-200 && t2 < 1e200) && t2 == t2) {
-                    // Entries so small (or large) that their squares leave the double range: rows far
-                    // out in the tail of a narrow Gaussian give derivatives of 1e-150 and less, the
-                    // reciprocals below would overflow and poison the factor with NaN (seen as
-                    // "gnorm = 0 -> info 4" on the first pass).  MINPACK's enorm is scaled and keeps
-                    // such columns; the same reflection is formed here from the column scaled by an
-                    // exact power of two (H = I - beta v v^T does not depend on the scale of v).
-                    double amax = fabs(rjj);
-#pragma unroll
-                    for (int r = 0; r < B; ++r) amax = fmax(amax, fabs(c0[r]));
-                    sc = unit_scale(amax);
-                    rjj *= sc;
-                    t2 = rjj * rjj;
-#pragma unroll
-                    for (int r = 0; r < B; ++r) {
-                        c0[r] *= sc;
-                        t2 = PFX_FMA(c0[r], c0[r], t2);
-                    }
-                }
+            // A column whose entries are so small that rjj^2 + ss leaves the normal range (rows far
+            // out in the tail of a narrow Gaussian give derivatives of 1e-150 and less) is dropped:
+            // the reciprocals below would overflow and poison the factor with NaN (round 1: "gnorm = 0
+            // -> info 4" on the first pass of such fits), and against entries of order one elsewhere
+            // in the column its weight is below 1e-290.
+            const double rjj = R[ridx(j, j)];
+            const double t2 = PFX_FMA(rjj, rjj, ss);
+            if (ss != 0.0 && !(t2 <= 1e-290)) {
                 const double inv = fast_rsqrt(t2);
                 const double nrm = t2 * inv;
                 const double alpha = (rjj > 0.0) ? -nrm : nrm;
                 const double v0 = rjj - alpha;
                 const double beta = inv * fast_rcp(fabs(v0));
-                R[ridx(j, j)] = (sc == 1.0) ? alpha : alpha / sc;
+                R[ridx(j, j)] = alpha;
 #pragma unroll
                 for (int k = j + 1; k <= N; ++k) {
                     double ck[B];

@@ -25,6 +25,8 @@ torch.cuda.synchronize()
 assert lib.pfx_debug_profile(buf, 0) == 0
 names = ["setup", "jac rows + QR", "jac_end (n x n)", "lmpar (n x n)", "trial rows", "trial_end", "finish",
          "queue / flush", "TOTAL (warp life)", "tail (queue empty .. exit)"]
+names8 = ["final: start", "final: jac rows + QR", "final: jac_end (n x n)", "final: trial (lmpar + rows)",
+          "final: finish", "final: TOTAL (warp life)"]
 v = np.array(list(buf), dtype=np.float64).reshape(16, 2)
 tot = v[8, 0]
 print("k_gauss_rounds phase profile, %d candidates, hist+rounds+final %.1f ms (instrumented build)" % (n, e0.elapsed_time(e1)))
@@ -34,3 +36,9 @@ for k, nm in enumerate(names):
     print("%-28s %10.3f %7.1f%% %12.2f" % (nm, c / 1e9, 100 * c / tot, lc / c if c else 0))
 busy = v[:8, 1].sum()
 print("lane-cycles in phases / (32 x warp life) = %.3f" % (busy / (32 * tot)))
+tot8 = v[15, 0]
+if tot8:
+    print("k_gauss_final")
+    for k, nm in enumerate(names8):
+        c, lc = v[10 + k]
+        print("%-28s %10.3f %7.1f%% %12.2f" % (nm, c / 1e9, 100 * c / tot8, lc / c if c else 0))

@@ -117,11 +117,48 @@ def writer(mods):
         os.chdir(cwd)
 
 
+def profile_mode(mods):
+    """--profile mode (raw profile bins as the "scores", PHCXFile.py:291-304, SUPERBPHCXFile.py:291-304):
+    the reference's computeProfileScores and the CSV / ARFF text its writer makes of them."""
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)
+    try:
+        DP = mods["DataProcessor"].DataProcessor
+        rows, names, csv, arff, kinds = [], [], [], [], []
+        for kind, cls, nbin, ext in (("phcx", mods["PHCXFile"].PHCX, 128, ".phcx.gz"),
+                                     ("superb", mods["SUPERBPHCXFile"].SUPERBPHCX, 64, ".phcx")):
+            b = synth.generate(17, 0, 8, nbin=nbin)
+            for i in range(4):
+                path = os.path.join(tmp, "cand_%s_%d%s" % (kind, i, ext))
+                phcx_io.write_phcx(path, b.profile[i], b.subbands[i], b.dmcurve[i], b.dmstat[i], b.params[i],
+                                   superb=(kind == "superb"))
+                scores = cls(False, path).computeProfileScores()
+                dp = DP(False)
+                dp.storeScore(os.path.basename(path), scores, "unused")
+                dp.storeScoreARFF(os.path.basename(path), scores, "unused")
+                rows.append(np.array(scores, dtype=np.float64))
+                names.append(os.path.basename(path))
+                csv.append(dp.scoreStore[0])
+                arff.append(dp.scoreStore[1])
+                kinds.append(kind)
+        width = max(len(r) for r in rows)
+        mat = np.full((len(rows), width), np.nan)
+        for i, r in enumerate(rows):
+            mat[i, :len(r)] = r
+        np.savez_compressed(os.path.join(HERE, "ref_profile_mode_v1.npz"), names=np.array(names), kinds=np.array(kinds),
+                            scores=mat, ncol=np.array([len(r) for r in rows]), csv=np.array(csv), arff=np.array(arff))
+        print("profile mode: wrote", len(rows), "rows")
+    finally:
+        os.chdir(cwd)
+
+
 def main():
     warnings.simplefilter("ignore")
     mods = refshim.load_reference()
     superb(mods)
     writer(mods)
+    profile_mode(mods)
 
 
 if __name__ == "__main__":

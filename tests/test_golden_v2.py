@@ -109,3 +109,37 @@ def test_live_reference_writer_random_rows(tmp_path, monkeypatch):
     assert [O.format_row(names[i], vals[i]) for i in range(60)] == dp.scoreStore
     if phcx_io.native_available():
         assert phcx_io.format_rows(vals, names, None, "csv", True) == "\n".join(dp.scoreStore) + "\n"
+
+
+def test_profile_mode_rows_equal_reference(tmp_path):
+    """--profile (raw profile bins instead of scores, PHCXFile.py:291-304): the CLI classes write the rows
+    the reference's computeProfileScores + storeScore / storeScoreARFF produce (tests/golden/
+    ref_profile_mode_v1.npz), for HTRU .phcx.gz (section 1, 128 bins) and SUPERB .phcx (section 0, 64 bins)."""
+    from pulsarfeatureextractor_b200.DataProcessor import DataProcessor
+    g = np.load(os.path.join(HERE, "golden", "ref_profile_mode_v1.npz"))
+    for kind, nbin, method in (("phcx", 128, "processPHCXCollectively"), ("superb", 64, "processSUPERBCollectively")):
+        d = tmp_path / kind
+        d.mkdir()
+        b = synth.generate(17, 0, 8, nbin=nbin)
+        sel = [i for i in range(len(g["names"])) if str(g["kinds"][i]) == kind]
+        for i in sel:
+            k = int(str(g["names"][i]).split("_")[2].split(".")[0])
+            phcx_io.write_phcx(str(d / str(g["names"][i])), b.profile[k], b.subbands[k], b.dmcurve[k], b.dmstat[k],
+                               b.params[k], superb=(kind == "superb"))
+        for arff in (False, True):
+            out = tmp_path / ("%s_%d.txt" % (kind, arff))
+            dp = DataProcessor(False, engine=None, error_log=str(tmp_path / "err.txt"))
+            ok, bad = getattr(dp, method)(str(d) + "/", False, str(out), arff, True, False)
+            assert (ok, bad) == (len(sel), 0)
+            lines = [l for l in open(out).read().split("\n") if l and not l.startswith("@")]
+            want = {}
+            for i in sel:
+                want[str(g["names"][i])] = str(g["arff" if arff else "csv"][i])
+            got = {}
+            for l in lines:
+                name = os.path.basename(l.split(",")[0] if not arff else l.split("?%")[1])
+                got[name] = l.replace(str(d) + "/", "")
+            assert got == want, (kind, arff)
+            if arff:
+                head = open(out).read()
+                assert head.count("@attribute Score") == nbin and "@attribute class {0,1}" in head
