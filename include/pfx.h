@@ -156,6 +156,11 @@ int pfx_reserve(pfx_ctx* ctx, const pfx_shape* shape, int64_t n_max);
  * DESIGN.md; kept as a knob).  Results do not depend on it: a candidate's row is a function of the
  * candidate alone. */
 int pfx_set_subbatches(pfx_ctx* ctx, int nsub);
+/* DM-curve fit (scores 17, 18; PHCXOperations.py:212, PFDOperations.py:369).  on = 1 (default): every sum
+ * inside lmdif runs in MINPACK's own order without contraction, and scores 16-19 and ier equal scipy's
+ * bit for bit (the model needs only correctly rounded operations).  on = 0: the faster streaming
+ * factorisation of the other fits, equal to scipy at the rounding level only. */
+int pfx_set_dm_exact(pfx_ctx* ctx, int on);
 
 /* ---- Lyon statistics -------------------------------------------------------------------
  * Replaces PHCX.computeProfileStatScores / computeDMCurveStatScores (PHCXFile.py:320-379,

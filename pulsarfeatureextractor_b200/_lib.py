@@ -33,7 +33,7 @@ EXPORTS = [
     "pfx_version", "pfx_create", "pfx_destroy", "pfx_last_error", "pfx_device_info",
     "pfx_lyon8_dev", "pfx_pfd_params_dev", "pfx_sinusoid_dev", "pfx_gaussian_dev", "pfx_dmfit_dev", "pfx_subband_dev",
     "pfx_score_dev", "pfx_score_host", "pfx_last_timing", "pfx_set_stage_timing",
-    "pfx_reserve", "pfx_set_subbatches",
+    "pfx_reserve", "pfx_set_subbatches", "pfx_set_dm_exact",
 ]
 
 
@@ -82,6 +82,7 @@ def load():
     lib.pfx_set_stage_timing.argtypes = [vp, ctypes.c_int]
     lib.pfx_reserve.argtypes = [vp, sp, i64]
     lib.pfx_set_subbatches.argtypes = [vp, ctypes.c_int]
+    lib.pfx_set_dm_exact.argtypes = [vp, ctypes.c_int]
     for name in EXPORTS:
         getattr(lib, name)
     return lib

@@ -62,6 +62,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     // sub-batches of the histogram -> Gaussian chain per call (see score_dev_impl); PFX_SUBBATCH
     // overrides the default for experiments
     ctx->subbatch = 0;
+    ctx->dm_exact = 1;
+    if (const char* e = getenv("PFX_DM_EXACT")) ctx->dm_exact = atoi(e) != 0;
     if (const char* e = getenv("PFX_SUBBATCH")) ctx->subbatch = atoi(e);
     *out = ctx;
     return PFX_OK;
@@ -437,6 +439,12 @@ extern "C" int pfx_reserve(pfx_ctx* ctx, const pfx_shape* shape, int64_t n_max) 
         if (rc) return rc;
     }
     ctx->reserved = true;
+    return PFX_OK;
+}
+
+extern "C" int pfx_set_dm_exact(pfx_ctx* ctx, int on) {
+    if (!ctx) return PFX_ERR_INVALID;
+    ctx->dm_exact = on != 0;
     return PFX_OK;
 }
 

@@ -73,6 +73,7 @@ struct Group;
 template <>
 struct Group<1> {
     static constexpr int W = 1;
+    static constexpr bool ordered = false;     // (one lane: sums run in row order anyway)
     PFX_HD Group() {}
     PFX_HD int lane() const { return 0; }
     PFX_HD bool leader() const { return true; }
@@ -94,6 +95,7 @@ struct Group<1> {
 template <int W_>
 struct Group {
     static constexpr int W = W_;
+    static constexpr bool ordered = false;
     unsigned mask;
     int ln;
     __device__ Group() {
@@ -155,9 +157,32 @@ struct Group {
 };
 #endif
 
+#if defined(__CUDACC__)
+// A group whose sums over rows run IN ROW ORDER, un-fused, on the leader (the other lanes wait):
+// element-wise work is still striped over the lanes, but every inner product rounds exactly like the
+// sequential loops of MINPACK and numpy do.  With it the DM-curve fit, whose model needs only
+// correctly rounded operations (+ - * / sqrt), reproduces scipy.optimize.leastsq BIT FOR BIT
+// (pfx_k_dmfit_exact.cu; checked on the host with the one-lane build in tests/test_hostsim_logic.py).
+template <int W_>
+struct OrderedGroup : Group<W_> {
+    static constexpr bool ordered = true;
+};
+#endif
+
+// sum over rows lo..m-1 of term(i), in row order, by the leader; every lane gets the result
+template <class G, class F>
+PFX_HD inline double ordered_rows(const G& g, int lo, int m, F term) {
+    g.sync();
+    double s = 0.0;
+    if (g.leader())
+        for (int i = lo; i < m; ++i) s = PFX_ADD(s, term(i));
+    return g.bcast(s, 0);
+}
+
 // ---- row-striped reductions --------------------------------------------------------------
 template <class G>
 PFX_HD inline double rows_sum(const G& g, const double* a, int lo, int m) {
+    if constexpr (G::ordered) return ordered_rows(g, lo < 0 ? 0 : lo, m, [&](int i) { return a[i]; });
     double s = 0.0;
     for (int i = g.lane(); i < m; i += G::W)
         if (i >= lo) s += a[i];
@@ -166,6 +191,7 @@ PFX_HD inline double rows_sum(const G& g, const double* a, int lo, int m) {
 
 template <class G>
 PFX_HD inline double rows_sumsq(const G& g, const double* a, int lo, int m) {
+    if constexpr (G::ordered) return ordered_rows(g, lo < 0 ? 0 : lo, m, [&](int i) { return PFX_MUL(a[i], a[i]); });
     double s = 0.0;
     for (int i = g.lane(); i < m; i += G::W)
         if (i >= lo) s = PFX_FMA(a[i], a[i], s);
@@ -174,6 +200,7 @@ PFX_HD inline double rows_sumsq(const G& g, const double* a, int lo, int m) {
 
 template <class G>
 PFX_HD inline double rows_dot(const G& g, const double* a, const double* b, int lo, int m) {
+    if constexpr (G::ordered) return ordered_rows(g, lo < 0 ? 0 : lo, m, [&](int i) { return PFX_MUL(a[i], b[i]); });
     double s = 0.0;
     for (int i = g.lane(); i < m; i += G::W)
         if (i >= lo) s = PFX_FMA(a[i], b[i], s);

@@ -63,6 +63,7 @@ struct pfx_ctx {
     int set_rr;
     pfx_grid_cache_entry grid_cache[32];
     int n_grid_cache;
+    int dm_exact;             // 1: DM-curve fit in MINPACK's own summation order (bit-exact form), 0: lane form
     int subbatch;             // sub-batches of the histogram/Gaussian chain per pfx_score_dev call
     bool reserved;            // pfx_reserve was called: growing scratch inside a call is reported
     cudaEvent_t ev[pfx::N_EVENTS];
@@ -134,6 +135,8 @@ int launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profil
                  int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_dmfit(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
                  double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
+int launch_dmfit_exact(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
+                       double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, const void* subbands,
                    const double* params, double* feat, int64_t ld, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_lyon(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, const void* dmstat,

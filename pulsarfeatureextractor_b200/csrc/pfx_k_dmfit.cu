@@ -74,31 +74,6 @@ int launch_n(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, c
     return PFX_OK;
 }
 
-// Warp form: the Jacobian is stored and factorised by MINPACK's own qrfac (pfx_lm.cuh), one warp per
-// candidate.  Used for the PFD family.  Its DM model is clipped (weff <= P, PFDOperations.py:305-307),
-// so a typical candidate has two or three unclipped trial DMs carrying four parameters: the Jacobian is
-// rank deficient, and what scipy returns is decided by the rounding residues of qrfac on the FULL
-// Jacobian (exact zeros outside the unclipped rows, 1e-16 inside).  The streaming factorisation of the
-// lane form cannot reproduce those residues (measured on 512 PFD-shaped candidates: 84 % of the
-// well-conditioned fits within 1e-6 against 96 % for the oracle's own re-associated twin, p90 of the
-// relative error 0.98 against 0.09); this form does (90 % / 0.06).  It costs more time per fit, and
-// the DM fit is a few per cent of the step.
-__global__ void __launch_bounds__(BLOCK_THREADS, 4)
-k_dmfit_warp(const void* __restrict__ dmcurve, int dm_dtype, long long n, int n_dm, int family,
-             const double* __restrict__ params, double* feat, long long ld, int8_t* ier,
-             int32_t* status, u64* counter, int work_doubles) {
-    extern __shared__ double smem[];
-    Group<WARP> g;
-    double* ws = smem + (threadIdx.x / WARP) * work_doubles;
-    for (;;) {
-        const long long c = next_candidate(g, counter);
-        if (c >= n) break;
-        unsigned st = dmfit_candidate(g, ws, dmcurve, dm_dtype, c, n_dm, family, params + c * PFX_NPARAM,
-                                      feat + c * ld, ier ? ier + c * PFX_NIER : nullptr);
-        if (st && g.leader()) atomicOr(status + c, (int)st);
-    }
-}
-
 __global__ void k_pfd_params(const void* __restrict__ profile, int dtype, long long n, int nbin, double* params) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -121,21 +96,9 @@ int pfx::launch_pfd_params(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const vo
 int pfx::launch_dmfit(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* dmcurve, const double* params,
                       double* feat, int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
     if (s->n_dm < 4) return set_err(ctx, PFX_ERR_UNSUPPORTED, "n_dm < 4");
-    if (s->family == PFX_FAMILY_PFD) {
-        const int wd = align_up(dm_work_doubles(s->n_dm), 2);
-        int warps = GROUPS_PER_BLOCK;
-        while (warps > 1 && (size_t)wd * 8 * warps > (size_t)ctx->smem_optin) warps >>= 1;
-        const size_t smem = (size_t)wd * 8 * warps;
-        if (smem > (size_t)ctx->smem_optin)
-            return set_err(ctx, PFX_ERR_UNSUPPORTED, "DM curve of %d trials needs %zu bytes of shared memory, limit %d",
-                           s->n_dm, smem, ctx->smem_optin);
-        int grid;
-        int rc = persistent_grid(ctx, k_dmfit_warp, warps * WARP, smem, &grid);
-        if (rc) return rc;
-        k_dmfit_warp<<<grid, warps * WARP, smem, st>>>(dmcurve, s->dm_dtype, n, s->n_dm, s->family, params, feat, ld,
-                                                        ier, status, take_counter(set, ck, st), wd);
-        PFX_CUDA(ctx, cudaGetLastError());
-        return PFX_OK;
-    }
+    // default: the bit-exact form (pfx_k_dmfit_exact.cu); pfx_set_dm_exact(ctx, 0) selects the lane form
+    if (ctx->dm_exact) return launch_dmfit_exact(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, set, ck);
+    if (s->family == PFX_FAMILY_PFD)
+        return launch_n<4>(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, set, ck);
     return launch_n<3>(ctx, s, n, dmcurve, params, feat, ld, ier, status, st, set, ck);
 }

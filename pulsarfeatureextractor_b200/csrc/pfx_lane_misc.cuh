@@ -213,13 +213,13 @@ struct DmLane {
     // sqrt((P - weff)/weff), weff = sqrt(wint + (prop kdm |dm + shift - x| df / f^3)^2)
     PFX_HD double shape(double prop, double shift, double xv) const {
         const double a = fabs(PFX_SUB(PFX_ADD(dm, shift), xv));
-        const double q = PFX_DIV(PFX_MUL(PFX_MUL(PFX_MUL(prop, 8300000.0), a), df), f3);
+        const double q = PFX_DIV(PFX_MUL(PFX_MUL(PFX_MUL(prop, 8300000.000000001), a), df), f3);
         double weff = sqrt(PFX_ADD(wint, PFX_MUL(q, q)));
         if (pfd && weff > period) weff = period;
         return sqrt(PFX_DIV(PFX_SUB(period, weff), weff));
     }
     PFX_HD double theo_shape(double xv) const {
-        const double q = PFX_DIV(PFX_MUL(PFX_MUL(8300000.0, fabs(PFX_SUB(dm, xv))), df), f3);
+        const double q = PFX_DIV(PFX_MUL(PFX_MUL(8300000.000000001, fabs(PFX_SUB(dm, xv))), df), f3);
         double weff = sqrt(PFX_ADD(wint, PFX_MUL(q, q)));
         if (pfd && weff > period) weff = period;
         return sqrt(PFX_DIV(PFX_SUB(period, weff), weff));

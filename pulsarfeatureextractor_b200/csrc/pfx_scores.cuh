@@ -843,7 +843,7 @@ PFX_HD inline unsigned dm_scores(const G& g, DmWork& w, int n_dm, int family, co
     if (!(length_all > 0.0)) length_all = pfd ? (double)n_dm : 128.0 * (double)n_dm;
     const double dm_step = fabs(dm_start - dm_end) / length_all;
     const double wint = (width * period_ms) * (width * period_ms);
-    const double kdm = 8300000.0;
+    const double kdm = 8300000.000000001;   // 8.3*10**6 as Python evaluates it (PHXO:187, PFDO:342): one ulp above 8.3e6
     const double df = pfd ? 32.0 : 400.0;
     const double f3 = pfd ? 2460375.0 : 2593941624.0;   // 135^3, 1374^3
     const double sw = sqrt(wint);
@@ -875,14 +875,23 @@ PFX_HD inline unsigned dm_scores(const G& g, DmWork& w, int n_dm, int family, co
         shift = p[2];
         double c = 0.0;
         fit_rows<3>(g, f, p, w.v.wa4, n_dm);
-        for (int i = g.lane(); i < n_dm; i += G::W) {
-            double fit = w.v.wa4[i];
-            if (fit >= 1.0) {
-                double d = w.y[i] - w.theo[i];
-                c = PFX_FMA(d, d, c);
+        if constexpr (G::ordered) {
+            // (a masked term adds nothing, like the skipped iteration of the reference's loop)
+            c = ordered_rows(g, 0, n_dm, [&](int i) {
+                const double d = PFX_SUB(w.y[i], w.theo[i]);
+                return (w.v.wa4[i] >= 1.0) ? PFX_MUL(d, d) : 0.0;
+            });
+        } else {
+            for (int i = g.lane(); i < n_dm; i += G::W) {
+                double fit = w.v.wa4[i];
+                if (fit >= 1.0) {
+                    double d = w.y[i] - w.theo[i];
+                    c = PFX_FMA(d, d, c);
+                }
             }
+            c = g.sum(c);
         }
-        chi_theo = g.sum(c) / (double)n_dm;    // PHXO:222-230: theoretical curve, masked by the fit
+        chi_theo = c / (double)n_dm;    // PHXO:222-230: theoretical curve, masked by the fit
     } else {
         DmPfdModel f;
         f.x = w.x; f.y = w.y; f.wint = wint; f.period = period_ms; f.dm = dm; f.kdm = kdm; f.df = df; f.f3 = f3;
@@ -894,17 +903,27 @@ PFX_HD inline unsigned dm_scores(const G& g, DmWork& w, int n_dm, int family, co
         shift = p[2];
         double c = 0.0;
         int ndeg = 0;
-        for (int i = g.lane(); i < n_dm; i += G::W) {
-            double th = w.theo[i];
-            if (th > 0.0) {
-                double d = w.y[i] - th;
-                c += (d * d) / th;
-                ++ndeg;
-            }
-        }
+        for (int i = g.lane(); i < n_dm; i += G::W)
+            if (w.theo[i] > 0.0) ++ndeg;
         ndeg = g.sum(ndeg);
         if (ndeg == 0) return st | PFX_ST_DM_NDEG_ZERO;
-        chi_theo = g.sum(c) / (double)ndeg;    // PFDO:378-387
+        if constexpr (G::ordered) {
+            c = ordered_rows(g, 0, n_dm, [&](int i) {
+                const double th = w.theo[i];
+                const double d = PFX_SUB(w.y[i], th);
+                return (th > 0.0) ? PFX_DIV(PFX_MUL(d, d), th) : 0.0;
+            });
+        } else {
+            for (int i = g.lane(); i < n_dm; i += G::W) {
+                double th = w.theo[i];
+                if (th > 0.0) {
+                    double d = w.y[i] - th;
+                    c += (d * d) / th;
+                }
+            }
+            c = g.sum(c);
+        }
+        chi_theo = c / (double)ndeg;    // PFDO:378-387
     }
     if (g.leader()) {
         feat[15] = peak;

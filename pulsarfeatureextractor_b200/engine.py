@@ -97,6 +97,10 @@ class Engine(object):
         """Sub-batches of the histogram/Gaussian chain per call (0 = default, 1 = off)."""
         self._check(self._lib.pfx_set_subbatches(self._h, int(nsub)))
 
+    def set_dm_exact(self, on):
+        """DM-curve fit in MINPACK's own summation order, bit-exact against scipy (default on)."""
+        self._check(self._lib.pfx_set_dm_exact(self._h, int(on)))
+
     def set_stage_timing(self, on):
         """Serialise and time the score groups of score_device (see pfx_set_stage_timing)."""
         self._check(self._lib.pfx_set_stage_timing(self._h, int(on)))

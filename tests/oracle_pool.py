@@ -137,6 +137,8 @@ def tier_table(rows, gpu_feat, gpu_ier, cols=LM):
             "gpu_within_1e-6_in_tier_w": float(np.mean(e_g[w, k] <= 1e-6)) if w.any() else None,
             "twin2_within_1e-6_in_tier_w": float(np.mean(e_2[w, k] <= 1e-6)) if w.any() else None,
             "gpu_p50_p90_p99": q(e_g), "twin1_p50_p90_p99": q(e_1), "twin2_p50_p90_p99": q(e_2),
+            "gpu_within_1e-6_all": float(np.mean(e_g[:, k] <= 1e-6)), "twin1_within_1e-6_all": float(np.mean(e_1[:, k] <= 1e-6)),
+            "gpu_bit_exact": float(np.mean(e_g[:, k] == 0)), "twin1_bit_exact": float(np.mean(e_1[:, k] == 0)),
         }
     slots = {}
     for s in range(16):

@@ -30,14 +30,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_phcx_v1.npz")
 DET = [2, 3, 11, 12, 13, 14, 15, 18, 19, 20, 21]
 LM = [0, 1, 4, 5, 6, 7, 8, 9, 10, 16, 17]
-# Thresholds of the distributional tests, set from the measured table profiles/r02_parity.json
-# (scripts/gpu_parity_table.py; SURVEY 8c asks for 99.9 % / 2x / -2 points where the data allow).
+# Thresholds of the distributional tests (scripts/gpu_parity_table.py writes the table).
+# Set from the measured table profiles/r02_parity.json (B200, 5 000 / 512 / 256 candidates): in Tier W the GPU is
+# within 0.2 (HTRU), 3.6 (PFD shape, 168-candidate tier) and 1.0 (1024 bins) points of twin 2, its p50 / p90 within
+# 1.4x (2.8x PFD score 6) of the twins', "every ier slot equal" 1.2 points under twin 1 in all three.  SURVEY 8c asks
+# for 2x / -2 points; the margins left here are sampling noise of the smaller batches.
 THRESH = {
-    "htru": dict(min_tier_w=20, slack_pts=0.12, q_factor=20.0, ier_slack=0.10),
-    "pfd": dict(min_tier_w=20, slack_pts=0.12, q_factor=20.0, ier_slack=0.10),
-    "1024": dict(min_tier_w=10, slack_pts=0.15, q_factor=20.0, ier_slack=0.10),
-    "bench_within_1e-6": {k: 0.0 for k in LM},
-    "bench_ier_all_slots": 0.0,
+    "htru": dict(min_tier_w=20, slack_pts=0.06, q_factor=4.0, ier_slack=0.06),       # 192-candidate module batch
+    "pfd": dict(min_tier_w=20, slack_pts=0.06, q_factor=4.0, ier_slack=0.04),
+    "1024": dict(min_tier_w=10, slack_pts=0.04, q_factor=3.0, ier_slack=0.04),
+    # fraction of the 5 000-candidate bench sample within 1e-6 of the oracle, per least-squares column (the
+    # oracle's own twin 1 reaches the same values +- 1 point; scores 17, 18: bit-exact DM fit)
+    "bench_within_1e-6": {0: 0.9992, 1: 0.9986, 4: 0.9659, 5: 0.9062, 6: 0.9397, 7: 0.5821, 8: 0.961, 9: 0.3917, 10: 0.7172, 16: 1.0, 17: 1.0},
+    "bench_ier_all_slots": 0.6276,
 }
 
 
@@ -152,14 +157,14 @@ def test_least_squares_scores_on_the_noise_floor(batch_and_oracle):
         w = e_t1[:, k] <= 1e-8
         assert w.sum() >= 20
         f_gpu, f_t2 = np.mean(e_gpu[w, k] <= 1e-6), np.mean(e_t2[w, k] <= 1e-6)
-        assert f_gpu >= f_t2 - 0.12, (k + 1, f_gpu, f_t2, int(w.sum()))
+        assert f_gpu >= f_t2 - THRESH["htru"]["slack_pts"], (k + 1, f_gpu, f_t2, int(w.sum()))
         for q in (0.5, 0.9):
             gq = np.quantile(e_gpu[:, k], q)
             tq = max(np.quantile(e_t1[:, k], q), np.quantile(e_t2[:, k], q))
-            assert gq <= max(20 * tq, 1e-7), (k + 1, q, gq, tq)
+            assert gq <= max(THRESH["htru"]["q_factor"] * tq, 1e-7), (k + 1, q, gq, tq)
     a_gpu = np.mean([np.array_equal(ier[i, :16], r.ier[:16]) for i, r, tws in good])
     a_t1 = np.mean([np.array_equal(tws[0].ier[:16], r.ier[:16]) for i, r, tws in good])
-    assert a_gpu >= a_t1 - 0.10, (a_gpu, a_t1)
+    assert a_gpu >= a_t1 - THRESH["htru"]["ier_slack"], (a_gpu, a_t1)
 
 
 def test_host_path_equals_device_path_and_sharding(eng, batch_and_oracle):
@@ -431,6 +436,7 @@ def test_pfd_files_end_to_end(eng, tmp_path):
     scan = pfd_io.PfdScan(paths)
     det = [2, 3, 11, 12, 13, 14, 15, 19, 20, 21]
     nok = 0
+    dm_exact = 0
     errs = []
     for k, p in enumerate(paths):
         assert scan.ok(k)
@@ -451,12 +457,12 @@ def test_pfd_files_end_to_end(eng, tmp_path):
         f = out.features[0, :22]
         for c in det:
             assert _det_ok(ref[c], f[c]), (k, c + 1, ref[c], f[c])
-        # scores 17 and 18 (Prop, Shift of the 4-parameter DM fit) are left out of the point-wise
-        # comparison: on these chi-square curves the fit is chaotic -- scipy itself moves them by
-        # O(1) when the model expression is merely re-associated (measured: |1 - Prop| 0.957 -> 0.607,
-        # ier 5 -> 2, ...) -- while score 19 and the other fits are reproducible
         e = _rel(ref, f)
-        assert np.isfinite(f[16]) and np.isfinite(f[17])
+        # scores 16-19: the DM-curve fit runs in MINPACK's own summation order (k_dmfit_exact) on a curve
+        # that is bit-identical to the reference's, so it reproduces the reference's scipy run exactly
+        # although the fit itself is chaotic (scipy moves |1 - Prop| from 0.957 to 0.607 when the model
+        # expression is merely re-associated)
+        dm_exact += int(np.array_equal(ref[15:19], f[15:19], equal_nan=True))
         # the well-conditioned fits agree point-wise: both sinusoid chi-squares, the chi-square of the
         # Gaussian + background fit, the chi-square of the theoretical DM curve
         for c in (0, 1, 8, 18):
@@ -464,11 +470,13 @@ def test_pfd_files_end_to_end(eng, tmp_path):
         errs.append(e)
     scan.close()
     assert nok >= 6
+    assert dm_exact >= nok - 1, (dm_exact, nok)
     # the histogram / double-Gaussian scores (5-8, 10, 11) sit on the usual noise floor of ill
-    # conditioned fits: judged by the median over the candidates
-    med = np.median(np.array(errs), axis=0)
+    # conditioned fits (oracle twins on PFD-shaped data: p50 1e-8 .. 1e-4, p90 up to 1,
+    # profiles/r02_parity.json): at least a third of the candidates within 1e-4 per column
+    errs = np.array(errs)
     for c in (4, 5, 6, 7, 9, 10):
-        assert med[c] <= 1e-4, (c + 1, med[c])
+        assert np.mean(errs[:, c] <= 1e-4) >= 1.0 / 3.0, (c + 1, np.sort(errs[:, c]))
     # the CLI classes on the same directory: one row per scored candidate, failures logged
     outp = tmp_path / "pfd_scores.csv"
     dp = DataProcessor(False, engine=eng, error_log=str(tmp_path / "pfd_err.txt"))
@@ -532,6 +540,12 @@ def test_pfd_family_least_squares_envelope(eng):
     feat, status, ier = _dev_family(eng, b, _lib.PFX_FAMILY_PFD)
     _deterministic(rows, feat, status)
     _envelope(rows, feat, ier, LM, **THRESH["pfd"])
+    # 4-parameter DM fit: bit-identical to scipy on >= 98 % of these rank-deficient curves (the oracle's
+    # own re-associated twins agree with it on 5 % of them)
+    ok = (rows.status & O.ST_FAIL_MASK) == 0
+    same = (rows.feat[ok, 15:19] == feat[ok, 15:19]) | (np.isnan(rows.feat[ok, 15:19]) & np.isnan(feat[ok, 15:19]))
+    assert np.mean(same.all(axis=1)) >= 0.98, float(np.mean(same.all(axis=1)))
+    assert np.mean(ier[ok, 15] == rows.ier[ok, 15]) >= 0.98
 
 
 def test_survey_1024_bins_least_squares_envelope(eng):
@@ -572,6 +586,31 @@ def test_bench_stream_sample_against_oracle(eng):
         assert frac >= THRESH["bench_within_1e-6"][k] - 0.02, (k + 1, frac)
     agree = float(np.mean((ier[ok, :16] == rows.ier[ok, :16]).all(axis=1)))
     assert agree >= THRESH["bench_ier_all_slots"] - 0.02, agree
+    # the DM-curve fit (k_dmfit_exact: MINPACK's own summation order, no contraction) equals scipy's bit for bit
+    same = (rows.feat[ok, 15:19] == feat[ok, 15:19]) | (np.isnan(rows.feat[ok, 15:19]) & np.isnan(feat[ok, 15:19]))
+    assert np.mean(same.all(axis=1)) >= 0.999, float(np.mean(same.all(axis=1)))
+    assert np.mean(ier[ok, 15] == rows.ier[ok, 15]) >= 0.999
+
+
+def test_dm_fit_lane_form_knob(eng):
+    """pfx_set_dm_exact(ctx, 0) selects the streaming-factorisation (lane) form of the DM fit: the same
+    algorithm at the rounding level -- scores 17, 18 within 1e-6 of the exact form on most candidates,
+    everything else unchanged bit for bit."""
+    b = synth.generate(2, 0, 2048)
+    f1, s1, i1 = _dev(eng, b)
+    eng.set_dm_exact(0)
+    try:
+        f0, s0, i0 = _dev(eng, b)
+    finally:
+        eng.set_dm_exact(1)
+    assert np.array_equal(s0, s1)
+    cols = [c for c in range(30) if c not in (15, 16, 17, 18)]
+    assert np.array_equal(f0[:, cols], f1[:, cols], equal_nan=True)
+    ok = (s1 & O.ST_FAIL_MASK) == 0
+    for c in (15, 18):      # peak S/N and the chi-square of the theoretical curve: summation order only
+        assert _rel(f1[ok, c], f0[ok, c]).max() <= 1e-12, c + 1
+    for c in (16, 17):
+        assert np.mean(_rel(f1[ok, c], f0[ok, c]) <= 1e-6) >= 0.75, c + 1
 
 
 def test_superb_golden(eng):

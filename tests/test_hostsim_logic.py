@@ -280,6 +280,57 @@ def test_warp_form_routines_agree_with_lane_form(hs):
     assert agree >= len(idx) - 2
 
 
+def test_dm_fit_in_minpack_order_equals_scipy_bit_for_bit(hs):
+    """The stored-Jacobian form with sums in row order and no contraction (what k_dmfit_exact runs on an
+    OrderedGroup; here the one-lane host build) against scipy through the oracle: scores 16-19 and ier
+    bit-identical on every PHCX-shaped candidate (3-parameter model, PHXO:121-259) and on >= 98 % of the
+    PFD-shaped ones (4-parameter clipped model, PFDO:274-393, rank deficient on most curves)."""
+    def host(dmc, dt, fam, prm):
+        feat = np.full(22, np.nan)
+        ier = np.zeros(18, np.int8)
+        dmc, prm = np.ascontiguousarray(dmc), np.ascontiguousarray(prm)
+        st = hs.hs_dmfit(P(dmc), dt, dmc.size, fam, P(prm), P(feat), P(ier))
+        return feat[15:19], ier[15], st
+
+    b = synth.generate(2, 0, 300)
+    same = []
+    for i in range(len(b)):
+        snr, dm, bary_p, width, dm_start, dm_end = [float(v) for v in b.params[i][:6]]
+        n_dm = b.dmcurve.shape[1]
+        log = O.FitLog()
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = O.dm_fittings_phcx(b.dmcurve[i].astype(np.int64), 128 * np.arange(n_dm) - 1, 128 * n_dm, snr, dm,
+                                         bary_p * 1000, width, dm_start, dm_end, log)
+        except Exception:
+            continue
+        f, ie, st = host(b.dmcurve[i], 0, 0, b.params[i])
+        if st & O.ST_FAIL_MASK:
+            continue
+        same.append(np.array_equal(f, np.array(ref), equal_nan=True) and ie == log.ier[O.FIT_DM])
+    assert len(same) >= 250 and all(same), (len(same), int(np.sum(same)))
+
+    bp = synth.generate_pfd_shaped(4, 0, 300)
+    same = []
+    for i in range(len(bp)):
+        snr, dm, bary_p, width, dm_start, dm_end = [float(v) for v in bp.params[i][:6]]
+        n = bp.dmcurve.shape[1]
+        dms = np.concatenate([[dm_start], np.linspace(dm_start, dm_end, n - 1)])
+        log = O.FitLog()
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                ref = O.dm_fittings_pfd(bp.dmcurve[i], dms, snr, dm, bary_p * 1000, width, log)
+        except Exception:
+            continue
+        f, ie, st = host(bp.dmcurve[i], 1, 1, bp.params[i])
+        if st & O.ST_FAIL_MASK:
+            continue
+        same.append(np.array_equal(f, np.array(ref), equal_nan=True) and ie == log.ier[O.FIT_DM])
+    assert len(same) >= 100 and np.mean(same) >= 0.98, (len(same), float(np.mean(same)))
+
+
 def test_lyon_rows(hs):
     rng = np.random.default_rng(2)
     for dt, code in ((np.uint8, 0), (np.float32, 1), (np.float64, 2)):
