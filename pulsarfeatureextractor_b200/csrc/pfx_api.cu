@@ -63,6 +63,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     // overrides the default for experiments
     ctx->subbatch = 0;
     ctx->dm_exact = 1;
+    ctx->gauss_hybrid = 0;
+    if (const char* e = getenv("PFX_HYBRID")) ctx->gauss_hybrid = atoi(e) != 0;
     if (const char* e = getenv("PFX_DM_EXACT")) ctx->dm_exact = atoi(e) != 0;
     if (const char* e = getenv("PFX_SUBBATCH")) ctx->subbatch = atoi(e);
     *out = ctx;

@@ -64,6 +64,39 @@ constexpr int ROUNDS_MAXT = ROUNDS_LANES == 1 ? 128 : (ROUNDS_LANES == 2 ? 224 :
 constexpr int FINAL_MAXT = FINAL_LANES == 1 ? 128 : 256;
 constexpr int FINAL_WS_PER_GROUP = 1;          // the lanes of a group share the n x n workspace
 
+// results of a candidate that finished its nine 4-parameter fits: scores 8, 9, the carry record of the
+// final-fit kernel, ier slots, status bits (called by the owner lane)
+template <class GL>
+__device__ __forceinline__ void flush_rounds(GL& g, double* feat, long long ld, int8_t* ier, int32_t* status,
+                                             GaussCarry* carry) {
+    double* row = feat + g.cand * ld;
+    row[7] = g.t1_fwhm;
+    row[8] = g.t1_chi;
+    GaussCarry& cy = carry[g.cand];
+    cy.skip = (g.sentinel || (g.status & PFX_ST_FAIL_MASK)) ? 1 : 0;
+    if (g.sentinel) {
+        row[9] = 1000000.0;
+        row[10] = 1000000.0;
+    }
+    if (!cy.skip) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cy.p_t1[k] = g.p_t1[k];
+            cy.p1[k] = g.p1[k];
+            cy.p2[k] = g.p2[k];
+        }
+        cy.minbg = g.minbg;
+        cy.sd = g.sd;
+        cy.t1_fwhm = g.t1_fwhm;
+    }
+    if (ier) {
+        int8_t* ir = ier + g.cand * PFX_NIER + PFX_FIT_T1;
+        for (int k = 0; k < 9; ++k) ir[k] = g.ier[k];
+    }
+    if (g.status) atomicOr(status + g.cand, (int)g.status);
+    g.cand = -1;
+}
+
 __global__ void __launch_bounds__(ROUNDS_MAXT, 1)
 k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
                int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
@@ -91,35 +124,7 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
 #endif
         if (g.phase == GP_IDLE) {
             if (g.cand >= 0 && G::rank() != 0) g.cand = -1;
-            if (g.cand >= 0) {
-                // flush the finished candidate (lane 0 of the group)
-                double* row = feat + g.cand * ld;
-                row[7] = g.t1_fwhm;
-                row[8] = g.t1_chi;
-                GaussCarry& cy = carry[g.cand];
-                cy.skip = (g.sentinel || (g.status & PFX_ST_FAIL_MASK)) ? 1 : 0;
-                if (g.sentinel) {
-                    row[9] = 1000000.0;
-                    row[10] = 1000000.0;
-                }
-                if (!cy.skip) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        cy.p_t1[k] = g.p_t1[k];
-                        cy.p1[k] = g.p1[k];
-                        cy.p2[k] = g.p2[k];
-                    }
-                    cy.minbg = g.minbg;
-                    cy.sd = g.sd;
-                    cy.t1_fwhm = g.t1_fwhm;
-                }
-                if (ier) {
-                    int8_t* ir = ier + g.cand * PFX_NIER + PFX_FIT_T1;
-                    for (int k = 0; k < 9; ++k) ir[k] = g.ier[k];
-                }
-                if (g.status) atomicOr(status + g.cand, (int)g.status);
-                g.cand = -1;
-            }
+            if (g.cand >= 0) flush_rounds(g, feat, ld, ier, status, carry);
             if (more) {
                 long long c = 0;
                 if (G::rank() == 0) c = (long long)atomicAdd(counter, 1ULL);
@@ -169,6 +174,133 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
             PFX_PROF_ADD(PROF_SETUP, ps0);
         }
         g.step(b, ws);
+    }
+    __syncwarp();
+    PFX_PROF_ADD(PROF_TOTAL, pk0);
+#if defined(PFX_PROFILE)
+    if (ptail) PFX_PROF_ADD(PROF_TAIL, ptail);
+#endif
+}
+
+// ---- hybrid form of the rounds kernel (pfx_lane_gauss.cuh, RowFactor4) --------------------------
+// A warp owns K candidates (lanes 0 .. K-1 hold their fit state and run the n x n work); all 32 lanes
+// serve the row passes, eight per candidate, four candidates per turn.  K must be 32 (the staging block of
+// a worker lane lives in its own n x n workspace).  EXPERIMENTAL, off by default (PFX_HYBRID=1 selects it):
+// measured on B200 at 100 000 candidates, histogram + rounds + final 621 ms against 633 ms for the lane
+// kernel -- the tail of slow candidates shrinks (20 % of a warp's life instead of 28 %) and 15 % fewer
+// instructions are issued, but four-row leaves plus three merge levels are 56 dependent Householder
+// chains per Jacobian pass and candidate where the lane kernel runs 16, and those chains, not the
+// exponentials, bound a pass (profiles/r02_phase_profile_hybrid_k32.txt, r02_rounds_hybrid_summary.txt).  Shared memory: ws[44][slots] | dat[slot][pitch] float64
+// | xs[slot][pitch] uint16, one contiguous data vector per candidate (pitch = bins + 8: neighbouring
+// candidates start 16 banks apart); long profiles keep the vectors in a global scratch of the same shape.
+#ifndef PFX_HY_K
+#define PFX_HY_K 32
+#endif
+constexpr int HY_K = PFX_HY_K;
+constexpr int HY_MAX_SLOTS = 128;
+constexpr int HY_MAXT = HY_MAX_SLOTS / HY_K * 32;
+
+__global__ void __launch_bounds__(HY_MAXT, 1)
+k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
+                 int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
+                 unsigned short* gxs, int pitch) {
+    extern __shared__ double smem[];
+    const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+    const int nslots = (int)(blockDim.x >> 5) * HY_K;
+    const int slot = warp * HY_K + lane;          // lanes >= K: never dereferenced, only used as a base for offsets
+    LaneWs ws;
+    ws.carve(smem + slot, nslots, 4);
+    LaneBuf b;
+    b.stride = 1;
+    b.pitch = pitch;
+    if (gdat) {
+        const size_t gslot = (size_t)blockIdx.x * nslots + slot;
+        b.dat = gdat + gslot * pitch;
+        b.xs = gxs + gslot * pitch;
+    } else {
+        double* dat = smem + (size_t)lane_ws_doubles(4) * nslots;
+        b.dat = dat + (size_t)slot * pitch;
+        b.xs = (unsigned short*)(dat + (size_t)nslots * pitch) + (size_t)slot * pitch;
+    }
+    GaussLaneT<1> g;
+    g.phase = GP_IDLE;
+    g.finished = false;
+    g.cand = -1;
+    g.nrows = 0;
+    bool more = lane < HY_K;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    PFX_PROF_T0(pk0);
+#if defined(PFX_PROFILE)
+    long long ptail = 0;
+#endif
+    for (;;) {
+        PFX_PROF_T0(pq0);
+#if defined(PFX_PROFILE)
+        if (!ptail && __any_sync(0xffffffffu, lane < HY_K && !more)) ptail = clock64();
+#endif
+        if (g.phase == GP_IDLE && lane < HY_K) {
+            if (g.cand >= 0) flush_rounds(g, feat, ld, ier, status, carry);
+            if (more) {
+                const long long c = (long long)atomicAdd(counter, 1ULL);
+                if (c < n) {
+                    double* row = feat + c * ld;
+                    const double ph = row[7];      // parked by k_hist
+                    const int before = (int)(PFX_ST_FAIL_MASK & ~(PFX_ST_DM_NDEG_ZERO | PFX_ST_SUBBAND_NO_PAIRS |
+                                                                  PFX_ST_SUBBAND_BAD_WIDTH));
+                    if (status[c] & before) {
+                        row[7] = qnan;             // the reference raised before reaching score 8
+                        carry[c].skip = 1;
+                    } else {
+                        g.start(profile, dtype, c, m, ph);
+                    }
+                } else {
+                    more = false;
+                }
+            }
+        }
+        __syncwarp();
+        PFX_PROF_ADD(PROF_QUEUE, pq0);
+        if (!__any_sync(0xffffffffu, g.phase != GP_IDLE || more)) break;
+        {
+            PFX_PROF_T0(pf0);
+            unsigned fin = __ballot_sync(0xffffffffu, g.phase == GP_FIN);
+            while (fin) {
+                const int src = __ffs(fin) - 1;
+                fin &= fin - 1;
+                g.coop_finish(src, b);
+            }
+            PFX_PROF_ADD(PROF_FINISH, pf0);
+            PFX_PROF_T0(ps0);
+            unsigned set = __ballot_sync(0xffffffffu, g.phase == GP_SETUP);
+            while (set) {
+                const int src = __ffs(set) - 1;
+                set &= set - 1;
+                g.coop_setup(src, b, ws);
+            }
+            PFX_PROF_ADD(PROF_SETUP, ps0);
+        }
+        // Jacobian pass: constants by the owners, rows by the warp, n x n by the owners
+        {
+            const bool isjac = g.phase == GP_JAC;
+            if (isjac) g.jac_prep(ws);
+            __syncwarp();
+            const unsigned jm = __ballot_sync(0xffffffffu, isjac);
+            PFX_PROF_T0(pj0);
+            if (jm) GaussLaneT<1>::hybrid_jac_rows(jm, g.nrows, b, ws);
+            PFX_PROF_ADD(PROF_JAC_ROWS, pj0);
+            if (isjac) g.jac_close(ws);
+        }
+        // trial point
+        {
+            const bool istr = g.phase == GP_TRIAL;
+            if (istr) g.trial_prep(ws);
+            __syncwarp();
+            const unsigned tm = __ballot_sync(0xffffffffu, istr);
+            PFX_PROF_T0(pt0);
+            if (tm) GaussLaneT<1>::hybrid_trial_rows(tm, g.nrows, b, ws);
+            PFX_PROF_ADD(PROF_TRIAL_ROWS, pt0);
+            if (istr) g.trial_close(ws);
+        }
     }
     __syncwarp();
     PFX_PROF_ADD(PROF_TOTAL, pk0);
@@ -271,27 +403,56 @@ struct GaussPlan {
     int threads[2], grid[2];
     size_t smem[2];
     bool in_smem[2];
+    int per_block[2];      // candidates resident per block
+    int pitch;             // hybrid rounds kernel: elements between the data vectors of two candidates
 };
 }  // namespace
+
+// hybrid rounds kernel: slots (candidates) per block, threads = 32 lanes per HY_K slots
+static bool hybrid_layout(pfx_ctx* ctx, int m, int* threads, size_t* smem, int* slots_out, int* pitch) {
+    *pitch = align_up(m, 8) + 8;
+    const size_t ws = (size_t)lane_ws_doubles(4) * 8;
+    const size_t per_slot = ws + (size_t)*pitch * 10;
+    const size_t budget = (size_t)ctx->smem_optin;
+    for (int slots = HY_MAX_SLOTS; slots >= 2 * HY_K; slots -= HY_K) {
+        if (per_slot * slots + 64 <= budget) {
+            *threads = slots / HY_K * 32;
+            *slots_out = slots;
+            *smem = (per_slot * slots + 64 + 15) / 16 * 16;
+            return true;
+        }
+    }
+    *threads = HY_MAXT;
+    *slots_out = HY_MAX_SLOTS;
+    *smem = ws * HY_MAX_SLOTS;
+    return false;
+}
 
 // launch geometry of the two kernels for n candidates of m bins, and the scratch they need
 static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, GaussPlan* p) {
     int rc = ensure_buf(ctx, &set->carry, (size_t)n * sizeof(GaussCarry));
     if (rc) return rc;
-    p->in_smem[0] = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, 10, &p->threads[0], &p->smem[0]);
-    rc = persistent_grid(ctx, k_gauss_rounds, p->threads[0], p->smem[0], &p->grid[0]);
+    p->pitch = m;
+    if (ctx->gauss_hybrid) {
+        p->in_smem[0] = hybrid_layout(ctx, m, &p->threads[0], &p->smem[0], &p->per_block[0], &p->pitch);
+        rc = persistent_grid(ctx, k_gauss_rounds_h, p->threads[0], p->smem[0], &p->grid[0]);
+    } else {
+        p->in_smem[0] = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, 10, &p->threads[0], &p->smem[0]);
+        p->per_block[0] = p->threads[0] / ROUNDS_LANES;
+        rc = persistent_grid(ctx, k_gauss_rounds, p->threads[0], p->smem[0], &p->grid[0]);
+    }
     if (rc) return rc;
     p->in_smem[1] = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, 8, &p->threads[1], &p->smem[1]);
+    p->per_block[1] = p->threads[1] / FINAL_LANES;
     rc = persistent_grid(ctx, k_gauss_final, p->threads[1], p->smem[1], &p->grid[1]);
     if (rc) return rc;
-    const int lanes[2] = {ROUNDS_LANES, FINAL_LANES};
     for (int k = 0; k < 2; ++k) {
-        const int per_block = p->threads[k] / lanes[k];
+        const int per_block = p->per_block[k];
         if ((long long)p->grid[k] * per_block > n) p->grid[k] = (int)((n + per_block - 1) / per_block);
         if (!p->in_smem[k]) {
             double* gdat;
             unsigned short* gxs;
-            rc = lane_scratch(ctx, &set->lane[k], (size_t)p->grid[k] * per_block, m, &gdat, &gxs);
+            rc = lane_scratch(ctx, &set->lane[k], (size_t)p->grid[k] * per_block, k == 0 ? p->pitch : m, &gdat, &gxs);
             if (rc) return rc;
         }
     }
@@ -314,11 +475,15 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     double* gdat = nullptr;
     unsigned short* gxs = nullptr;
     if (!p.in_smem[0]) {
-        rc = lane_scratch(ctx, &set->lane[0], (size_t)p.grid[0] * (p.threads[0] / ROUNDS_LANES), m, &gdat, &gxs);
+        rc = lane_scratch(ctx, &set->lane[0], (size_t)p.grid[0] * p.per_block[0], p.pitch, &gdat, &gxs);
         if (rc) return rc;
     }
-    k_gauss_rounds<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
-                                                                take_counter(set, ck, st), carry, gdat, gxs);
+    if (ctx->gauss_hybrid)
+        k_gauss_rounds_h<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
+                                                                      take_counter(set, ck, st), carry, gdat, gxs, p.pitch);
+    else
+        k_gauss_rounds<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
+                                                                    take_counter(set, ck, st), carry, gdat, gxs);
     PFX_CUDA(ctx, cudaGetLastError());
     gdat = nullptr;
     gxs = nullptr;

@@ -42,6 +42,9 @@ enum { PROF_SETUP = 0, PROF_JAC_ROWS = 1, PROF_JAC_END = 2, PROF_LMPAR = 3, PROF
        PROF_FINISH = 6, PROF_QUEUE = 7, PROF_TOTAL = 8, PROF_TAIL = 9,
        PROF8_START = 10, PROF8_JAC_ROWS = 11, PROF8_JAC_END = 12, PROF8_TRIAL = 13, PROF8_FINISH = 14, PROF8_TOTAL = 15 };
 
+#ifndef PFX_HYBRID
+#define PFX_HYBRID 0    // host build: 1 = follow the hybrid kernel's arithmetic, 0 = the lane kernel's (the default kernel)
+#endif
 #ifndef PFX_COOP
 #define PFX_COOP 1      // 0: every lane sets up and closes its own fits (round-1 behaviour, for comparison)
 #endif
@@ -52,6 +55,8 @@ struct LaneBuf {
     double* dat;           // element i of this lane at dat[i * stride]
     unsigned short* xs;    // element i of this lane at xs[i * stride]
     int stride;
+    int pitch = 1;         // distance between the vectors of neighbouring lanes (1: lane index fastest;
+                           // m + pad with stride 1: one contiguous vector per candidate, hybrid kernel)
     PFX_HD double& d(int i) const { return dat[(size_t)i * stride]; }
     PFX_HD unsigned short& x(int i) const { return xs[(size_t)i * stride]; }
 };
@@ -132,6 +137,138 @@ struct G4Jac {
         a3 = (PFX_SUB(yv, PFX_ADD(base, bgh)) - f0) * ih3;
     }
 };
+
+// ---- hybrid rows: EIGHT LANES PER CANDIDATE for the passes over the data, ONE for the n x n work ----
+// The row loops of a fit (Jacobian pass, trial point) are the part of a trip that is proportional to
+// the number of bins, the n x n work (pivoting, lmpar, the convergence tests) is not.  Run by the
+// candidate's own lane, the row loops cost a warp the same whether 32 or 3 of its candidates need
+// them -- the lanes whose fit is retrying a step, is being set up or has run out of candidates idle
+// through them (20 of 32 lanes active on average, profiles/r02_phase_profile_coop.txt; the tail of
+// slow candidates is 28 % of a warp's life).  In the hybrid kernel the warp instead serves the
+// candidates that need a pass four at a time with eight lanes each: lane s of a group takes the rows
+// s, s + 8, s + 16, ... in blocks of four, eliminates them against its own triangular factor in
+// registers, and the eight factors are merged by a butterfly (both partners stack the lower lane's
+// factor on the upper lane's, so they end with the same bits); the group leader hands R, Q^T f, the
+// column norms and |f|^2 to the owner through its n x n workspace.  The cost of a pass is now
+// proportional to the candidates that need it, every lane of the warp works in it, and four rows
+// (twelve exponentials) are in flight per lane.  The arithmetic (which rows meet in which factor,
+// the merge tree) depends only on the number of rows, never on scheduling; the host build walks the
+// eight lanes of a group in turn.
+struct RowFactor4 {
+    double R[10], q[4], acn2[4], f2;      // packed upper triangle (row i at i*4 - i(i-1)/2), Q^T f, sums
+    PFX_HD static constexpr int ridx(int i, int j) { return i * 4 - (i * (i - 1)) / 2 + (j - i); }
+    PFX_HD void zero() {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) R[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            q[k] = 0.0;
+            acn2[k] = 0.0;
+        }
+        f2 = 0.0;
+    }
+    // Householder elimination of four rows (A[r][0..3] | A[r][4] = f) against the factor; with TRI the
+    // block is itself upper triangular (row r empty left of column r: the factor of a partner lane).
+    // Same formulas as LaneLM::jac_block (reciprocal square root and reciprocal; columns whose norm
+    // leaves the normal range are dropped).
+    template <bool TRI>
+    PFX_HD void eliminate(double (&A)[4][5]) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double ss = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (!TRI || r <= j) ss = PFX_FMA(A[r][j], A[r][j], ss);
+            const double rjj = R[ridx(j, j)];
+            const double t2 = PFX_FMA(rjj, rjj, ss);
+            if (ss != 0.0 && !(t2 <= 1e-290)) {
+                const double inv = fast_rsqrt(t2);
+                const double nrm = t2 * inv;
+                const double alpha = (rjj > 0.0) ? -nrm : nrm;
+                const double v0 = rjj - alpha;
+                const double beta = inv * fast_rcp(fabs(v0));
+                R[ridx(j, j)] = alpha;
+#pragma unroll
+                for (int k = j + 1; k <= 4; ++k) {
+                    double d = v0 * ((k < 4) ? R[ridx(j, k < 4 ? k : j)] : q[j]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (!TRI || r <= j) d = PFX_FMA(A[r][j], A[r][k], d);
+                    const double t = beta * d;
+                    if (k < 4) R[ridx(j, k < 4 ? k : j)] = PFX_FMA(-t, v0, R[ridx(j, k < 4 ? k : j)]);
+                    else q[j] = PFX_FMA(-t, v0, q[j]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (!TRI || r <= j) A[r][k] = PFX_FMA(-t, A[r][j], A[r][k]);
+                }
+            }
+        }
+    }
+    // The same elimination with the block staged in the lane's workspace (row r, column k at
+    // blk[r * 5 + k], column 4 = f; rows beyond `rows` count as zeros): the rows are produced by a compact
+    // rolled loop -- unrolling four rows with their twelve exponentials made the row pass four times the
+    // size of the instruction cache (ncu: instruction fetch 57 % of the stalls there).
+    PFX_HD void eliminate_staged(const SPtr<double>& blk, int rows) {
+        double c0[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double ss = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                c0[r] = (r < rows) ? blk[r * 5 + j] : 0.0;
+                ss = PFX_FMA(c0[r], c0[r], ss);
+            }
+            const double rjj = R[ridx(j, j)];
+            const double t2 = PFX_FMA(rjj, rjj, ss);
+            if (ss != 0.0 && !(t2 <= 1e-290)) {
+                const double inv = fast_rsqrt(t2);
+                const double nrm = t2 * inv;
+                const double alpha = (rjj > 0.0) ? -nrm : nrm;
+                const double v0 = rjj - alpha;
+                const double beta = inv * fast_rcp(fabs(v0));
+                R[ridx(j, j)] = alpha;
+#pragma unroll
+                for (int k = j + 1; k <= 4; ++k) {
+                    double ck[4];
+                    double d = v0 * ((k < 4) ? R[ridx(j, k < 4 ? k : j)] : q[j]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        ck[r] = (r < rows) ? blk[r * 5 + k] : 0.0;
+                        d = PFX_FMA(c0[r], ck[r], d);
+                    }
+                    const double t = beta * d;
+                    if (k < 4) R[ridx(j, k < 4 ? k : j)] = PFX_FMA(-t, v0, R[ridx(j, k < 4 ? k : j)]);
+                    else q[j] = PFX_FMA(-t, v0, q[j]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (r < rows) blk[r * 5 + k] = PFX_FMA(-t, c0[r], ck[r]);
+                }
+            }
+        }
+    }
+    // this := factor of (rows of this stacked on the rows of up); the sums add (commutative: both
+    // partners of an exchange get the same bits)
+    PFX_HD void absorb(const RowFactor4& up) {
+        double A[4][5];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) A[r][k] = (k >= r) ? up.R[ridx(r < k ? r : k, k)] : 0.0;
+            A[r][4] = up.q[r];
+        }
+        eliminate<true>(A);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acn2[k] = PFX_ADD(acn2[k], up.acn2[k]);
+        f2 = PFX_ADD(f2, up.f2);
+    }
+};
+constexpr int HY_GROUP = 8;                 // lanes per candidate in the row passes
+// Slots of the owner's n x n workspace used for the hand-over (LaneWs::blk[k]).  Slots 24 .. 43 of every
+// lane are its staging block during Jacobian passes (LaneWs::stg).  A lane that owns a Jacobian pass has
+// a dead workspace (its factor is rebuilt by jac_close): constants in 0 .. 11, the result over them in
+// 0 .. 18 once the group is done with the constants.  Around a trial point r and qtf (0 .. 23) are live:
+// constants and result go to the staging area, which is idle during trial passes.
+enum { HY_JC = 0, HY_JR = 0, HY_TC = 24, HY_TS = 28 };
 
 // ---- warp-cooperative helpers --------------------------------------------------------------
 // The set-up and the close of a fit (copying / rebuilding the data vector, its statistics, the
@@ -594,6 +731,219 @@ struct GaussLaneT {
         PFX_PROF_ADD(PROF_TRIAL_END, pt2);
     }
 
+    // ---- hybrid rows (see RowFactor4): lane-mode halves of a pass -------------------------------
+    PFX_HD void jac_prep(const LaneWs& ws) {
+        lm.jac_begin();
+        G4Jac J;
+        J.set(lm.x, lm.h, fl);
+        const double c[12] = {J.isg, J.isgh, J.mu, J.muh, J.amx, J.amxh, J.bg, J.bgh, J.ih0, J.ih1, J.ih2, J.ih3};
+#pragma unroll
+        for (int k = 0; k < 12; ++k) ws.blk[HY_JC + k] = c[k];
+    }
+    PFX_HD void jac_close(const LaneWs& ws) {
+        PFX_PROF_T0(pt1);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) lm.R[k] = ws.blk[HY_JR + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lm.q[k] = ws.blk[HY_JR + 10 + k];
+            lm.acn2[k] = ws.blk[HY_JR + 14 + k];
+        }
+        lm.f2 = ws.blk[HY_JR + 18];
+        const int r = lm.jac_end(ws, nrows);
+        phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+        PFX_PROF_ADD(PROF_JAC_END, pt1);
+    }
+    PFX_HD void trial_prep(const LaneWs& ws) {
+        PFX_PROF_T0(pt0);
+        lm.trial_begin(ws);
+        G4Eval ev;
+        ev.set(lm.xnew, fl);
+        ws.blk[HY_TC + 0] = ev.mu;
+        ws.blk[HY_TC + 1] = ev.inv;
+        ws.blk[HY_TC + 2] = ev.amx;
+        ws.blk[HY_TC + 3] = ev.bg;
+        PFX_PROF_ADD(PROF_LMPAR, pt0);
+    }
+    PFX_HD void trial_close(const LaneWs& ws) {
+        PFX_PROF_T0(pt2);
+        const int r = lm.trial_end(sqrt(ws.blk[HY_TS]));
+        phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+        PFX_PROF_ADD(PROF_TRIAL_END, pt2);
+    }
+    // the rows of lane s of a group: s, s + 8, s + 16, ... in blocks of four
+    PFX_HD static void rows_factor(const LaneBuf& bs, int nr, int s, const G4Jac& J, RowFactor4& F,
+                                   const SPtr<double>& stg) {
+        F.zero();
+#pragma unroll 1
+        for (int i0 = s; i0 < nr; i0 += 4 * HY_GROUP) {
+            int rows = 0;
+#pragma unroll 1
+            for (int i = i0; i < nr && rows < 4; i += HY_GROUP, ++rows) {
+                double a0, a1, a2, a3, f0;
+                J.row((double)bs.x(i), bs.d(i), a0, a1, a2, a3, f0);
+                F.acn2[0] = PFX_FMA(a0, a0, F.acn2[0]);
+                F.acn2[1] = PFX_FMA(a1, a1, F.acn2[1]);
+                F.acn2[2] = PFX_FMA(a2, a2, F.acn2[2]);
+                F.acn2[3] = PFX_FMA(a3, a3, F.acn2[3]);
+                F.f2 = PFX_FMA(f0, f0, F.f2);
+                stg[rows * 5 + 0] = a0;
+                stg[rows * 5 + 1] = a1;
+                stg[rows * 5 + 2] = a2;
+                stg[rows * 5 + 3] = a3;
+                stg[rows * 5 + 4] = f0;
+            }
+            F.eliminate_staged(stg, rows);
+        }
+    }
+    PFX_HD static double rows_trial(const LaneBuf& bs, int nr, int s, const G4Eval& ev) {
+        double acc = 0.0;
+#pragma unroll 4
+        for (int i = s; i < nr; i += HY_GROUP) {
+            const double f = PFX_SUB(bs.d(i), ev.value((double)bs.x(i)));
+            acc = PFX_FMA(f, f, acc);
+        }
+        return acc;
+    }
+    PFX_HD static void load_jac_consts(const double* w, int st, G4Jac& J) {
+        J.isg = w[(HY_JC + 0) * st];
+        J.isgh = w[(HY_JC + 1) * st];
+        J.mu = w[(HY_JC + 2) * st];
+        J.muh = w[(HY_JC + 3) * st];
+        J.amx = w[(HY_JC + 4) * st];
+        J.amxh = w[(HY_JC + 5) * st];
+        J.bg = w[(HY_JC + 6) * st];
+        J.bgh = w[(HY_JC + 7) * st];
+        J.ih0 = w[(HY_JC + 8) * st];
+        J.ih1 = w[(HY_JC + 9) * st];
+        J.ih2 = w[(HY_JC + 10) * st];
+        J.ih3 = w[(HY_JC + 11) * st];
+    }
+    PFX_HD static void store_factor(double* w, int st, const RowFactor4& F) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) w[(HY_JR + k) * st] = F.R[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w[(HY_JR + 10 + k) * st] = F.q[k];
+            w[(HY_JR + 14 + k) * st] = F.acn2[k];
+        }
+        w[(HY_JR + 18) * st] = F.f2;
+    }
+#if defined(__CUDACC__)
+    // Called by all 32 lanes.  mask = the owners (lanes of this warp) whose fit needs a Jacobian pass and
+    // have run jac_prep; my_nrows = the caller's own row count.  Four candidates per turn, eight lanes each.
+    __device__ static void hybrid_jac_rows(unsigned mask, int my_nrows, const LaneBuf& b, const LaneWs& ws) {
+        const int lane = (int)(threadIdx.x & 31), g = lane >> 3, s = lane & (HY_GROUP - 1);
+        const unsigned gmask = 0xffu << (8 * g);
+        while (mask) {
+            const unsigned pos = __fns(mask, 0, g + 1);          // lane of the g-th candidate of this turn
+            const int src = (pos < 32u) ? (int)pos : -1;
+            const int nr = __shfl_sync(0xffffffffu, my_nrows, src < 0 ? 0 : src);
+#pragma unroll
+            for (int t = 0; t < 32 / HY_GROUP; ++t) mask &= mask - 1;
+            if (src >= 0) {
+                const LaneBuf bs = buf_of(b, src);
+                double* w = ws.blk.p + (src - lane);
+                const int st = ws.blk.stride;
+                RowFactor4 F;
+                {
+                    G4Jac J;
+                    load_jac_consts(w, st, J);
+                    rows_factor(bs, nr, s, J, F, ws.stg);
+                }
+#pragma unroll 1
+                for (int sh = 1; sh < HY_GROUP; sh <<= 1) {
+                    const bool upper = (s & sh) != 0;
+                    RowFactor4 lo, up;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+                        const double o = __shfl_xor_sync(gmask, F.R[k], sh);
+                        lo.R[k] = upper ? o : F.R[k];
+                        up.R[k] = upper ? F.R[k] : o;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double o = __shfl_xor_sync(gmask, F.q[k], sh);
+                        lo.q[k] = upper ? o : F.q[k];
+                        up.q[k] = upper ? F.q[k] : o;
+                        const double oa = __shfl_xor_sync(gmask, F.acn2[k], sh);
+                        lo.acn2[k] = upper ? oa : F.acn2[k];
+                        up.acn2[k] = upper ? F.acn2[k] : oa;
+                    }
+                    {
+                        const double o = __shfl_xor_sync(gmask, F.f2, sh);
+                        lo.f2 = upper ? o : F.f2;
+                        up.f2 = upper ? F.f2 : o;
+                    }
+                    lo.absorb(up);
+                    F = lo;
+                }
+                if (s == 0) store_factor(w, st, F);
+            }
+            __syncwarp();
+        }
+    }
+    __device__ static void hybrid_trial_rows(unsigned mask, int my_nrows, const LaneBuf& b, const LaneWs& ws) {
+        const int lane = (int)(threadIdx.x & 31), g = lane >> 3, s = lane & (HY_GROUP - 1);
+        const unsigned gmask = 0xffu << (8 * g);
+        while (mask) {
+            const unsigned pos = __fns(mask, 0, g + 1);
+            const int src = (pos < 32u) ? (int)pos : -1;
+            const int nr = __shfl_sync(0xffffffffu, my_nrows, src < 0 ? 0 : src);
+#pragma unroll
+            for (int t = 0; t < 32 / HY_GROUP; ++t) mask &= mask - 1;
+            if (src >= 0) {
+                const LaneBuf bs = buf_of(b, src);
+                double* w = ws.blk.p + (src - lane);
+                const int st = ws.blk.stride;
+                G4Eval ev;
+                ev.mu = w[(HY_TC + 0) * st];
+                ev.inv = w[(HY_TC + 1) * st];
+                ev.amx = w[(HY_TC + 2) * st];
+                ev.bg = w[(HY_TC + 3) * st];
+                double acc = rows_trial(bs, nr, s, ev);
+#pragma unroll
+                for (int sh = 1; sh < HY_GROUP; sh <<= 1) acc = PFX_ADD(acc, __shfl_xor_sync(gmask, acc, sh));
+                if (s == 0) w[HY_TS * st] = acc;
+            }
+            __syncwarp();
+        }
+    }
+#endif
+#if !defined(__CUDA_ARCH__)
+    // host build: one lane walks the eight lanes of its group in turn (same rows, same merge tree)
+    PFX_HD void host_group_jac(const LaneBuf& b, const LaneWs& ws) {
+        RowFactor4 F[HY_GROUP];
+        G4Jac J;
+        load_jac_consts(ws.blk.p, ws.blk.stride, J);
+        for (int s = 0; s < HY_GROUP; ++s) rows_factor(b, nrows, s, J, F[s], ws.stg);
+        for (int sh = 1; sh < HY_GROUP; sh <<= 1)
+            for (int s = 0; s < HY_GROUP; ++s)
+                if (!(s & sh)) {
+                    RowFactor4 lo = F[s];
+                    lo.absorb(F[s | sh]);
+                    F[s] = lo;
+                    F[s | sh] = lo;
+                }
+        store_factor(ws.blk.p, ws.blk.stride, F[0]);
+    }
+    PFX_HD void host_group_trial(const LaneBuf& b, const LaneWs& ws) {
+        G4Eval ev;
+        ev.mu = ws.blk[HY_TC + 0];
+        ev.inv = ws.blk[HY_TC + 1];
+        ev.amx = ws.blk[HY_TC + 2];
+        ev.bg = ws.blk[HY_TC + 3];
+        double p[HY_GROUP];
+        for (int s = 0; s < HY_GROUP; ++s) p[s] = rows_trial(b, nrows, s, ev);
+        for (int sh = 1; sh < HY_GROUP; sh <<= 1) {
+            double t[HY_GROUP];
+            for (int s = 0; s < HY_GROUP; ++s) t[s] = PFX_ADD(p[s], p[s ^ sh]);
+            for (int s = 0; s < HY_GROUP; ++s) p[s] = t[s];
+        }
+        ws.blk[HY_TS] = p[0];
+    }
+#endif
+
     PFX_HD void finish(const LaneBuf& b) {
         double p[4] = {lm.x[0], lm.x[1], lm.x[2], lm.x[3]};
         ier[stage] = (int8_t)lm.info;
@@ -650,7 +1000,7 @@ struct GaussLaneT {
     // passes over its bins are dealt to the 32 lanes, and lane src alone commits the results.
     PFX_HD static LaneBuf buf_of(const LaneBuf& b, int src) {
         LaneBuf o = b;
-        const int d = src - WarpCoop::lane();
+        const int d = (src - WarpCoop::lane()) * b.pitch;
         o.dat = b.dat + d;
         o.xs = b.xs + d;
         return o;
@@ -922,6 +1272,24 @@ struct GaussLaneT {
     // phases of the warp cooperatively before it calls step(); the host build (one lane) serves
     // itself here.
     PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {
+#if !defined(__CUDA_ARCH__)
+        if (C == 1 && PFX_HYBRID) {
+            // host build of the hybrid kernel's trip (the device kernel drives these pieces itself)
+            if (phase == GP_SETUP) coop_setup(0, b, ws);
+            if (phase == GP_JAC) {
+                jac_prep(ws);
+                host_group_jac(b, ws);
+                jac_close(ws);
+            }
+            if (phase == GP_TRIAL) {
+                trial_prep(ws);
+                host_group_trial(b, ws);
+                trial_close(ws);
+            }
+            if (phase == GP_FIN) coop_finish(0, b);
+            return;
+        }
+#endif
         if (C == 1 && PFX_COOP) {
 #if !defined(__CUDA_ARCH__)
             if (phase == GP_SETUP) coop_setup(0, b, ws);

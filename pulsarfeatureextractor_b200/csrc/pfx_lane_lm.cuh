@@ -441,7 +441,7 @@ PFX_HD inline int lane_ws_doubles(int n) {
     return a > b ? a : b;
 }
 struct LaneWs {
-    SPtr<double> r, diag, qtf, step, sdiag, wa1, wa2, blk;
+    SPtr<double> r, diag, qtf, step, sdiag, wa1, wa2, blk, stg;
     SPtr<int> ipvt;
     // base points at this lane's first element; consecutive elements are `stride` doubles apart
     PFX_HD void carve(double* base, int stride, int n) {
@@ -457,6 +457,10 @@ struct LaneWs {
         ipvt.p = (int*)(base + (size_t)(n * n + 6 * n) * stride);
         ipvt.stride = 2 * stride;
         blk = at(0);      // aliases r .. ipvt (see lane_ws_doubles)
+        // hybrid Gaussian kernel (n = 4): a 4-row staging block in step .. ipvt (20 slots), which the
+        // register-resident n x n solve leaves free, so a lane whose own fit is between a Jacobian pass
+        // and its trial points (r and qtf live) can serve the row passes of other candidates
+        stg = at(n * n + 2 * n);
     }
 };
 
@@ -466,6 +470,7 @@ struct LaneLM {
     double x[N], diag[N];
     double par, delta, xnorm, fnorm, gnorm;
     int iter, nfev, info;
+    int ipv;             // pivot order of the last factorisation, one byte per column (N <= 4)
     // Jacobian pass accumulators
     double h[N];
     double R[N * (N + 1) / 2];   // packed upper triangle, row i starts at i*N - i*(i-1)/2
@@ -697,6 +702,11 @@ struct LaneLM {
             for (int i = 0; i < N; ++i) s.r[i + N * j] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
         (void)m;
         qrfac_small(N, N, s.r, s.ipvt, rdiag, wa);
+        if (N <= 4) {
+            ipv = 0;
+#pragma unroll
+            for (int j = 0; j < (N <= 4 ? N : 0); ++j) ipv |= s.ipvt[j] << (8 * j);
+        }
         if (iter == 1) {
             double sq = 0.0;
 #pragma unroll
@@ -761,7 +771,7 @@ struct LaneLM {
             for (int j = 0; j < N; ++j) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) q.r[i][j] = (i <= j) ? s.r[i + N * j] : 0.0;
-                q.ipvt[j] = s.ipvt[j];
+                q.ipvt[j] = (ipv >> (8 * j)) & 0xff;
                 q.diag[j] = diag[j];
                 q.qtb[j] = s.qtf[j];
             }

@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/../pulsarfeatureextractor_b200/csrc"
 make -j8 >/dev/null
 FL="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC"
-ALL="pfx_api pfx_k_sinusoid pfx_k_hist pfx_k_gauss pfx_k_dmfit pfx_k_subband pfx_k_lyon"
+ALL="pfx_api pfx_k_sinusoid pfx_k_hist pfx_k_gauss pfx_k_dmfit pfx_k_dmfit_exact pfx_k_subband pfx_k_lyon"
 for v in "$@"; do
   set -- $v
   U=$1; TAG=$2; shift; shift
