@@ -64,6 +64,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     ctx->subbatch = 0;
     ctx->dm_exact = 1;
     ctx->gauss_hybrid = 0;
+    ctx->hist_u8 = 1;
+    if (const char* e = getenv("PFX_HIST_U8")) ctx->hist_u8 = atoi(e) != 0;
     if (const char* e = getenv("PFX_HYBRID")) ctx->gauss_hybrid = atoi(e) != 0;
     if (const char* e = getenv("PFX_DM_EXACT")) ctx->dm_exact = atoi(e) != 0;
     if (const char* e = getenv("PFX_SUBBATCH")) ctx->subbatch = atoi(e);

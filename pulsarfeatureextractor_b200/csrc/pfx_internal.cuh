@@ -63,6 +63,7 @@ struct pfx_ctx {
     int set_rr;
     pfx_grid_cache_entry grid_cache[32];
     int n_grid_cache;
+    int hist_u8;              // 1: warp-cooperative histogram set-up for uint8 profiles of <= 128 bins (default)
     int gauss_hybrid;         // 1: hybrid rounds kernel (eight lanes per candidate in the row passes), 0: lane kernel
     int dm_exact;             // 1: DM-curve fit in MINPACK's own summation order (bit-exact form), 0: lane form
     int subbatch;             // sub-batches of the histogram/Gaussian chain per pfx_score_dev call

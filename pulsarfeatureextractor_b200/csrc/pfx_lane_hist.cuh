@@ -28,9 +28,37 @@ struct HistLaneBuf {
         hx = at(2 * m + next_pow2(m));
         hy = at(2 * m + next_pow2(m) + HIST_LANE_CAP);
     }
+    PFX_HD void pad(int i) const {      // PO:943-947 zero padding to three points
+        hx[i] = 0.0;
+        hy[i] = 0.0;
+    }
 };
 
-struct HistLane {
+// The histogram of a uint8 profile of at most 255 bins as k_hist_lane_u8 keeps it: the counts are
+// bytes in shared memory (a count never exceeds the number of bins of the profile) and the left
+// edges are not stored at all -- numpy's edge i is i * step + first, two operations.  Reads only; the
+// kernel builds the table with the whole warp (pfx_k_hist.cu).  Element i of the table of a lane is
+// stored at (i + rot) & 255 with rot = 4 * lane, which spreads the 32 lanes of a warp over the 32
+// banks when every lane reads its own bin i, and keeps the bins of one lane consecutive when the
+// warp fills one table together.
+struct HistEdgeView {
+    double first, step;
+    int nb;
+    PFX_HD double operator[](int i) const { return (i < nb) ? PFX_ADD(PFX_MUL((double)i, step), first) : 0.0; }
+};
+struct HistCountView {
+    const unsigned char* p;
+    int rot, nb;
+    PFX_HD double operator[](int i) const { return (i < nb) ? (double)p[(i + rot) & 255] : 0.0; }
+};
+struct HistBufU8 {
+    HistEdgeView hx;
+    HistCountView hy;
+    PFX_HD void pad(int) const {}       // entries beyond the histogram read as zeros
+};
+
+template <class BUF>
+struct HistLaneT {
     long long cand;
     int m, phase, stage;
     bool int_data;
@@ -133,7 +161,7 @@ struct HistLane {
     }
 
     // set up the fit of the histogram currently in hx/hy (PO:829-857, 943-947)
-    PFX_HD void begin_hist_fit(const HistLaneBuf& b, int nbins) {
+    PFX_HD void begin_hist_fit(const BUF& b, int nbins) {
         nb = nbins;
         int am = 0;
         double vmax = b.hy[0], bmax = b.hy[0], s = 0.0;
@@ -161,15 +189,19 @@ struct HistLane {
         expect = b.hx[am];
         nfit = nbins;
         for (int i = nbins; i < 3; ++i) {
-            b.hx[i] = 0.0;
-            b.hy[i] = 0.0;
+            b.pad(i);
             nfit = 3;
         }
         counter = 0;
         nfits = 0;
     }
 
-    PFX_HD void setup(const HistLaneBuf& b, const void* profile, int dtype) {
+    // histogram currently described by the lane (k_hist_lane_u8 builds its views from these)
+    double h_first, h_step;
+    int h_nb;
+
+    // heavy part of a set-up: order statistics, bin counts, the histogram (stages 0 and 1)
+    PFX_HD void setup_data(const BUF& b, const void* profile, int dtype) {
         if (stage == 0) {
             for (int i = 0; i < m; ++i) b.y[i] = load_elem(profile, dtype, cand * (long long)m + i);
             for (int i = 0; i < m - 1; ++i) b.dy[i] = b.y[i] - b.y[i + 1];
@@ -188,11 +220,18 @@ struct HistLane {
             nbp = (int)np_;
             nbd = (int)nd_;
             histogram(b.dy, m - 1, nbd, dmin, dmax, b.hx, b.hy);
-            begin_hist_fit(b, nbd);
         } else if (stage == 1) {
             histogram(b.y, m, nbp, pmin, pmax, b.hx, b.hy);
-            begin_hist_fit(b, nbp);
         }
+    }
+    PFX_HD void setup(const BUF& b, const void* profile, int dtype) {
+        setup_data(b, profile, dtype);
+        if (phase == GP_SETUP) setup_fit(b);
+    }
+    // the rest: statistics of the counts, starting values
+    PFX_HD void setup_fit(const BUF& b) {
+        if (stage == 0) begin_hist_fit(b, nbd);
+        else if (stage == 1) begin_hist_fit(b, nbp);
         if (stage <= 1) {
             double x0[3] = {sigma0, expect, max0};
             lm3.init(x0);
@@ -223,7 +262,7 @@ struct HistLane {
         phase = GP_JAC;
     }
 
-    PFX_HD void jac_pass(const HistLaneBuf& b, const LaneWs& ws) {
+    PFX_HD void jac_pass(const BUF& b, const LaneWs& ws) {
         constexpr int B = LANE_BLOCK_ROWS;
         if (stage <= 1) {
             lm3.jac_begin();
@@ -285,7 +324,7 @@ struct HistLane {
         }
     }
 
-    PFX_HD void trial_pass(const HistLaneBuf& b, const LaneWs& ws) {
+    PFX_HD void trial_pass(const BUF& b, const LaneWs& ws) {
         int r;
         if (stage <= 1) {
             lm3.trial_begin(ws);
@@ -309,7 +348,7 @@ struct HistLane {
         phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
     }
 
-    PFX_HD void finish(const HistLaneBuf& b) {
+    PFX_HD void finish(const BUF& b) {
         if (stage <= 1) {
             // PO:957-978: chi-square over the original bins, retry test, moved start position
             ++nfits;
@@ -378,7 +417,7 @@ struct HistLane {
         }
     }
 
-    PFX_HD void step(const HistLaneBuf& b, const LaneWs& ws, const void* profile, int dtype) {
+    PFX_HD void step(const BUF& b, const LaneWs& ws, const void* profile, int dtype) {
         if (phase == GP_SETUP) setup(b, profile, dtype);
         if (phase == GP_JAC) jac_pass(b, ws);
         if (phase == GP_TRIAL) trial_pass(b, ws);
@@ -394,5 +433,7 @@ struct HistLane {
     }
     PFX_HD bool complete() const { return stage == 3 && !(status & PFX_ST_FAIL_MASK) && !overflow; }
 };
+
+typedef HistLaneT<HistLaneBuf> HistLane;
 
 }  // namespace pfx
