@@ -64,6 +64,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     ctx->subbatch = 0;
     ctx->dm_exact = 1;
     ctx->gauss_hybrid = 0;
+    ctx->gauss_wave = 0;
+    if (const char* e = getenv("PFX_WAVE")) ctx->gauss_wave = atoi(e) != 0;
     ctx->hist_u8 = 1;
     if (const char* e = getenv("PFX_HIST_U8")) ctx->hist_u8 = atoi(e) != 0;
     if (const char* e = getenv("PFX_HYBRID")) ctx->gauss_hybrid = atoi(e) != 0;
@@ -80,7 +82,7 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     cudaFree(ctx->counters);
     for (int i = 0; i < N_SETS; ++i) {
         pfx_scratch_set& t = ctx->sets[i];
-        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp};
+        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp, &t.wave_state, &t.wave_ws, &t.wave_list};
         for (pfx_buf* b : bufs)
             if (b->p) cudaFree(b->p);
         cudaEventDestroy(t.done);

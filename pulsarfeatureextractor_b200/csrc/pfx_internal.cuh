@@ -40,6 +40,7 @@ struct pfx_scratch_set {
     pfx::u64* counters;       // COUNTERS_PER_SET
     pfx_buf carry;            // per-candidate records passed between the two Gaussian kernels
     pfx_buf lane[2];          // per-lane data vectors of the Gaussian lane kernels (long profiles)
+    pfx_buf wave_state, wave_ws, wave_list;   // wave form of the rounds kernel: fit state, n x n workspaces, active lists
     pfx_buf hist_lane;        // per-lane arrays of k_hist_lane
     pfx_buf ovf;              // candidates whose histogram overflowed the per-lane capacity
     pfx_buf hist_warp;        // global histogram slots of the warp-form kernel
@@ -64,6 +65,7 @@ struct pfx_ctx {
     pfx_grid_cache_entry grid_cache[32];
     int n_grid_cache;
     int hist_u8;              // 1: warp-cooperative histogram set-up for uint8 profiles of <= 128 bins (default)
+    int gauss_wave;           // 1: wave form of the rounds kernel (state in global memory, phases per block)
     int gauss_hybrid;         // 1: hybrid rounds kernel (eight lanes per candidate in the row passes), 0: lane kernel
     int dm_exact;             // 1: DM-curve fit in MINPACK's own summation order (bit-exact form), 0: lane form
     int subbatch;             // sub-batches of the histogram/Gaussian chain per pfx_score_dev call

@@ -309,6 +309,239 @@ k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m
 #endif
 }
 
+// ---- wave form of the rounds kernel ---------------------------------------------------------------
+// The lane kernel keeps a candidate on one lane from its first fit to its last and lets the lanes of a
+// warp wander through 240 KB of code independently: ncu shows instruction fetch (29 %) and fixed-latency
+// dependencies (35 %) as its top stalls with one warp per scheduler, 12.5 of 32 lanes active per
+// instruction, and a tail of slow candidates of 28 % of a warp's life.  Here the fit state lives in
+// GLOBAL memory (fit state, n x n workspace and data vector: 2.3 KB per candidate), every candidate of
+// the call is in flight from the start, and a block (one per SM, eight warps) walks ITS share of the
+// candidates in phases separated by block barriers:
+//     rows-jac    eight lanes per candidate: Jacobian rows, TSQR (RowFactor4), all lanes busy
+//     lane A      one lane per candidate: pivoting / Q^T f (jac_end), then lmpar for every fit at a trial point
+//     rows-trial  eight lanes per candidate: the residual norm at the trial point
+//     lane B      one lane per candidate: the step decision; fits that ended are closed and the next one
+//                 set up with the whole warp (coop_finish / coop_setup); finished candidates leave the list
+// All warps of an SM run the same phase (one code region in the instruction cache), the cost of an
+// iteration is proportional to the fits that still run, and the slowest candidate -- which bounds the
+// number of iterations -- has been running since the first one: no queue, no tail of idle lanes.
+// Arithmetic = the hybrid kernel's (which rows meet in which factor depends on the row count only).
+constexpr int WV_THREADS = 256;
+constexpr int WV_GROUPS = WV_THREADS / HY_GROUP;
+
+struct WaveBufs {
+    GaussLaneT<1>* state;      // [n]
+    double* ws;                // [n][44]
+    double* dat;               // [n][pitch]
+    unsigned short* xs;        // [n][pitch]
+    int* list;                 // [grid][2][cap]
+    int pitch, cap;
+};
+
+__device__ __forceinline__ LaneWs wave_ws(const WaveBufs& wb, long long c) {
+    LaneWs ws;
+    ws.carve(wb.ws + c * lane_ws_doubles(4), 1, 4);
+    return ws;
+}
+__device__ __forceinline__ LaneBuf wave_buf(const WaveBufs& wb, long long c) {
+    LaneBuf b;
+    b.dat = wb.dat + c * wb.pitch;
+    b.xs = wb.xs + c * wb.pitch;
+    b.stride = 1;
+    b.pitch = -1;
+    return b;
+}
+
+// shared memory of the wave kernel: staging blocks of the row passes [20][threads] | n x n workspaces of
+// the lane phases [44][threads] | data vector of the candidate a group is working on [groups][pitch] float64
+// + uint16 (only when it fits: profiles up to 256 bins; longer ones are read from global memory)
+__host__ __device__ inline size_t wave_smem_bytes(int pitch, bool stage_data) {
+    size_t b = (size_t)(20 + 44) * 8 * WV_THREADS;
+    if (stage_data) b += (size_t)WV_GROUPS * pitch * 10;
+    return b;
+}
+
+__global__ void __launch_bounds__(WV_THREADS, 1)
+k_gauss_wave(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
+             int8_t* ier, int32_t* status, GaussCarry* carry, WaveBufs wb, int stage_data) {
+    extern __shared__ double smem[];
+    __shared__ int s_count, s_next[3];
+    const int tid = (int)threadIdx.x, lane = tid & 31;
+    SPtr<double> stg;
+    stg.p = smem + tid;
+    stg.stride = WV_THREADS;
+    LaneWs wss;                                       // this thread's n x n workspace in shared memory
+    wss.carve(smem + 20 * WV_THREADS + tid, WV_THREADS, 4);
+    const int gi0 = tid / HY_GROUP, gs = tid & (HY_GROUP - 1);
+    const unsigned gmask = 0xffu << (8 * ((tid & 31) >> 3));
+    double* sdat = smem + (20 + 44) * WV_THREADS + (size_t)gi0 * wb.pitch;
+    unsigned short* sxs = (unsigned short*)(smem + (20 + 44) * WV_THREADS + (size_t)WV_GROUPS * wb.pitch) + (size_t)gi0 * wb.pitch;
+    int* list[2] = {wb.list + (size_t)blockIdx.x * 2 * wb.cap, wb.list + (size_t)blockIdx.x * 2 * wb.cap + wb.cap};
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const int nws = lane_ws_doubles(4);
+    // candidates of this block: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const long long mine = (n > (long long)blockIdx.x) ? (n - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    for (long long k = tid; k < mine; k += WV_THREADS) {
+        const long long c = (long long)blockIdx.x + k * gridDim.x;
+        GaussLaneT<1> g;
+        g.phase = GP_IDLE;
+        g.finished = false;
+        g.cand = -1;
+        g.nrows = 0;
+        double* row = feat + c * ld;
+        const double ph = row[7];      // parked by k_hist
+        const int before = (int)(PFX_ST_FAIL_MASK & ~(PFX_ST_DM_NDEG_ZERO | PFX_ST_SUBBAND_NO_PAIRS | PFX_ST_SUBBAND_BAD_WIDTH));
+        if (status[c] & before) {
+            row[7] = qnan;             // the reference raised before reaching score 8
+            carry[c].skip = 1;
+        } else {
+            g.start(profile, dtype, c, m, ph);
+        }
+        wb.state[c] = g;
+        list[0][k] = (int)c;
+    }
+    if (tid == 0) {
+        s_count = 0;
+        s_next[0] = s_next[1] = s_next[2] = 0;
+    }
+    __syncthreads();
+    int cur = 0;
+    int A = (int)mine;
+    for (;;) {
+        // ---- lane B: step decision, close / set up fits, constants of the next Jacobian pass, new list ----
+        for (int base = (tid & ~31); base < A; base += WV_THREADS) {
+            const int k = base + lane;
+            const bool valid = k < A;
+            const long long c = valid ? (long long)list[cur][k] : 0;
+            GaussLaneT<1> g;
+            if (valid) g = wb.state[c];
+            else {
+                g.phase = GP_IDLE;
+                g.cand = -1;
+                g.stage = 0;
+                g.nrows = 0;
+            }
+            const LaneWs ws = wave_ws(wb, c);
+            const LaneBuf b = wave_buf(wb, c);
+            if (valid && g.phase == GP_TRIAL) g.trial_close(ws);
+            unsigned fin = __ballot_sync(0xffffffffu, valid && g.phase == GP_FIN);
+            while (fin) {
+                const int src = __ffs(fin) - 1;
+                fin &= fin - 1;
+                g.coop_finish(src, b);
+            }
+            unsigned set = __ballot_sync(0xffffffffu, valid && g.phase == GP_SETUP);
+            while (set) {
+                const int src = __ffs(set) - 1;
+                set &= set - 1;
+                g.coop_setup(src, b, wss);        // (the workspace is only the owner's bit set of the peak stripping)
+            }
+            bool keep = false;
+            if (valid) {
+                if (g.phase == GP_JAC) g.jac_prep(ws);
+                if (g.phase == GP_IDLE) {
+                    if (g.cand >= 0) flush_rounds(g, feat, ld, ier, status, carry);
+                } else {
+                    wb.state[c] = g;
+                    keep = true;
+                }
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            int pos = 0;
+            if (lane == 0 && km) pos = atomicAdd(&s_count, __popc(km));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (keep) list[cur ^ 1][pos + __popc(km & ((1u << lane) - 1u))] = (int)c;
+        }
+        __syncthreads();
+        A = s_count;
+        cur ^= 1;
+        __syncthreads();
+        if (tid == 0) {
+            s_count = 0;
+            s_next[2] = 0;
+        }
+        if (A == 0) break;
+        // ---- rows-jac: groups of eight lanes pull candidates ------------------------------------------
+        for (;;) {
+            int k = 0;
+            if (gs == 0) k = atomicAdd(&s_next[0], 1);
+            k = __shfl_sync(gmask, k, 0, HY_GROUP);
+            if (k >= A) break;
+            const long long c = (long long)list[cur][k];
+            const GaussLaneT<1>& st = wb.state[c];
+            if (st.phase != GP_JAC) continue;
+            const int nr = st.nrows;
+            LaneBuf bs = wave_buf(wb, c);
+            if (stage_data) {
+                __syncwarp(gmask);
+#pragma unroll 4
+                for (int i = gs; i < nr; i += HY_GROUP) {
+                    sdat[i] = bs.dat[i];
+                    sxs[i] = bs.xs[i];
+                }
+                __syncwarp(gmask);
+                bs.dat = sdat;
+                bs.xs = sxs;
+            }
+            GaussLaneT<1>::group_jac_pass(bs, nr, gs, gmask, wb.ws + c * nws, 1, stg);
+        }
+        __syncthreads();
+        if (tid == 0) s_next[0] = 0;
+        // ---- lane A: close the Jacobian pass, lmpar for every fit at a trial point (warps pull 32 at a time) ----
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_next[1], 32);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= A) break;
+            const int k = base + lane;
+            if (k < A) {
+                const long long c = (long long)list[cur][k];
+                GaussLaneT<1> g = wb.state[c];
+                double* gw = wb.ws + c * nws;
+                if (g.phase == GP_JAC) {
+#pragma unroll
+                    for (int q = 0; q < 19; ++q) wss.blk[HY_JR + q] = gw[HY_JR + q];
+                    g.jac_close(wss);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 24; ++q) wss.blk[q] = gw[q];       // r and qtf of the factorisation in use
+                }
+                if (g.phase == GP_TRIAL) g.trial_prep(wss);
+#pragma unroll
+                for (int q = 0; q < 28; ++q) gw[q] = wss.blk[q];           // r, diag, qtf, trial constants
+                wb.state[c] = g;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_next[1] = 0;
+        // ---- rows-trial ------------------------------------------------------------------------------
+        for (;;) {
+            int k = 0;
+            if (gs == 0) k = atomicAdd(&s_next[2], 1);
+            k = __shfl_sync(gmask, k, 0, HY_GROUP);
+            if (k >= A) break;
+            const long long c = (long long)list[cur][k];
+            const GaussLaneT<1>& st = wb.state[c];
+            if (st.phase != GP_TRIAL) continue;
+            const int nr = st.nrows;
+            LaneBuf bs = wave_buf(wb, c);
+            if (stage_data) {
+                __syncwarp(gmask);
+#pragma unroll 4
+                for (int i = gs; i < nr; i += HY_GROUP) {
+                    sdat[i] = bs.dat[i];
+                    sxs[i] = bs.xs[i];
+                }
+                __syncwarp(gmask);
+                bs.dat = sdat;
+                bs.xs = sxs;
+            }
+            GaussLaneT<1>::group_trial_pass(bs, nr, gs, gmask, wb.ws + c * nws, 1);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(FINAL_MAXT, 1)
 k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
               int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat,
@@ -433,7 +666,27 @@ static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, Gaus
     int rc = ensure_buf(ctx, &set->carry, (size_t)n * sizeof(GaussCarry));
     if (rc) return rc;
     p->pitch = m;
-    if (ctx->gauss_hybrid) {
+    if (ctx->gauss_wave) {
+        // wave kernel: one block per SM, fit state / workspaces / data vectors / lists of the whole call in global memory
+        p->pitch = align_up(m, 8);
+        p->threads[0] = WV_THREADS;
+        p->smem[0] = wave_smem_bytes(p->pitch, true);
+        if (p->smem[0] > (size_t)ctx->smem_optin) p->smem[0] = wave_smem_bytes(p->pitch, false);
+        p->in_smem[0] = true;
+        p->per_block[0] = 1 << 30;
+        int g0;
+        rc = persistent_grid(ctx, k_gauss_wave, WV_THREADS, p->smem[0], &g0);      // (sets the shared-memory attribute)
+        if (rc) return rc;
+        p->grid[0] = ctx->sm_count;
+        if (p->grid[0] > n) p->grid[0] = (int)(n > 0 ? n : 1);
+        const size_t cap = (size_t)((n + p->grid[0] - 1) / p->grid[0]);
+        if ((rc = ensure_buf(ctx, &set->wave_state, (size_t)n * sizeof(GaussLaneT<1>)))) return rc;
+        if ((rc = ensure_buf(ctx, &set->wave_ws, (size_t)n * lane_ws_doubles(4) * 8))) return rc;
+        if ((rc = ensure_buf(ctx, &set->wave_list, (size_t)p->grid[0] * 2 * cap * sizeof(int)))) return rc;
+        double* gd;
+        unsigned short* gx;
+        if ((rc = lane_scratch(ctx, &set->lane[0], (size_t)n, p->pitch, &gd, &gx))) return rc;
+    } else if (ctx->gauss_hybrid) {
         p->in_smem[0] = hybrid_layout(ctx, m, &p->threads[0], &p->smem[0], &p->per_block[0], &p->pitch);
         rc = persistent_grid(ctx, k_gauss_rounds_h, p->threads[0], p->smem[0], &p->grid[0]);
     } else {
@@ -447,6 +700,7 @@ static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, Gaus
     rc = persistent_grid(ctx, k_gauss_final, p->threads[1], p->smem[1], &p->grid[1]);
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
+        if (k == 0 && ctx->gauss_wave) continue;
         const int per_block = p->per_block[k];
         if ((long long)p->grid[k] * per_block > n) p->grid[k] = (int)((n + per_block - 1) / per_block);
         if (!p->in_smem[k]) {
@@ -474,11 +728,22 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     GaussCarry* carry = (GaussCarry*)set->carry.p;
     double* gdat = nullptr;
     unsigned short* gxs = nullptr;
-    if (!p.in_smem[0]) {
+    if (!p.in_smem[0] && !ctx->gauss_wave) {
         rc = lane_scratch(ctx, &set->lane[0], (size_t)p.grid[0] * p.per_block[0], p.pitch, &gdat, &gxs);
         if (rc) return rc;
     }
-    if (ctx->gauss_hybrid)
+    if (ctx->gauss_wave) {
+        WaveBufs wb;
+        wb.state = (GaussLaneT<1>*)set->wave_state.p;
+        wb.ws = (double*)set->wave_ws.p;
+        rc = lane_scratch(ctx, &set->lane[0], (size_t)n, p.pitch, &wb.dat, &wb.xs);
+        if (rc) return rc;
+        wb.list = (int*)set->wave_list.p;
+        wb.pitch = p.pitch;
+        wb.cap = (int)((n + p.grid[0] - 1) / p.grid[0]);
+        k_gauss_wave<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status, carry, wb,
+                                                                  p.smem[0] == wave_smem_bytes(p.pitch, true) ? 1 : 0);
+    } else if (ctx->gauss_hybrid)
         k_gauss_rounds_h<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                                       take_counter(set, ck, st), carry, gdat, gxs, p.pitch);
     else

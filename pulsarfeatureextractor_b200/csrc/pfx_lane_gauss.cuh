@@ -830,6 +830,57 @@ struct GaussLaneT {
         w[(HY_JR + 18) * st] = F.f2;
     }
 #if defined(__CUDACC__)
+    // One Jacobian pass of one candidate by the eight lanes of a group (s = lane of the group, gmask = its
+    // lanes): constants from the owner's workspace w (element k at w[k * st]), rows of lane s eliminated
+    // into its own factor (staging block stg), butterfly merge, result into the owner's workspace.
+    __device__ static void group_jac_pass(const LaneBuf& bs, int nr, int s, unsigned gmask, double* w, int st,
+                                          const SPtr<double>& stg) {
+        RowFactor4 F;
+        {
+            G4Jac J;
+            load_jac_consts(w, st, J);
+            rows_factor(bs, nr, s, J, F, stg);
+        }
+#pragma unroll 1
+        for (int sh = 1; sh < HY_GROUP; sh <<= 1) {
+            const bool upper = (s & sh) != 0;
+            RowFactor4 lo, up;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const double o = __shfl_xor_sync(gmask, F.R[k], sh);
+                lo.R[k] = upper ? o : F.R[k];
+                up.R[k] = upper ? F.R[k] : o;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double o = __shfl_xor_sync(gmask, F.q[k], sh);
+                lo.q[k] = upper ? o : F.q[k];
+                up.q[k] = upper ? F.q[k] : o;
+                const double oa = __shfl_xor_sync(gmask, F.acn2[k], sh);
+                lo.acn2[k] = upper ? oa : F.acn2[k];
+                up.acn2[k] = upper ? F.acn2[k] : oa;
+            }
+            {
+                const double o = __shfl_xor_sync(gmask, F.f2, sh);
+                lo.f2 = upper ? o : F.f2;
+                up.f2 = upper ? F.f2 : o;
+            }
+            lo.absorb(up);
+            F = lo;
+        }
+        if (s == 0) store_factor(w, st, F);
+    }
+    __device__ static void group_trial_pass(const LaneBuf& bs, int nr, int s, unsigned gmask, double* w, int st) {
+        G4Eval ev;
+        ev.mu = w[(HY_TC + 0) * st];
+        ev.inv = w[(HY_TC + 1) * st];
+        ev.amx = w[(HY_TC + 2) * st];
+        ev.bg = w[(HY_TC + 3) * st];
+        double acc = rows_trial(bs, nr, s, ev);
+#pragma unroll
+        for (int sh = 1; sh < HY_GROUP; sh <<= 1) acc = PFX_ADD(acc, __shfl_xor_sync(gmask, acc, sh));
+        if (s == 0) w[HY_TS * st] = acc;
+    }
     // Called by all 32 lanes.  mask = the owners (lanes of this warp) whose fit needs a Jacobian pass and
     // have run jac_prep; my_nrows = the caller's own row count.  Four candidates per turn, eight lanes each.
     __device__ static void hybrid_jac_rows(unsigned mask, int my_nrows, const LaneBuf& b, const LaneWs& ws) {
@@ -841,45 +892,7 @@ struct GaussLaneT {
             const int nr = __shfl_sync(0xffffffffu, my_nrows, src < 0 ? 0 : src);
 #pragma unroll
             for (int t = 0; t < 32 / HY_GROUP; ++t) mask &= mask - 1;
-            if (src >= 0) {
-                const LaneBuf bs = buf_of(b, src);
-                double* w = ws.blk.p + (src - lane);
-                const int st = ws.blk.stride;
-                RowFactor4 F;
-                {
-                    G4Jac J;
-                    load_jac_consts(w, st, J);
-                    rows_factor(bs, nr, s, J, F, ws.stg);
-                }
-#pragma unroll 1
-                for (int sh = 1; sh < HY_GROUP; sh <<= 1) {
-                    const bool upper = (s & sh) != 0;
-                    RowFactor4 lo, up;
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) {
-                        const double o = __shfl_xor_sync(gmask, F.R[k], sh);
-                        lo.R[k] = upper ? o : F.R[k];
-                        up.R[k] = upper ? F.R[k] : o;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double o = __shfl_xor_sync(gmask, F.q[k], sh);
-                        lo.q[k] = upper ? o : F.q[k];
-                        up.q[k] = upper ? F.q[k] : o;
-                        const double oa = __shfl_xor_sync(gmask, F.acn2[k], sh);
-                        lo.acn2[k] = upper ? oa : F.acn2[k];
-                        up.acn2[k] = upper ? F.acn2[k] : oa;
-                    }
-                    {
-                        const double o = __shfl_xor_sync(gmask, F.f2, sh);
-                        lo.f2 = upper ? o : F.f2;
-                        up.f2 = upper ? F.f2 : o;
-                    }
-                    lo.absorb(up);
-                    F = lo;
-                }
-                if (s == 0) store_factor(w, st, F);
-            }
+            if (src >= 0) group_jac_pass(buf_of(b, src), nr, s, gmask, ws.blk.p + (src - lane), ws.blk.stride, ws.stg);
             __syncwarp();
         }
     }
@@ -892,20 +905,7 @@ struct GaussLaneT {
             const int nr = __shfl_sync(0xffffffffu, my_nrows, src < 0 ? 0 : src);
 #pragma unroll
             for (int t = 0; t < 32 / HY_GROUP; ++t) mask &= mask - 1;
-            if (src >= 0) {
-                const LaneBuf bs = buf_of(b, src);
-                double* w = ws.blk.p + (src - lane);
-                const int st = ws.blk.stride;
-                G4Eval ev;
-                ev.mu = w[(HY_TC + 0) * st];
-                ev.inv = w[(HY_TC + 1) * st];
-                ev.amx = w[(HY_TC + 2) * st];
-                ev.bg = w[(HY_TC + 3) * st];
-                double acc = rows_trial(bs, nr, s, ev);
-#pragma unroll
-                for (int sh = 1; sh < HY_GROUP; sh <<= 1) acc = PFX_ADD(acc, __shfl_xor_sync(gmask, acc, sh));
-                if (s == 0) w[HY_TS * st] = acc;
-            }
+            if (src >= 0) group_trial_pass(buf_of(b, src), nr, s, gmask, ws.blk.p + (src - lane), ws.blk.stride);
             __syncwarp();
         }
     }
@@ -1000,6 +1000,11 @@ struct GaussLaneT {
     // passes over its bins are dealt to the 32 lanes, and lane src alone commits the results.
     PFX_HD static LaneBuf buf_of(const LaneBuf& b, int src) {
         LaneBuf o = b;
+        if (b.pitch < 0) {      // buffers of the lanes anywhere in memory (wave kernel): fetch the owner's pointers
+            o.dat = (double*)WarpCoop::bc((long long)b.dat, src);
+            o.xs = (unsigned short*)WarpCoop::bc((long long)b.xs, src);
+            return o;
+        }
         const int d = (src - WarpCoop::lane()) * b.pitch;
         o.dat = b.dat + d;
         o.xs = b.xs + d;

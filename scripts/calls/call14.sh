@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python scripts/gpu_ab.py 20000 htru PFX_HYBRID=1 PFX_WAVE=1 > gpurun_out/c14_ab.log 2>&1
+timeout 600 python scripts/gpu_ab.py 100000 htru PFX_WAVE=0 PFX_WAVE=1 >> gpurun_out/c14_ab.log 2>&1
+timeout 600 python scripts/gpu_ab.py 400000 htru PFX_WAVE=0 PFX_WAVE=1 >> gpurun_out/c14_ab.log 2>&1
+cat gpurun_out/c14_ab.log
