@@ -69,6 +69,13 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     ctx->hist_u8 = 1;
     if (const char* e = getenv("PFX_HIST_U8")) ctx->hist_u8 = atoi(e) != 0;
     if (const char* e = getenv("PFX_HYBRID")) ctx->gauss_hybrid = atoi(e) != 0;
+    ctx->gauss_slots = 1;      // the rounds kernel in use; PFX_SLOTS=0 selects the lane kernel (or PFX_HYBRID / PFX_WAVE)
+    if (const char* e = getenv("PFX_SLOTS")) ctx->gauss_slots = atoi(e) != 0;
+    else if (getenv("PFX_HYBRID") || getenv("PFX_WAVE")) ctx->gauss_slots = 0;
+    ctx->hy_k = 0;
+    ctx->hy_warps = 8;
+    if (const char* e = getenv("PFX_HY_K")) ctx->hy_k = atoi(e);
+    if (const char* e = getenv("PFX_HY_WARPS")) ctx->hy_warps = atoi(e);
     if (const char* e = getenv("PFX_DM_EXACT")) ctx->dm_exact = atoi(e) != 0;
     if (const char* e = getenv("PFX_SUBBATCH")) ctx->subbatch = atoi(e);
     *out = ctx;

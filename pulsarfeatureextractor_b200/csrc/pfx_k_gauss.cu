@@ -193,23 +193,32 @@ k_gauss_rounds(const void* __restrict__ profile, int dtype, long long n, int m, 
 // exponentials, bound a pass (profiles/r02_phase_profile_hybrid_k32.txt, r02_rounds_hybrid_summary.txt).  Shared memory: ws[44][slots] | dat[slot][pitch] float64
 // | xs[slot][pitch] uint16, one contiguous data vector per candidate (pitch = bins + 8: neighbouring
 // candidates start 16 banks apart); long profiles keep the vectors in a global scratch of the same shape.
-#ifndef PFX_HY_K
-#define PFX_HY_K 32
-#endif
-constexpr int HY_K = PFX_HY_K;
-constexpr int HY_MAX_SLOTS = 128;
-constexpr int HY_MAXT = HY_MAX_SLOTS / HY_K * 32;
+// Layout "packed" (K < 32, the one in use): a warp owns K < 32 candidates and a block has EIGHT warps, i.e. two
+// per scheduler, which is what hides the dependent Householder chains of the row passes (with K = 32 and four
+// warps the kernel only matched the lane kernel).  Every thread has a private 4-row staging block; a slot keeps
+// only what lives between the phases (r, diag, qtf, the trial constants: HY_WSN doubles).
+//     ws[HY_WSN][slots] | stg[20][threads] | dat[slot][pitch] float64 | xs[slot][pitch] uint16
+constexpr int HY_MAX_SLOTS = 128;     // K = 32 layout
+constexpr int HY_MAXT = 256;
 
 __global__ void __launch_bounds__(HY_MAXT, 1)
 k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
                  int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
-                 unsigned short* gxs, int pitch) {
+                 unsigned short* gxs, int pitch, int HY_K) {
     extern __shared__ double smem[];
     const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
     const int nslots = (int)(blockDim.x >> 5) * HY_K;
     const int slot = warp * HY_K + lane;          // lanes >= K: never dereferenced, only used as a base for offsets
+    const bool packed = HY_K < 32;
     LaneWs ws;
     ws.carve(smem + slot, nslots, 4);
+    double* rest = smem + (size_t)(packed ? HY_WSN : lane_ws_doubles(4)) * nslots;
+    if (packed) {
+        ws.stg.p = rest + threadIdx.x;
+        ws.stg.stride = (int)blockDim.x;
+        ws.ipvt.p = (int*)(smem + slot + (size_t)HY_TC * nslots);      // dead before trial_prep writes the constants
+        rest += (size_t)20 * blockDim.x;
+    }
     LaneBuf b;
     b.stride = 1;
     b.pitch = pitch;
@@ -218,9 +227,8 @@ k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m
         b.dat = gdat + gslot * pitch;
         b.xs = gxs + gslot * pitch;
     } else {
-        double* dat = smem + (size_t)lane_ws_doubles(4) * nslots;
-        b.dat = dat + (size_t)slot * pitch;
-        b.xs = (unsigned short*)(dat + (size_t)nslots * pitch) + (size_t)slot * pitch;
+        b.dat = rest + (size_t)slot * pitch;
+        b.xs = (unsigned short*)(rest + (size_t)nslots * pitch) + (size_t)slot * pitch;
     }
     GaussLaneT<1> g;
     g.phase = GP_IDLE;
@@ -307,6 +315,235 @@ k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m
 #if defined(PFX_PROFILE)
     if (ptail) PFX_PROF_ADD(PROF_TAIL, ptail);
 #endif
+}
+
+// ---- block-synchronous form of the hybrid kernel ("slots") ------------------------------------------
+// What bounds the lane and hybrid kernels is instruction FETCH: a trip walks ~200 KB of mostly straight-line
+// code (the unrolled n x n solve, the merge levels, set-up and close of a fit) and every warp of an SM is at its
+// own place in it, so every warp instruction is fetched for one use (ncu: no_instruction 30 % of the stalls,
+// more resident warps make the kernel SLOWER: packed hybrid layout with eight warps 643 ms against 525 ms with
+// four).  The wave kernel showed the cure -- with all warps of a block in the same phase no_instruction falls
+// to 2 % -- but paid for its global-memory state and its draining blocks with barrier and memory stalls.
+// Here the fit state stays in the REGISTERS of an owner lane as in the hybrid kernel (K owners per warp, eight
+// warps, slot = warp * K + lane), the data vectors and the small per-slot workspace stay in shared memory, the
+// slots are refilled from the work queue, and only the PHASES of a trip are block-wide:
+//     owners   trial_close of the previous trip, flush / refill, close and set up fits (warp-cooperative),
+//              jac_prep; owners whose fit needs a Jacobian pass enter the block's list
+//     rows     groups of eight lanes pull slots from the list: Jacobian rows + TSQR merge (group_jac_pass)
+//     owners   jac_close, trial_prep (lmpar); owners with a trial point enter the second list
+//     rows     groups pull: residual norm at the trial point
+// Same arithmetic as the hybrid kernel (rows of a fit are dealt to eight lanes by row index only).
+//     ws[HY_WSN][slots] | stg[20][threads] | nrows[slots], list[2][slots] int | dat[slot][pitch] | xs[slot][pitch]
+constexpr int SL_MAXT = 256;
+
+// Set-up and close of a fit as block-wide TASKS: run by the owner's warp (as in the hybrid kernel) they
+// serialise inside that warp, and a trip waits for the warp with the most fits ending (ncu: 11.5 % of all
+// samples at the barrier after the owners' phase).  Owners instead post a record in the idle workspace of
+// their slot (rows SR .. SR+14: what to do, the fit parameters; the results come back in it), any warp
+// takes the tasks before it pulls row passes, and the owner commits the results in the next trip.
+constexpr int SR = 14;       // first workspace row of the task record; the bit set of the peak stripping keeps rows 0 .. SR-1
+enum { SR_OP = SR, SR_ST_FIN, SR_ST_SET, SR_CAND, SR_P, SR_MEAN = SR_P, SR_SD, SR_PH = SR_P + 4, SR_CHI, SR_X0, SR_NR = SR_X0 + 4 };
+static_assert(SR_NR < HY_WSN, "task record exceeds the slot workspace");
+
+__global__ void __launch_bounds__(SL_MAXT, 1)
+k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
+                 int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
+                 unsigned short* gxs, int pitch, int K) {
+    extern __shared__ double smem[];
+    __shared__ int s_cnt[3], s_next[3];
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = (int)(blockDim.x >> 5) * K;
+    const int slot = warp * K + lane;             // lanes >= K: only a base for offsets, never dereferenced
+    const bool owner = lane < K;
+    const int gs = lane & (HY_GROUP - 1);
+    const unsigned gmask = 0xffu << (8 * (lane >> 3));
+    LaneWs ws;
+    ws.carve(smem + slot, S, 4);
+    double* rest = smem + (size_t)HY_WSN * S;
+    ws.stg.p = rest + tid;
+    ws.stg.stride = (int)blockDim.x;
+    ws.ipvt.p = (int*)(smem + slot + (size_t)HY_TC * S);     // dead before trial_prep writes the constants
+    rest += (size_t)20 * blockDim.x;
+    int* snrows = (int*)rest;
+    int* list0 = snrows + S;
+    int* list1 = list0 + S;
+    int* list2 = list1 + S;
+    rest += 2 * S;
+    double* datbase;
+    unsigned short* xsbase;
+    if (gdat) {
+        datbase = gdat + (size_t)blockIdx.x * S * pitch;
+        xsbase = gxs + (size_t)blockIdx.x * S * pitch;
+    } else {
+        datbase = rest;
+        xsbase = (unsigned short*)(rest + (size_t)S * pitch);
+    }
+    GaussLaneT<1> g;
+    g.phase = GP_IDLE;
+    g.finished = false;
+    g.cand = -1;
+    g.nrows = 0;
+    bool more = owner;
+    bool istr = false;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (tid == 0) {
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+        s_next[0] = s_next[1] = s_next[2] = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        // ---- owners: result of the trial pass, results of the tasks, new tasks, constants of the Jacobian pass ----
+        if (istr) g.trial_close(ws);
+        if (owner) {
+            if (g.phase == GP_WAIT) {
+                if (((int)ws.blk[SR_OP] & 1) && (int)ws.blk[SR_ST_FIN] == 0) g.t1_chi = ws.blk[SR_CHI];
+                GaussLaneT<1>::SetupOut o;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o.x0[k] = ws.blk[SR_X0 + k];
+                o.nr = (int)ws.blk[SR_NR];
+                o.mean = ws.blk[SR_MEAN];
+                o.sd = ws.blk[SR_SD];
+                o.minbg = (o.mean < g.ph_expect) ? o.mean : g.ph_expect;      // builtin min(ph_expect, mean)
+                g.commit_setup(g.stage, o);
+            }
+            int op = 0, st_fin = 0;
+            double p[4] = {0.0, 0.0, 0.0, 0.0};
+            if (g.phase == GP_FIN) {
+                st_fin = g.stage;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) p[k] = g.lm.x[k];
+                g.commit_finish();
+                if (st_fin < 8) op = 1;          // (the close of the last round has no pass over the data)
+            }
+            if (g.phase == GP_IDLE) {
+                if (g.cand >= 0) flush_rounds(g, feat, ld, ier, status, carry);
+                if (more) {
+                    const long long c = (long long)atomicAdd(counter, 1ULL);
+                    if (c < n) {
+                        double* row = feat + c * ld;
+                        const double ph = row[7];      // parked by k_hist
+                        const int before = (int)(PFX_ST_FAIL_MASK & ~(PFX_ST_DM_NDEG_ZERO | PFX_ST_SUBBAND_NO_PAIRS |
+                                                                      PFX_ST_SUBBAND_BAD_WIDTH));
+                        if (status[c] & before) {
+                            row[7] = qnan;             // the reference raised before reaching score 8
+                            carry[c].skip = 1;
+                        } else {
+                            g.start(profile, dtype, c, m, ph);
+                        }
+                    } else {
+                        more = false;
+                    }
+                }
+            }
+            if (g.phase == GP_SETUP) op |= 2;
+            if (op) {
+                ws.blk[SR_OP] = (double)op;
+                ws.blk[SR_ST_FIN] = (double)st_fin;
+                ws.blk[SR_ST_SET] = (double)g.stage;
+                ws.blk[SR_CAND] = (double)g.cand;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ws.blk[SR_P + k] = p[k];
+                ws.blk[SR_PH] = g.ph_expect;
+                list2[atomicAdd(&s_cnt[2], 1)] = slot;
+                g.phase = GP_WAIT;
+            }
+        }
+        const bool isjac = g.phase == GP_JAC;
+        if (isjac) {
+            g.jac_prep(ws);
+            snrows[slot] = g.nrows;
+            list0[atomicAdd(&s_cnt[0], 1)] = slot;
+        }
+        if (!__syncthreads_or((g.phase != GP_IDLE || more) ? 1 : 0)) break;
+        // ---- tasks (a warp each), then the rows of the Jacobian passes (eight lanes each) ----
+        {
+            const int F = s_cnt[2];
+            for (;;) {
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&s_next[2], 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k >= F) break;
+                const int sl = list2[k];
+                double* w = smem + sl;
+                const int op = (int)w[(size_t)SR_OP * S], st_fin = (int)w[(size_t)SR_ST_FIN * S], st_set = (int)w[(size_t)SR_ST_SET * S];
+                const long long cd = (long long)w[(size_t)SR_CAND * S];
+                double p[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) p[q] = w[(size_t)(SR_P + q) * S];
+                const double ph = w[(size_t)SR_PH * S];
+                LaneBuf bs;
+                bs.dat = datbase + (size_t)sl * pitch;
+                bs.xs = xsbase + (size_t)sl * pitch;
+                bs.stride = 1;
+                __syncwarp();      // inputs read by every lane before lane 0 writes results over them
+                double chi = 0.0;
+                if (op & 1) chi = GaussLaneT<1>::work_finish(bs, st_fin, p, profile, dtype, cd, m, m / 2);
+                GaussLaneT<1>::SetupOut o;
+                SPtr<double> bits;
+                bits.p = w;
+                bits.stride = S;
+                GaussLaneT<1>::work_setup(0, bs, bits, SR, st_set, ph, profile, dtype, cd, m, m / 2, o);
+                if (lane == 0) {
+                    w[(size_t)SR_CHI * S] = chi;
+                    w[(size_t)SR_MEAN * S] = o.mean;
+                    w[(size_t)SR_SD * S] = o.sd;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[(size_t)(SR_X0 + q) * S] = o.x0[q];
+                    w[(size_t)SR_NR * S] = (double)o.nr;
+                }
+                __syncwarp();
+            }
+        }
+        {
+            const int A = s_cnt[0];
+            for (;;) {
+                int k = 0;
+                if (gs == 0) k = atomicAdd(&s_next[0], 1);
+                k = __shfl_sync(gmask, k, 0, HY_GROUP);
+                if (k >= A) break;
+                const int sl = list0[k];
+                LaneBuf bs;
+                bs.dat = datbase + (size_t)sl * pitch;
+                bs.xs = xsbase + (size_t)sl * pitch;
+                bs.stride = 1;
+                GaussLaneT<1>::group_jac_pass(bs, snrows[sl], gs, gmask, smem + sl, S, ws.stg);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_cnt[0] = s_cnt[2] = 0;
+            s_next[0] = s_next[2] = 0;
+        }
+        // ---- owners: pivoting / Q^T f, lmpar ----
+        if (isjac) g.jac_close(ws);
+        istr = g.phase == GP_TRIAL;
+        if (istr) {
+            g.trial_prep(ws);
+            list1[atomicAdd(&s_cnt[1], 1)] = slot;
+        }
+        __syncthreads();
+        // ---- rows of the trial points ----
+        {
+            const int A = s_cnt[1];
+            for (;;) {
+                int k = 0;
+                if (gs == 0) k = atomicAdd(&s_next[1], 1);
+                k = __shfl_sync(gmask, k, 0, HY_GROUP);
+                if (k >= A) break;
+                const int sl = list1[k];
+                LaneBuf bs;
+                bs.dat = datbase + (size_t)sl * pitch;
+                bs.xs = xsbase + (size_t)sl * pitch;
+                bs.stride = 1;
+                GaussLaneT<1>::group_trial_pass(bs, snrows[sl], gs, gmask, smem + sl, S);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_cnt[1] = 0;
+            s_next[1] = 0;
+        }
+    }
 }
 
 // ---- wave form of the rounds kernel ---------------------------------------------------------------
@@ -638,26 +875,73 @@ struct GaussPlan {
     bool in_smem[2];
     int per_block[2];      // candidates resident per block
     int pitch;             // hybrid rounds kernel: elements between the data vectors of two candidates
+    int hy_k;              // hybrid rounds kernel: candidates per warp
 };
 }  // namespace
 
-// hybrid rounds kernel: slots (candidates) per block, threads = 32 lanes per HY_K slots
-static bool hybrid_layout(pfx_ctx* ctx, int m, int* threads, size_t* smem, int* slots_out, int* pitch) {
+// hybrid rounds kernel: candidates per warp (K), warps, shared memory.  k_req = 32 selects the first layout
+// (every lane an owner, staging inside the lane's workspace, up to four warps); otherwise the packed layout:
+// eight warps and as many candidates per warp as fit (at most k_req; 0 = as many as fit, at most 24).
+static bool hybrid_layout(pfx_ctx* ctx, int m, int k_req, int* threads, size_t* smem, int* slots_out, int* pitch, int* k_out) {
     *pitch = align_up(m, 8) + 8;
-    const size_t ws = (size_t)lane_ws_doubles(4) * 8;
-    const size_t per_slot = ws + (size_t)*pitch * 10;
     const size_t budget = (size_t)ctx->smem_optin;
-    for (int slots = HY_MAX_SLOTS; slots >= 2 * HY_K; slots -= HY_K) {
-        if (per_slot * slots + 64 <= budget) {
-            *threads = slots / HY_K * 32;
-            *slots_out = slots;
-            *smem = (per_slot * slots + 64 + 15) / 16 * 16;
-            return true;
+    if (k_req == 32) {
+        const size_t ws = (size_t)lane_ws_doubles(4) * 8;
+        const size_t per_slot = ws + (size_t)*pitch * 10;
+        *k_out = 32;
+        for (int slots = HY_MAX_SLOTS; slots >= 64; slots -= 32) {
+            if (per_slot * slots + 64 <= budget) {
+                *threads = slots;
+                *slots_out = slots;
+                *smem = (per_slot * slots + 64 + 15) / 16 * 16;
+                return true;
+            }
         }
+        *threads = HY_MAX_SLOTS;
+        *slots_out = HY_MAX_SLOTS;
+        *smem = ws * HY_MAX_SLOTS;
+        return false;
     }
-    *threads = HY_MAXT;
-    *slots_out = HY_MAX_SLOTS;
-    *smem = ws * HY_MAX_SLOTS;
+    const int warps = ctx->hy_warps > 0 ? ctx->hy_warps : 8;
+    const int kmax = k_req > 0 ? (k_req < 31 ? k_req : 31) : 24;
+    const size_t fixed = (size_t)20 * 8 * warps * 32 + 64;
+    const size_t per_slot = (size_t)HY_WSN * 8 + (size_t)*pitch * 10;
+    *threads = warps * 32;
+    int k = (budget > fixed) ? (int)((budget - fixed) / per_slot / warps) : 0;
+    if (k > kmax) k = kmax;
+    if (k >= 8) {
+        *k_out = k;
+        *slots_out = k * warps;
+        *smem = (fixed + per_slot * k * warps + 15) / 16 * 16;
+        return true;
+    }
+    // long profiles: data vectors in the global scratch, workspaces and staging blocks in shared memory
+    *k_out = kmax < 16 ? kmax : 16;
+    *slots_out = *k_out * warps;
+    *smem = (fixed + (size_t)HY_WSN * 8 * *slots_out + 15) / 16 * 16;
+    return false;
+}
+
+// block-synchronous kernel: eight warps, as many candidates per warp as fit (at most k_req; 0: at most 24)
+static bool slots_layout(pfx_ctx* ctx, int m, int k_req, int* threads, size_t* smem, int* slots_out, int* pitch, int* k_out) {
+    *pitch = align_up(m, 8) + 8;
+    const size_t budget = (size_t)ctx->smem_optin;
+    const int warps = ctx->hy_warps > 0 ? ctx->hy_warps : 8;
+    const int kmax = k_req > 0 ? (k_req < 32 ? k_req : 32) : 24;
+    const size_t fixed = (size_t)20 * 8 * warps * 32 + 64;
+    const size_t per_slot = (size_t)HY_WSN * 8 + (size_t)*pitch * 10 + 16;
+    *threads = warps * 32;
+    int k = (budget > fixed) ? (int)((budget - fixed) / per_slot / warps) : 0;
+    if (k > kmax) k = kmax;
+    if (k >= 6) {
+        *k_out = k;
+        *slots_out = k * warps;
+        *smem = (fixed + per_slot * k * warps + 15) / 16 * 16;
+        return true;
+    }
+    *k_out = kmax < 16 ? kmax : 16;
+    *slots_out = *k_out * warps;
+    *smem = (fixed + ((size_t)HY_WSN * 8 + 16) * *slots_out + 15) / 16 * 16;
     return false;
 }
 
@@ -686,8 +970,11 @@ static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, Gaus
         double* gd;
         unsigned short* gx;
         if ((rc = lane_scratch(ctx, &set->lane[0], (size_t)n, p->pitch, &gd, &gx))) return rc;
+    } else if (ctx->gauss_slots) {
+        p->in_smem[0] = slots_layout(ctx, m, ctx->hy_k, &p->threads[0], &p->smem[0], &p->per_block[0], &p->pitch, &p->hy_k);
+        rc = persistent_grid(ctx, k_gauss_rounds_s, p->threads[0], p->smem[0], &p->grid[0]);
     } else if (ctx->gauss_hybrid) {
-        p->in_smem[0] = hybrid_layout(ctx, m, &p->threads[0], &p->smem[0], &p->per_block[0], &p->pitch);
+        p->in_smem[0] = hybrid_layout(ctx, m, ctx->hy_k, &p->threads[0], &p->smem[0], &p->per_block[0], &p->pitch, &p->hy_k);
         rc = persistent_grid(ctx, k_gauss_rounds_h, p->threads[0], p->smem[0], &p->grid[0]);
     } else {
         p->in_smem[0] = lane_layout(ctx, m, 4, ROUNDS_LANES, ROUNDS_MAXT, ROUNDS_LANES, 10, &p->threads[0], &p->smem[0]);
@@ -743,9 +1030,12 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
         wb.cap = (int)((n + p.grid[0] - 1) / p.grid[0]);
         k_gauss_wave<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status, carry, wb,
                                                                   p.smem[0] == wave_smem_bytes(p.pitch, true) ? 1 : 0);
-    } else if (ctx->gauss_hybrid)
+    } else if (ctx->gauss_slots)
+        k_gauss_rounds_s<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
+                                                                      take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k);
+    else if (ctx->gauss_hybrid)
         k_gauss_rounds_h<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
-                                                                      take_counter(set, ck, st), carry, gdat, gxs, p.pitch);
+                                                                      take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k);
     else
         k_gauss_rounds<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                                     take_counter(set, ck, st), carry, gdat, gxs);

@@ -71,7 +71,7 @@ struct GaussCarry {
     int pad;
 };
 
-enum { GP_IDLE = 0, GP_SETUP = 1, GP_JAC = 2, GP_TRIAL = 3, GP_FIN = 4 };
+enum { GP_IDLE = 0, GP_SETUP = 1, GP_JAC = 2, GP_TRIAL = 3, GP_FIN = 4, GP_WAIT = 5 };
 
 // rows of the 4-parameter family: value = |p2| exp(-((x-p1)/s)^2/2) + b,
 // s = |p0| or p0, b = p3 or |p3|
@@ -269,6 +269,9 @@ constexpr int HY_GROUP = 8;                 // lanes per candidate in the row pa
 // 0 .. 18 once the group is done with the constants.  Around a trial point r and qtf (0 .. 23) are live:
 // constants and result go to the staging area, which is idle during trial passes.
 enum { HY_JC = 0, HY_JR = 0, HY_TC = 24, HY_TS = 28 };
+// doubles per candidate slot in the packed layout of the hybrid kernel (0..23 r/diag/qtf, 24..28 trial constants
+// and result, ipvt over 24..27); also the number of workspace slots the bit set of the peak stripping may use
+constexpr int HY_WSN = 30;
 
 // ---- warp-cooperative helpers --------------------------------------------------------------
 // The set-up and the close of a fit (copying / rebuilding the data vector, its statistics, the
@@ -617,8 +620,8 @@ struct GaussLaneT {
     }
 
     // PO:1305-1354 on the index list kept in xs; returns the survivor count or -1 (IndexError)
-    PFX_HD int strip_peak(const LaneBuf& b, int pos) const {
-        const int n = m;
+    PFX_HD int strip_peak(const LaneBuf& b, int pos) const { return strip_peak_list(b, m, pos); }
+    PFX_HD static int strip_peak_list(const LaneBuf& b, int n, int pos) {
         int len = n;
         const bool writer = (G::rank() == 0);     // every lane follows the control flow, lane 0 edits the list
         if (writer)
@@ -1027,8 +1030,7 @@ struct GaussLaneT {
     }
 
     // PO:1305-1354 with the index list kept as a bit set (BinSet); same control flow as strip_peak
-    PFX_HD int strip_peak_bits(const LaneBuf& b, BinSet& set, int pos) const {
-        const int n = m;
+    PFX_HD static int strip_peak_bits(const LaneBuf& b, int n, BinSet& set, int pos) {
         int len = n;
         set.fill(n);
 #define PFX_DEL(k_)                              \
@@ -1082,19 +1084,22 @@ struct GaussLaneT {
         return len;
     }
 
-    PFX_HD void coop_setup(int src, const LaneBuf& b, const LaneWs& ws) {
+    // The passes of a set-up / close as functions of plain values, called by ALL lanes of a warp with the
+    // same arguments (bs = the candidate's data vector, lead = the lane that runs the serial list surgery
+    // in bits[] and writes single elements): the owner-lane forms below broadcast the owner's state and
+    // commit the results to it; the block-synchronous kernel runs them as tasks on any warp.
+    struct SetupOut {
+        double x0[4], mean, sd, minbg;
+        int nr;          // rows of the fit; <= 0: no fit (-1: IndexError -> sentinels, 0: empty sequence)
+    };
+    PFX_HD static void work_setup(int lead, const LaneBuf& bs, const SPtr<double>& bits, int bit_slots, int st, double ph,
+                                  const void* prof, int dt, long long cd, int mm, int ct, SetupOut& o) {
         typedef WarpCoop WC;
-        const bool me = WC::lane() == src;
-        const LaneBuf bs = buf_of(b, src);
-        const int st = WC::bc(stage, src), mm = WC::bc(m, src), ct = WC::bc(cut, src), dt = WC::bc(dtype, src);
-        const long long cd = WC::bc(cand, src);
-        const void* prof = (const void*)WC::bc((long long)profile, src);
-        double x0[4];
-        int nr = mm;
-        G4Flags f;
+        const bool me = WC::lane() == lead;
+        o.nr = mm;
+        o.mean = o.sd = o.minbg = 0.0;
         if (st == 0) {
             // profile statistics and the T1 data vector (PO:724-739, 1098-1110)
-            const double ph = WC::bc(ph_expect, src);
             WC::rows(mm, [&](int i) {
                 bs.d(i) = yrot_of(prof, dt, cd, mm, ct, i);
                 bs.x(i) = (unsigned short)i;
@@ -1117,17 +1122,13 @@ struct GaussLaneT {
             double mu, sdev, vmax, bmax;
             int amax;
             coop_stats(bs, mm, mu, sdev, amax, vmax, bmax);
-            x0[0] = sdev;
-            x0[1] = (double)amax;
-            x0[2] = vmax;
-            x0[3] = 1.0;
-            f.abs_sigma = true;
-            f.abs_bg = false;
-            if (me) {
-                mean = mean_;
-                sd = sd_;
-                minbg = minbg_;
-            }
+            o.x0[0] = sdev;
+            o.x0[1] = (double)amax;
+            o.x0[2] = vmax;
+            o.x0[3] = 1.0;
+            o.mean = mean_;
+            o.sd = sd_;
+            o.minbg = minbg_;
         } else if (st == 1) {
             // rotated raw profile, peak stripping (PO:1305-1354)
             WC::rows(mm, [&](int i) { bs.d(i) = yrot_of(prof, dt, cd, mm, ct, i); });
@@ -1137,10 +1138,10 @@ struct GaussLaneT {
             WC::maxima(mm, [&](int i) { return bs.d(i); }, amax, vmax, bmax);
             int nlen = 0;
             if (me) {
-                if (mm <= BinSet::capacity(lane_ws_doubles(4))) {
+                if (mm <= BinSet::capacity(bit_slots)) {
                     BinSet set;
-                    set.w = ws.blk;
-                    nlen = strip_peak_bits(bs, set, amax);
+                    set.w = bits;
+                    nlen = strip_peak_bits(bs, mm, set, amax);
                     if (nlen > 0) {
                         int cnt = 0;
                         for (int i = 0; i < mm; ++i)
@@ -1151,33 +1152,24 @@ struct GaussLaneT {
                             }
                     }
                 } else {
-                    nlen = strip_peak(bs, amax);
+                    nlen = strip_peak_list(bs, mm, amax);
                     for (int k = 0; k < nlen; ++k) bs.d(k) = bs.d(bs.x(k));
                 }
             }
-            nlen = WC::bc(nlen, src);
+            nlen = WC::bc(nlen, lead);
             WC::sync();
             if (nlen <= 0) {
-                if (me) {
-                    if (nlen < 0) {                 // IndexError -> 1e6 sentinels (PO:762-764)
-                        sentinel = true;
-                        status |= PFX_ST_DG_SENTINEL;
-                    } else {
-                        status |= PFX_ST_EMPTY_SEQUENCE;
-                    }
-                    finished = true;
-                    phase = GP_IDLE;
-                }
+                o.nr = nlen;
                 return;
             }
             double mu, sdev;
             int am2;
             coop_stats(bs, nlen, mu, sdev, am2, vmax, bmax);
-            x0[0] = sdev;
-            x0[1] = (double)bs.x(am2);
-            x0[2] = bmax;
-            x0[3] = mu;
-            nr = nlen;
+            o.x0[0] = sdev;
+            o.x0[1] = (double)bs.x(am2);
+            o.x0[2] = bmax;
+            o.x0[3] = mu;
+            o.nr = nlen;
             WC::sync();
             if (nlen < 4) {                          // PO:1373-1377 zero padding
                 if (me)
@@ -1185,41 +1177,24 @@ struct GaussLaneT {
                         bs.d(k) = 0.0;
                         bs.x(k) = 0;
                     }
-                nr = 4;
+                o.nr = 4;
             }
             WC::sync();
-            f.abs_sigma = false;
-            f.abs_bg = true;
         } else {
             // rounds 2..8: data were rebuilt by the previous round's close
             double mu, sdev, vmax, bmax;
             int amax;
             coop_stats(bs, mm, mu, sdev, amax, vmax, bmax);
-            x0[0] = sdev;
-            x0[1] = (double)bs.x(amax);
-            x0[2] = bmax;
-            x0[3] = mu;
-            f.abs_sigma = false;
-            f.abs_bg = true;
-        }
-        if (me) {
-            fl = f;
-            nrows = nr;
-            lm.init(x0);
-            phase = GP_JAC;
+            o.x0[0] = sdev;
+            o.x0[1] = (double)bs.x(amax);
+            o.x0[2] = bmax;
+            o.x0[3] = mu;
         }
     }
-
-    PFX_HD void coop_finish(int src, const LaneBuf& b) {
+    // close of fit `st` with parameters p: the chi-square of the T1 fit (returned), or the data of the next round
+    PFX_HD static double work_finish(const LaneBuf& bs, int st, const double (&p)[4], const void* prof, int dt,
+                                     long long cd, int mm, int ct) {
         typedef WarpCoop WC;
-        const bool me = WC::lane() == src;
-        const LaneBuf bs = buf_of(b, src);
-        const int st = WC::bc(stage, src), mm = WC::bc(m, src), ct = WC::bc(cut, src), dt = WC::bc(dtype, src);
-        const long long cd = WC::bc(cand, src);
-        const void* prof = (const void*)WC::bc((long long)profile, src);
-        double p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = WC::bc(lm.x[k], src);
         G4Flags f;
         f.abs_sigma = (st == 0);
         f.abs_bg = (st != 0);
@@ -1227,49 +1202,101 @@ struct GaussLaneT {
             G4Eval ev;
             ev.set(p, f);
             const double c = WC::template sum<true>(mm, [&](int i) { return bs.d(i) - ev.value((double)i); });
-            if (me) {
-                for (int k = 0; k < 4; ++k) p_t1[k] = p[k];
-                t1_fwhm = fabs(FWHM_K * p[0]);
-                t1_chi = c / (double)mm;
-            }
-        } else {
-            // rebuild the data for the next round over the full profile (PO:1388-1399)
-            const double nfwhm = fabs(FWHM_K * p[0]);
-            const double lo = p[2] - (1.5 * nfwhm) / 2.0;
-            const double hi = p[2] + (1.5 * nfwhm) / 2.0;
-            G4Eval fe;
-            fe.set(p, f);
-            WC::sync();
-            if (st < 8) {
-                WC::rows(mm, [&](int i) {
-                    const double xv = (double)i;
-                    const double ev = fe.value(xv);
-                    const double yv = yrot_of(prof, dt, cd, mm, ct, i);
-                    double nv;
-                    if (ev <= yv) nv = PFX_ADD(PFX_SUB(yv, ev), p[3]);
-                    else if ((ev > yv) && (xv > lo) && (xv < hi)) nv = p[3];
-                    else nv = yv;
-                    bs.d(i) = nv;
-                    bs.x(i) = (unsigned short)i;
-                });
-            }
-            WC::sync();
-            if (me) {
-                if (st == 7)
-                    for (int k = 0; k < 4; ++k) p2[k] = p[k];
-                if (st == 8)
-                    for (int k = 0; k < 4; ++k) p1[k] = p[k];
-            }
+            return c / (double)mm;
         }
-        if (me) {
-            ier[st] = (int8_t)lm.info;
-            ++stage;
-            if (stage > 8) {
-                finished = true;
-                phase = GP_IDLE;
+        // rebuild the data for the next round over the full profile (PO:1388-1399)
+        const double nfwhm = fabs(FWHM_K * p[0]);
+        const double lo = p[2] - (1.5 * nfwhm) / 2.0;
+        const double hi = p[2] + (1.5 * nfwhm) / 2.0;
+        G4Eval fe;
+        fe.set(p, f);
+        WC::sync();
+        if (st < 8) {
+            WC::rows(mm, [&](int i) {
+                const double xv = (double)i;
+                const double ev = fe.value(xv);
+                const double yv = yrot_of(prof, dt, cd, mm, ct, i);
+                double nv;
+                if (ev <= yv) nv = PFX_ADD(PFX_SUB(yv, ev), p[3]);
+                else if ((ev > yv) && (xv > lo) && (xv < hi)) nv = p[3];
+                else nv = yv;
+                bs.d(i) = nv;
+                bs.x(i) = (unsigned short)i;
+            });
+        }
+        WC::sync();
+        return 0.0;
+    }
+    // owner-side halves: what a set-up / close changes in the state of the candidate's lane
+    PFX_HD void commit_setup(int st, const SetupOut& o) {
+        if (st == 0) {
+            mean = o.mean;
+            sd = o.sd;
+            minbg = o.minbg;
+        }
+        if (o.nr <= 0) {
+            if (o.nr < 0) {                 // IndexError -> 1e6 sentinels (PO:762-764)
+                sentinel = true;
+                status |= PFX_ST_DG_SENTINEL;
             } else {
-                phase = GP_SETUP;
+                status |= PFX_ST_EMPTY_SEQUENCE;
             }
+            finished = true;
+            phase = GP_IDLE;
+            return;
+        }
+        fl.abs_sigma = (st == 0);
+        fl.abs_bg = (st != 0);
+        nrows = o.nr;
+        lm.init(o.x0);
+        phase = GP_JAC;
+    }
+    // (t1_chi of a stage-0 close is set by the caller from work_finish)
+    PFX_HD void commit_finish() {
+        const int st = stage;
+        if (st == 0) {
+            for (int k = 0; k < 4; ++k) p_t1[k] = lm.x[k];
+            t1_fwhm = fabs(FWHM_K * lm.x[0]);
+        }
+        if (st == 7)
+            for (int k = 0; k < 4; ++k) p2[k] = lm.x[k];
+        if (st == 8)
+            for (int k = 0; k < 4; ++k) p1[k] = lm.x[k];
+        ier[st] = (int8_t)lm.info;
+        ++stage;
+        if (stage > 8) {
+            finished = true;
+            phase = GP_IDLE;
+        } else {
+            phase = GP_SETUP;
+        }
+    }
+
+    PFX_HD void coop_setup(int src, const LaneBuf& b, const LaneWs& ws) {
+        typedef WarpCoop WC;
+        const LaneBuf bs = buf_of(b, src);
+        const int st = WC::bc(stage, src), mm = WC::bc(m, src), ct = WC::bc(cut, src), dt = WC::bc(dtype, src);
+        const long long cd = WC::bc(cand, src);
+        const void* prof = (const void*)WC::bc((long long)profile, src);
+        const double ph = WC::bc(ph_expect, src);
+        SetupOut o;
+        work_setup(src, bs, ws.blk, HY_WSN, st, ph, prof, dt, cd, mm, ct, o);
+        if (WC::lane() == src) commit_setup(st, o);
+    }
+
+    PFX_HD void coop_finish(int src, const LaneBuf& b) {
+        typedef WarpCoop WC;
+        const LaneBuf bs = buf_of(b, src);
+        const int st = WC::bc(stage, src), mm = WC::bc(m, src), ct = WC::bc(cut, src), dt = WC::bc(dtype, src);
+        const long long cd = WC::bc(cand, src);
+        const void* prof = (const void*)WC::bc((long long)profile, src);
+        double p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = WC::bc(lm.x[k], src);
+        const double chi = work_finish(bs, st, p, prof, dt, cd, mm, ct);
+        if (WC::lane() == src) {
+            if (st == 0) t1_chi = chi;
+            commit_finish();
         }
     }
 

@@ -1,6 +1,6 @@
 """Development helper (GPU): score the same batch under two environments (e.g. PFX_HIST_U8=0 / 1) in
 separate processes, compare the rows bit for bit and print the stage times.
-usage: gpu_ab.py N CONFIG VAR=a VAR=b     (CONFIG: htru | superb64)"""
+usage: gpu_ab.py N CONFIG VAR=a[,VAR2=c] VAR=b ...     (CONFIG: htru | superb64); rows are compared with the first set"""
 import os, sys, subprocess, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if sys.argv[1] == "--one":
@@ -26,13 +26,18 @@ else:
     import numpy as np
     n, cfg = sys.argv[1], sys.argv[2]
     outs = []
-    for k, kv in enumerate(sys.argv[3:5]):
-        var, val = kv.split("=")
+    for k, kv in enumerate(sys.argv[3:]):
+        env = dict(x.split("=") for x in kv.split(","))
         out = "/tmp/ab_%d.npz" % k
         print(kv, end=" ", flush=True)
-        subprocess.run([sys.executable, __file__, "--one", n, cfg, out], env=dict(os.environ, **{var: val}), check=True)
-        outs.append(np.load(out))
-    a, b = outs
-    for f in ("feat", "status", "ier"):
-        same = np.array_equal(a[f], b[f], equal_nan=True) if f == "feat" else np.array_equal(a[f], b[f])
-        print(f, "identical" if same else "DIFFERENT: %d rows" % int((a[f] != b[f]).reshape(len(a[f]), -1).any(axis=1).sum()))
+        rc = subprocess.run([sys.executable, __file__, "--one", n, cfg, out], env=dict(os.environ, **env)).returncode
+        if rc != 0:
+            print("FAILED rc=%d" % rc)
+            continue
+        outs.append((kv, np.load(out)))
+    base = outs[0][1]
+    for kv, b in outs[1:]:
+        print("--", kv, "against", outs[0][0])
+        for f in ("feat", "status", "ier"):
+            same = np.array_equal(base[f], b[f], equal_nan=True) if f == "feat" else np.array_equal(base[f], b[f])
+            print(f, "identical" if same else "DIFFERENT: %d rows" % int((base[f] != b[f]).reshape(len(base[f]), -1).any(axis=1).sum()))
