@@ -107,6 +107,86 @@ PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag
     }
 }
 
+// The same factorisation with everything in registers (n <= 4): every loop unrolled, the pivot column
+// chosen by predicated swaps.  Statement for statement qrfac_small (same sums in the same order, the same
+// divisions), so the results are bit-identical; what it removes is the local-memory traffic of the
+// dynamically indexed rdiag / wa / acn0 (ncu on k_gauss_rounds_s: 12.5 % of all samples in qrfac_small,
+// two thirds of them waiting for local loads that miss the small L1 left beside 222 KB of shared memory).
+// a[j][i] = element (row i, column j).
+template <int N>
+PFX_HD inline void qrfac_reg(double (&a)[N][N], int (&ipvt)[N], double (&rdiag)[N], double (&wa)[N]) {
+    double acn0[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        ipvt[j] = j;
+        acn0[j] = rdiag[j];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        int kmax = j;
+        double vmax = rdiag[j];
+#pragma unroll
+        for (int k = j + 1; k < N; ++k)
+            if (rdiag[k] > vmax) {
+                kmax = k;
+                vmax = rdiag[k];
+            }
+#pragma unroll
+        for (int k = j + 1; k < N; ++k)
+            if (kmax == k) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double t = a[j][i];
+                    a[j][i] = a[k][i];
+                    a[k][i] = t;
+                }
+                rdiag[k] = rdiag[j];
+                wa[k] = wa[j];
+                acn0[k] = acn0[j];
+                const int t = ipvt[j];
+                ipvt[j] = ipvt[k];
+                ipvt[k] = t;
+            }
+        double s = 0.0;
+#pragma unroll
+        for (int i = j; i < N; ++i) s = PFX_FMA(a[j][i], a[j][i], s);
+        double ajnorm = sqrt(s);
+        if (ajnorm != 0.0) {
+            if (a[j][j] < 0.0) ajnorm = -ajnorm;
+#pragma unroll
+            for (int i = j; i < N; ++i) a[j][i] /= ajnorm;
+            a[j][j] = PFX_ADD(a[j][j], 1.0);
+#pragma unroll
+            for (int k = j + 1; k < N; ++k) {
+                double sum = 0.0;
+#pragma unroll
+                for (int i = j; i < N; ++i) sum = PFX_FMA(a[j][i], a[k][i], sum);
+                double temp = sum / a[j][j];
+#pragma unroll
+                for (int i = j; i < N; ++i) a[k][i] = PFX_FMA(-temp, a[j][i], a[k][i]);
+                if (rdiag[k] != 0.0) {
+                    temp = a[k][j] / rdiag[k];
+                    rdiag[k] = PFX_MUL(rdiag[k], sqrt(fmax(0.0, PFX_FMA(-temp, temp, 1.0))));
+                    double q = rdiag[k] / wa[k];
+                    if (PFX_MUL(0.05, PFX_MUL(q, q)) <= LM_EPSMCH) {
+                        double s2 = 0.0;
+#pragma unroll
+                        for (int i = j + 1; i < N; ++i) s2 = PFX_FMA(a[k][i], a[k][i], s2);
+                        rdiag[k] = sqrt(s2);
+                        if (rdiag[k] <= PFX_MUL(1e-13, acn0[k])) {      // exact rank deficiency, see qrfac_small
+#pragma unroll
+                            for (int i = j + 1; i < N; ++i) a[k][i] = 0.0;
+                            rdiag[k] = 0.0;
+                        }
+                        wa[k] = rdiag[k];
+                    }
+                }
+            }
+        }
+        rdiag[j] = -ajnorm;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // C lanes of a warp share one fit (C = 1, 2, 4, ... 32).  The rows of the residual vector are
 // dealt to the C lanes, every lane accumulates the triangular factor of its own rows, and the C
@@ -695,12 +775,81 @@ struct LaneLM {
             rdiag[j] = acnorm[j];
             wa[j] = acnorm[j];
         }
+#ifndef PFX_QRFAC_REG
+#define PFX_QRFAC_REG 1
+#endif
+        (void)m;
+        if constexpr (PFX_QRFAC_REG && N <= 4) {
+            // the n x n factorisation, Q^T f and the gradient test in registers (qrfac_reg); the workspace
+            // receives what the trial points read: the upper triangle, Q^T f and diag
+            double a[N][N];
+            int ip[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+#pragma unroll
+                for (int i = 0; i < N; ++i) a[j][i] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
+            qrfac_reg<N>(a, ip, rdiag, wa);
+            ipv = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) ipv |= ip[j] << (8 * j);
+            if (iter == 1) {
+                double sq = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    diag[j] = acnorm[j];
+                    if (acnorm[j] == 0.0) diag[j] = 1.0;
+                    const double t = PFX_MUL(diag[j], x[j]);
+                    sq = PFX_FMA(t, t, sq);
+                }
+                xnorm = sqrt(sq);
+                delta = PFX_MUL(100.0, xnorm);
+                if (delta == 0.0) delta = 100.0;
+            }
+            double w4[N], qtf[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) w4[j] = q[j];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double ajj = a[j][j];
+                if (ajj != 0.0) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = j; i < N; ++i) sum = PFX_FMA(a[j][i], w4[i], sum);
+                    double temp = -sum / ajj;
+#pragma unroll
+                    for (int i = j; i < N; ++i) w4[i] = PFX_FMA(a[j][i], temp, w4[i]);
+                }
+                a[j][j] = rdiag[j];
+                qtf[j] = w4[j];
+            }
+            gnorm = 0.0;
+            if (fnorm != 0.0) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double al = acnorm[0];
+#pragma unroll
+                    for (int k = 1; k < N; ++k) al = (ip[j] == k) ? acnorm[k] : al;
+                    if (al != 0.0) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int i = 0; i <= j; ++i) sum = PFX_FMA(a[j][i], qtf[i] / fnorm, sum);
+                        gnorm = fmax(gnorm, fabs(sum / al));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+#pragma unroll
+                for (int i = 0; i <= j; ++i) s.r[i + N * j] = a[j][i];
+                s.qtf[j] = qtf[j];
+                s.ipvt[j] = ip[j];      // (read by the rolled lmpar of the histogram and DM kernels)
+            }
+        } else {
         // unpack the triangular factor; rows beyond m do not exist (m >= N is guaranteed upstream)
 #pragma unroll
         for (int j = 0; j < N; ++j)
 #pragma unroll
             for (int i = 0; i < N; ++i) s.r[i + N * j] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
-        (void)m;
         qrfac_small(N, N, s.r, s.ipvt, rdiag, wa);
         if (N <= 4) {
             ipv = 0;
@@ -746,6 +895,7 @@ struct LaneLM {
                     gnorm = fmax(gnorm, fabs(sum / al));
                 }
             }
+        }
         }
         if (gnorm <= 0.0) {     // gtol = 0
             info = 4;
