@@ -834,6 +834,224 @@ k_gauss_final(const void* __restrict__ profile, int dtype, long long n, int m, d
     PFX_PROF_ADD(PROF8_TOTAL, pk0);
 }
 
+// ---- block-synchronous form of the final-fit kernel ----------------------------------------------
+// Same organisation as k_gauss_rounds_s for the 8-parameter fit: the scalars of a fit (par, delta, norms,
+// counters) stay in the registers of an owner lane, its vectors (x, diag, the trial point) and the n x n
+// workspace of the rolled MINPACK routines live in the slot's shared-memory workspace, and the phases of a
+// trip are block-wide: owners (trial_end, start / close tasks posted, x published) | tasks by whole warps,
+// then Jacobian rows by groups of FS_GROUP lanes (Gauss8LaneT<FS_GROUP>::group_jac: blocks of two rows
+// eliminated against the lane's factor, butterfly merge, the leader leaves the factor unpacked in the
+// workspace) | owners (jac_end on the unpacked factor, lmpar) | trial rows by groups.
+// The lane-pair kernel it replaces ran 8.4 of 32 lanes per instruction with 255 registers and 21 KB of
+// spill traffic per candidate, and at 100 000 candidates a fifth of its time was the tail of fits that run
+// to maxfev (200 trips): here a trip of a lone fit is a third as long.
+//     ws[G8_WSN][slots] | nrows-free lists: list[3][slots] int (+pad) | dat[slot][pitch] float64
+#ifndef PFX_FS_GROUP
+#define PFX_FS_GROUP 8
+#endif
+constexpr int FS_GROUP = PFX_FS_GROUP;
+constexpr int FS_MAXT = 256;
+typedef Gauss8LaneT<FS_GROUP> G8;
+
+__global__ void __launch_bounds__(FS_MAXT, 1)
+k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
+                int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat, int pitch, int K) {
+    extern __shared__ double smem[];
+    __shared__ int s_cnt[3], s_next[3];
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = (int)(blockDim.x >> 5) * K;
+    const int slot = warp * K + lane;             // lanes >= K: only a base for offsets, never dereferenced
+    const bool owner = lane < K;
+    const int gs = lane & (FS_GROUP - 1);
+    const unsigned gmask = (FS_GROUP == 32) ? 0xffffffffu : (((1u << (FS_GROUP & 31)) - 1u) << (lane & ~(FS_GROUP - 1)));
+    LaneWs ws;
+    ws.carve(smem + slot, S, 8);
+    const SPtr<double> wsl = ws.blk;              // row k of this slot's workspace: wsl[k]
+    double* rest = smem + (size_t)G8::G8_WSN * S;
+    int* list0 = (int*)rest;
+    int* list1 = list0 + S;
+    int* list2 = list1 + S;
+    rest += 2 * S;
+    double* datbase = gdat ? gdat + (size_t)blockIdx.x * S * pitch : rest;
+    LaneLM<8> lm;
+    long long cand = -1;
+    int phase = GP_IDLE;
+    bool more = owner, istr = false;
+    if (tid == 0) {
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+        s_next[0] = s_next[1] = s_next[2] = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        // ---- owners ----
+        int op = 0;
+        if (owner) {
+            if (istr) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    lm.x[k] = wsl[G8::G8_X + k];
+                    lm.diag[k] = ws.diag[k];
+                    lm.xnew[k] = wsl[G8::G8_XN + k];
+                }
+                const int r = lm.trial_end(sqrt(wsl[G8::G8_TS]));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wsl[G8::G8_X + k] = lm.x[k];
+                phase = (r == LANE_JAC) ? GP_JAC : (r == LANE_TRIAL ? GP_TRIAL : GP_FIN);
+            }
+            if (phase == GP_WAIT) phase = GP_JAC;          // the profile of the new candidate is in place
+            long long cfin = -1;
+            if (phase == GP_FIN) {
+                // close: parameters to the trial-point rows (dead now), the task writes scores 10 and 11
+                if (ier) ier[cand * PFX_NIER + PFX_FIT_DG_FINAL] = (int8_t)lm.info;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) wsl[G8::G8_XN + k] = wsl[G8::G8_X + k];
+                cfin = cand;
+                cand = -1;
+                op = 1;
+                phase = GP_IDLE;
+            }
+            if (phase == GP_IDLE && more) {
+                // candidates the rounds kernel finished itself (failure, sentinel) are skipped
+                for (;;) {
+                    const long long c = (long long)atomicAdd(counter, 1ULL);
+                    if (c >= n) {
+                        more = false;
+                        break;
+                    }
+                    if (!carry[c].skip) {
+                        cand = c;
+                        break;
+                    }
+                }
+                if (cand >= 0) {
+                    const GaussCarry& cy = carry[cand];
+                    double x0[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        x0[k] = cy.p1[k];
+                        x0[4 + k] = cy.p2[k];
+                    }
+                    lm.init(x0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        wsl[G8::G8_X + k] = x0[k];
+                        ws.diag[k] = 0.0;
+                    }
+                    op |= 2;
+                    phase = GP_WAIT;
+                }
+            }
+            if (op) {
+                wsl[G8::G8_OP] = (double)op;
+                wsl[G8::G8_CFIN] = (double)cfin;
+                wsl[G8::G8_CNEW] = (double)cand;
+                list2[atomicAdd(&s_cnt[2], 1)] = slot;
+            }
+        }
+        const bool isjac = phase == GP_JAC;
+        if (isjac) list0[atomicAdd(&s_cnt[0], 1)] = slot;
+        if (!__syncthreads_or((phase != GP_IDLE || more || op) ? 1 : 0)) break;
+        // ---- tasks (a warp each), then the rows of the Jacobian passes ----
+        {
+            const int F = s_cnt[2];
+            for (;;) {
+                int k = 0;
+                if (lane == 0) k = atomicAdd(&s_next[2], 1);
+                k = __shfl_sync(0xffffffffu, k, 0);
+                if (k >= F) break;
+                const int sl = list2[k];
+                double* w = smem + sl;
+                const int top = (int)w[(size_t)G8::G8_OP * S];
+                const long long cfin = (long long)w[(size_t)G8::G8_CFIN * S], cnew = (long long)w[(size_t)G8::G8_CNEW * S];
+                LaneBuf bs;
+                bs.dat = datbase + (size_t)sl * pitch;
+                bs.xs = nullptr;
+                bs.stride = 1;
+                if (top & 1) {
+                    double q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) q[j] = w[(size_t)(G8::G8_XN + j) * S];
+                    double s10, s11;
+                    G8::task_finish(bs, q, carry[cfin], m, s10, s11);
+                    if (lane == 0) {
+                        feat[cfin * ld + 9] = s10;
+                        feat[cfin * ld + 10] = s11;
+                    }
+                }
+                if (top & 2) G8::task_start(bs, profile, dtype, cnew, m);
+                __syncwarp();
+            }
+        }
+        {
+            const int A = s_cnt[0];
+            for (;;) {
+                int k = 0;
+                if (gs == 0) k = atomicAdd(&s_next[0], 1);
+                k = __shfl_sync(gmask, k, 0, FS_GROUP);
+                if (k >= A) break;
+                const int sl = list0[k];
+                LaneBuf bs;
+                bs.dat = datbase + (size_t)sl * pitch;
+                bs.xs = nullptr;
+                bs.stride = 1;
+                G8::group_jac(bs, m, smem + sl, S);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_cnt[0] = s_cnt[2] = 0;
+            s_next[0] = s_next[2] = 0;
+        }
+        // ---- owners: pivoting / Q^T f, lmpar ----
+        if (isjac) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                lm.x[k] = wsl[G8::G8_X + k];
+                lm.diag[k] = ws.diag[k];
+                lm.q[k] = wsl[G8::G8_Q + k];
+                lm.acn2[k] = wsl[G8::G8_ACN2 + k];
+            }
+            lm.f2 = wsl[G8::G8_F2];
+            const int r = lm.jac_end(ws, m, true);
+            phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
+        }
+        istr = phase == GP_TRIAL;
+        if (istr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                lm.x[k] = wsl[G8::G8_X + k];
+                lm.diag[k] = ws.diag[k];
+            }
+            lm.trial_begin(ws);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wsl[G8::G8_XN + k] = lm.xnew[k];
+            list1[atomicAdd(&s_cnt[1], 1)] = slot;
+        }
+        __syncthreads();
+        // ---- rows of the trial points ----
+        {
+            const int A = s_cnt[1];
+            for (;;) {
+                int k = 0;
+                if (gs == 0) k = atomicAdd(&s_next[1], 1);
+                k = __shfl_sync(gmask, k, 0, FS_GROUP);
+                if (k >= A) break;
+                const int sl = list1[k];
+                LaneBuf bs;
+                bs.dat = datbase + (size_t)sl * pitch;
+                bs.xs = nullptr;
+                bs.stride = 1;
+                G8::group_trial(bs, m, smem + sl, S);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_cnt[1] = 0;
+            s_next[1] = 0;
+        }
+    }
+}
+
 }  // namespace
 
 
@@ -876,6 +1094,7 @@ struct GaussPlan {
     int per_block[2];      // candidates resident per block
     int pitch;             // hybrid rounds kernel: elements between the data vectors of two candidates
     int hy_k;              // hybrid rounds kernel: candidates per warp
+    int final_pitch, final_k;   // block-synchronous final-fit kernel: elements between data vectors, candidates per warp
 };
 }  // namespace
 
@@ -945,6 +1164,27 @@ static bool slots_layout(pfx_ctx* ctx, int m, int k_req, int* threads, size_t* s
     return false;
 }
 
+// block-synchronous final-fit kernel: eight warps, as many candidates per warp as fit (at most 24)
+static bool final_slots_layout(pfx_ctx* ctx, int m, int* threads, size_t* smem, int* slots_out, int* pitch, int* k_out) {
+    *pitch = align_up(m, 8) + 8;
+    const size_t budget = (size_t)ctx->smem_optin;
+    const int warps = 8;
+    const size_t per_slot = (size_t)G8::G8_WSN * 8 + (size_t)*pitch * 8 + 16;
+    *threads = warps * 32;
+    int k = (budget > 64) ? (int)((budget - 64) / per_slot / warps) : 0;
+    if (k > 24) k = 24;
+    if (k >= 4) {
+        *k_out = k;
+        *slots_out = k * warps;
+        *smem = (64 + per_slot * k * warps + 15) / 16 * 16;
+        return true;
+    }
+    *k_out = 16;
+    *slots_out = 16 * warps;
+    *smem = (64 + ((size_t)G8::G8_WSN * 8 + 16) * *slots_out + 15) / 16 * 16;
+    return false;
+}
+
 // launch geometry of the two kernels for n candidates of m bins, and the scratch they need
 static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, GaussPlan* p) {
     int rc = ensure_buf(ctx, &set->carry, (size_t)n * sizeof(GaussCarry));
@@ -982,9 +1222,15 @@ static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, Gaus
         rc = persistent_grid(ctx, k_gauss_rounds, p->threads[0], p->smem[0], &p->grid[0]);
     }
     if (rc) return rc;
-    p->in_smem[1] = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, 8, &p->threads[1], &p->smem[1]);
-    p->per_block[1] = p->threads[1] / FINAL_LANES;
-    rc = persistent_grid(ctx, k_gauss_final, p->threads[1], p->smem[1], &p->grid[1]);
+    p->final_pitch = m;
+    if (ctx->final_slots) {
+        p->in_smem[1] = final_slots_layout(ctx, m, &p->threads[1], &p->smem[1], &p->per_block[1], &p->final_pitch, &p->final_k);
+        rc = persistent_grid(ctx, k_gauss_final_s, p->threads[1], p->smem[1], &p->grid[1]);
+    } else {
+        p->in_smem[1] = lane_layout(ctx, m, 8, FINAL_LANES, FINAL_MAXT, FINAL_WS_PER_GROUP, 8, &p->threads[1], &p->smem[1]);
+        p->per_block[1] = p->threads[1] / FINAL_LANES;
+        rc = persistent_grid(ctx, k_gauss_final, p->threads[1], p->smem[1], &p->grid[1]);
+    }
     if (rc) return rc;
     for (int k = 0; k < 2; ++k) {
         if (k == 0 && ctx->gauss_wave) continue;
@@ -993,7 +1239,7 @@ static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, Gaus
         if (!p->in_smem[k]) {
             double* gdat;
             unsigned short* gxs;
-            rc = lane_scratch(ctx, &set->lane[k], (size_t)p->grid[k] * per_block, k == 0 ? p->pitch : m, &gdat, &gxs);
+            rc = lane_scratch(ctx, &set->lane[k], (size_t)p->grid[k] * per_block, k == 0 ? p->pitch : p->final_pitch, &gdat, &gxs);
             if (rc) return rc;
         }
     }
@@ -1043,11 +1289,15 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     gdat = nullptr;
     gxs = nullptr;
     if (!p.in_smem[1]) {
-        rc = lane_scratch(ctx, &set->lane[1], (size_t)p.grid[1] * (p.threads[1] / FINAL_LANES), m, &gdat, &gxs);
+        rc = lane_scratch(ctx, &set->lane[1], (size_t)p.grid[1] * p.per_block[1], p.final_pitch, &gdat, &gxs);
         if (rc) return rc;
     }
-    k_gauss_final<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
-                                                               take_counter(set, ck + 4, st), carry, gdat, gxs);
+    if (ctx->final_slots)
+        k_gauss_final_s<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
+                                                                     take_counter(set, ck + 4, st), carry, gdat, p.final_pitch, p.final_k);
+    else
+        k_gauss_final<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
+                                                                   take_counter(set, ck + 4, st), carry, gdat, gxs);
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }

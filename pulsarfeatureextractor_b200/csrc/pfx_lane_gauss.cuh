@@ -1388,9 +1388,9 @@ struct Gauss8LaneT {
         return PFX_ADD(PFX_ADD(a, c), bg);
     }
 
-    PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
-        PFX_PROF_T0(pt0);
-        lm.jac_begin();
+    // rows of one Jacobian pass dealt to the C lanes of a group (L.x set, L.jac_begin() done): every lane
+    // eliminates its blocks of rows against its own factor in L
+    PFX_HD static void rows_jac(LaneLM<8>& lm, const LaneBuf& b, int m) {
         const double* x = lm.x;
         const double* h = lm.h;
         const double s1 = 1.0 / fabs(x[0]), s1h = 1.0 / fabs(x[0] + h[0]), m1 = x[1], m1h = x[1] + h[1];
@@ -1435,6 +1435,11 @@ struct Gauss8LaneT {
             }
             lm.template jac_block<B>(A, bv);
         }
+    }
+    PFX_HD void jac_pass(const LaneBuf& b, const LaneWs& ws) {
+        PFX_PROF_T0(pt0);
+        lm.jac_begin();
+        rows_jac(lm, b, m);
         lm.template jac_combine<C>();
         PFX_PROF_ADD(PROF8_JAC_ROWS, pt0);
         PFX_PROF_T0(pt1);
@@ -1521,6 +1526,105 @@ struct Gauss8LaneT {
         s11 = dg_chi;
         finished = true;
         phase = GP_IDLE;
+    }
+
+    // ---- block-synchronous kernel (k_gauss_final_s): row passes by a group of C lanes for a slot whose fit
+    // state lives in its owner lane; hand-over through the slot's workspace w (element k at w[k * st]) ----
+    //   G8_X  x of the pass (owner)        G8_XN  trial point (owner) / parameters of the close
+    //   r rows 0..63  merged factor, unpacked (group leader)    G8_Q, G8_ACN2, G8_F2  Q^T f, column norms^2, |f|^2
+    //   G8_TS  sum of squares at the trial point
+    enum { G8_Q = 80, G8_ACN2 = 88, G8_F2 = 96, G8_TS = 97, G8_OP = 98, G8_CFIN = 99, G8_CNEW = 100,
+           G8_X = 120, G8_XN = 128, G8_WSN = 136 };
+#if defined(__CUDACC__)
+    __device__ static void group_jac(const LaneBuf& b, int m, double* w, int st) {
+        LaneLM<8> L;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) L.x[k] = w[(size_t)(G8_X + k) * st];
+        L.jac_begin();
+        rows_jac(L, b, m);
+        L.template jac_combine<C>();
+        if (G::rank() == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    w[(size_t)(i + 8 * j) * st] = (i <= j) ? L.R[LaneLM<8>::ridx(i < j ? i : j, j)] : 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                w[(size_t)(G8_Q + k) * st] = L.q[k];
+                w[(size_t)(G8_ACN2 + k) * st] = L.acn2[k];
+            }
+            w[(size_t)G8_F2 * st] = L.f2;
+        }
+    }
+    __device__ static void group_trial(const LaneBuf& b, int m, double* w, int st) {
+        double xn[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xn[k] = w[(size_t)(G8_XN + k) * st];
+        double s = 0.0;
+        for (int i = G::rank(); i < m; i += C) {
+            const double f = PFX_SUB(b.d(i), value(xn, (double)i));
+            s = PFX_FMA(f, f, s);
+        }
+        s = G::sum(s);
+        if (G::rank() == 0) w[(size_t)G8_TS * st] = s;
+    }
+#endif
+    // tasks of the block-synchronous kernel, called by all lanes of a warp with the same arguments:
+    // the rotated profile of a new candidate ...
+    PFX_HD static void task_start(const LaneBuf& bs, const void* prof, int dt, long long cd, int mm) {
+        typedef WarpCoop WC;
+        WC::rows(mm, [&](int i) { bs.d(i) = GaussLaneT<1>::yrot_of(prof, dt, cd, mm, mm / 2, i); });
+        WC::sync();
+    }
+    // ... and the close of a fit (PO:1407-1428, PO:747-761; finish() with the bins dealt to the warp)
+    PFX_HD static void task_finish(const LaneBuf& bs, const double (&q)[8], const GaussCarry& cy, int mm, double& s10,
+                                   double& s11) {
+        typedef WarpCoop WC;
+        const double fwhm1 = fabs(FWHM_K * q[0]), fwhm2 = fabs(FWHM_K * q[4]);
+        const G4Flags rf = {false, true};
+        const G4Flags tf = {true, false};
+        const double bgmix = PFX_MUL(PFX_ADD(cy.p1[3], cy.p2[3]), 0.5);
+        auto combi = [&](double xv) {
+            return PFX_ADD(PFX_SUB(PFX_SUB(PFX_ADD(g4_value(cy.p1, rf, xv), g4_value(cy.p2, rf, xv)), cy.p1[3]), cy.p2[3]), bgmix);
+        };
+        const double c = WC::template sum<false>(mm, [&](int i) {
+            const double fi = value(q, (double)i);
+            const double dlt = bs.d(i) - fi;
+            return (fi >= 1.0) ? (dlt * dlt) / (double)mm : 0.0;
+        });
+        const double cc = WC::template sum<false>(mm, [&](int i) {
+            const double cf = combi((double)i);
+            const double dlt = bs.d(i) - cf;
+            return (cf >= 1.0) ? (dlt * dlt) / (double)mm : 0.0;
+        });
+        const bool use_final = (c <= cc);
+        double fw_a, fw_b, dg_chi;
+        if (use_final) {
+            fw_a = fwhm1;
+            fw_b = fwhm2;
+            dg_chi = c;
+        } else {
+            fw_a = fabs(FWHM_K * cy.p2[0]);
+            fw_b = fabs(FWHM_K * cy.p1[0]);
+            dg_chi = cc;
+        }
+        // std of (chosen fit) - (T1 fit + minbg - std)   (PO:755-756)
+        WC::sync();
+        WC::rows(mm, [&](int i) {
+            const double xv = (double)i;
+            const double dg = use_final ? value(q, xv) : combi(xv);
+            bs.d(i) = dg - PFX_SUB(PFX_ADD(g4_value(cy.p_t1, tf, xv), cy.minbg), cy.sd);      // the data vector is no longer needed
+        });
+        WC::sync();
+        const double ds = WC::template sum<false>(mm, [&](int i) { return bs.d(i); });
+        const double dmean = ds / (double)mm;
+        const double dv = WC::template sum<true>(mm, [&](int i) { return bs.d(i) - dmean; });
+        const double dstd = fabs(sqrt(dv / (double)mm));
+        if (dstd < 3.0) s10 = cy.t1_fwhm;
+        else s10 = (fw_b < fw_a) ? fw_b : fw_a;
+        s11 = dg_chi;
+        WC::sync();
     }
 
     PFX_HD void step(const LaneBuf& b, const LaneWs& ws) {

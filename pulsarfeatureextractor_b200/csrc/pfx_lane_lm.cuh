@@ -765,7 +765,9 @@ struct LaneLM {
     }
 
     // returns LANE_TRIAL, or LANE_DONE with info set
-    PFX_HD int jac_end(const LaneWs& s, int m) {
+    // pre_unpacked: s.r already holds the triangular factor (upper triangle, zeros below), put there by the
+    // lanes that ran the row pass; R[] of this object is not read
+    PFX_HD int jac_end(const LaneWs& s, int m, bool pre_unpacked = false) {
         nfev += N;
         if (iter == 1) fnorm = sqrt(f2);
         double rdiag[N], wa[N];
@@ -846,10 +848,12 @@ struct LaneLM {
             }
         } else {
         // unpack the triangular factor; rows beyond m do not exist (m >= N is guaranteed upstream)
+        if (!pre_unpacked) {
 #pragma unroll
-        for (int j = 0; j < N; ++j)
+            for (int j = 0; j < N; ++j)
 #pragma unroll
-            for (int i = 0; i < N; ++i) s.r[i + N * j] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
+                for (int i = 0; i < N; ++i) s.r[i + N * j] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
+        }
         qrfac_small(N, N, s.r, s.ipvt, rdiag, wa);
         if (N <= 4) {
             ipv = 0;

@@ -41,3 +41,11 @@ else:
         for f in ("feat", "status", "ier"):
             same = np.array_equal(base[f], b[f], equal_nan=True) if f == "feat" else np.array_equal(base[f], b[f])
             print(f, "identical" if same else "DIFFERENT: %d rows" % int((base[f] != b[f]).reshape(len(base[f]), -1).any(axis=1).sum()))
+            if not same and f == "feat":
+                x, y = base[f], b[f]
+                for c in range(x.shape[1]):
+                    d = ~((x[:, c] == y[:, c]) | (np.isnan(x[:, c]) & np.isnan(y[:, c])))
+                    if d.any():
+                        rel = np.abs(x[d, c] - y[d, c]) / np.maximum(np.abs(x[d, c]), 1e-300)
+                        print("   col %d: %d rows differ, rel diff median %.1e p90 %.1e max %.1e, > 1e-6: %d" % (
+                            c, int(d.sum()), np.nanmedian(rel), np.nanpercentile(rel, 90), np.nanmax(rel), int((rel > 1e-6).sum())))
