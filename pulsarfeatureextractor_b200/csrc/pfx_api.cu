@@ -74,6 +74,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     else if (getenv("PFX_HYBRID") || getenv("PFX_WAVE")) ctx->gauss_slots = 0;
     ctx->final_slots = 1;      // PFX_FINAL_SLOTS=0: the lane-pair final-fit kernel
     if (const char* e = getenv("PFX_FINAL_SLOTS")) ctx->final_slots = atoi(e) != 0;
+    ctx->lmpar_budget = 2;
+    if (const char* e = getenv("PFX_LMPAR_BUDGET")) ctx->lmpar_budget = atoi(e);
     ctx->hy_k = 0;
     ctx->hy_warps = 8;
     if (const char* e = getenv("PFX_HY_K")) ctx->hy_k = atoi(e);

@@ -67,6 +67,7 @@ struct pfx_ctx {
     int hist_u8;              // 1: warp-cooperative histogram set-up for uint8 profiles of <= 128 bins (default)
     int gauss_wave;           // 1: wave form of the rounds kernel (state in global memory, phases per block)
     int hy_k, hy_warps;       // hybrid rounds kernel: candidates per warp (32: first layout, 0: as many as fit), warps per block
+    int lmpar_budget;         // block-synchronous kernels: lmpar iterations per trip (<= 0: no limit)
     int final_slots;          // 1: block-synchronous final-fit kernel, 0: lane-pair kernel
     int gauss_slots;          // 1: block-synchronous hybrid kernel (phases of a trip are block-wide)
     int gauss_hybrid;         // 1: hybrid rounds kernel (eight lanes per candidate in the row passes), 0: lane kernel

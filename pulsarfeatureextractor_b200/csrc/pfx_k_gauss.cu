@@ -348,7 +348,7 @@ static_assert(SR_NR < HY_WSN, "task record exceeds the slot workspace");
 __global__ void __launch_bounds__(SL_MAXT, 1)
 k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
                  int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
-                 unsigned short* gxs, int pitch, int K) {
+                 unsigned short* gxs, int pitch, int K, int lmpar_budget) {
     extern __shared__ double smem[];
     __shared__ int s_cnt[3], s_next[3];
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -384,7 +384,10 @@ k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m
     g.cand = -1;
     g.nrows = 0;
     bool more = owner;
-    bool istr = false;
+    bool istr = false, lpend = false;
+    LmparState lst;
+    lst.parl = lst.paru = lst.fp = 0.0;
+    lst.iter = 0;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     if (tid == 0) {
         s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
@@ -516,10 +519,13 @@ k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m
         }
         // ---- owners: pivoting / Q^T f, lmpar ----
         if (isjac) g.jac_close(ws);
-        istr = g.phase == GP_TRIAL;
-        if (istr) {
-            g.trial_prep(ws);
-            list1[atomicAdd(&s_cnt[1], 1)] = slot;
+        // (at most lmpar_budget iterations of lmpar per trip: a phase lasts as long as its slowest owner, and one
+        // sub-problem in twenty-five needs more than two -- such a fit stays in this phase for another trip)
+        istr = false;
+        if (g.phase == GP_TRIAL) {
+            istr = g.trial_prep_budget(ws, lst, lpend, lmpar_budget);
+            lpend = !istr;
+            if (istr) list1[atomicAdd(&s_cnt[1], 1)] = slot;
         }
         __syncthreads();
         // ---- rows of the trial points ----
@@ -855,7 +861,8 @@ typedef Gauss8LaneT<FS_GROUP> G8;
 
 __global__ void __launch_bounds__(FS_MAXT, 1)
 k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
-                int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat, int pitch, int K) {
+                int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat, int pitch, int K,
+                int lmpar_budget) {
     extern __shared__ double smem[];
     __shared__ int s_cnt[3], s_next[3];
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -876,7 +883,10 @@ k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m,
     LaneLM<8> lm;
     long long cand = -1;
     int phase = GP_IDLE;
-    bool more = owner, istr = false;
+    bool more = owner, istr = false, lpend = false;
+    LmparState lst;
+    lst.parl = lst.paru = lst.fp = 0.0;
+    lst.iter = 0;
     if (tid == 0) {
         s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
         s_next[0] = s_next[1] = s_next[2] = 0;
@@ -1015,17 +1025,26 @@ k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m,
             const int r = lm.jac_end(ws, m, true);
             phase = (r == LANE_TRIAL) ? GP_TRIAL : GP_FIN;
         }
-        istr = phase == GP_TRIAL;
-        if (istr) {
+        // lmpar: at most lmpar_budget iterations per trip.  One sub-problem in six needs more than two, one in
+        // fifty more than four, and a phase lasts as long as its slowest owner: a fit whose sub-problem is hard
+        // stays in this phase for another trip (its iteration state is four scalars) instead of holding up the block.
+        istr = false;
+        if (phase == GP_TRIAL) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 lm.x[k] = wsl[G8::G8_X + k];
                 lm.diag[k] = ws.diag[k];
             }
-            lm.trial_begin(ws);
+            bool done = lpend ? false : lm.lmpar_start(ws, lst);
+            for (int it = 0; !done && it < lmpar_budget; ++it) done = lm.lmpar_step(ws, lst);
+            lpend = !done;
+            if (done) {
+                lm.trial_point_seq(ws);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) wsl[G8::G8_XN + k] = lm.xnew[k];
-            list1[atomicAdd(&s_cnt[1], 1)] = slot;
+                for (int k = 0; k < 8; ++k) wsl[G8::G8_XN + k] = lm.xnew[k];
+                list1[atomicAdd(&s_cnt[1], 1)] = slot;
+                istr = true;
+            }
         }
         __syncthreads();
         // ---- rows of the trial points ----
@@ -1278,7 +1297,8 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
                                                                   p.smem[0] == wave_smem_bytes(p.pitch, true) ? 1 : 0);
     } else if (ctx->gauss_slots)
         k_gauss_rounds_s<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
-                                                                      take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k);
+                                                                      take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k,
+                                                                      ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10);
     else if (ctx->gauss_hybrid)
         k_gauss_rounds_h<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                                       take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k);
@@ -1294,7 +1314,8 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     }
     if (ctx->final_slots)
         k_gauss_final_s<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
-                                                                     take_counter(set, ck + 4, st), carry, gdat, p.final_pitch, p.final_k);
+                                                                     take_counter(set, ck + 4, st), carry, gdat, p.final_pitch, p.final_k,
+                                                                     ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10);
     else
         k_gauss_final<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
                                                                    take_counter(set, ck + 4, st), carry, gdat, gxs);

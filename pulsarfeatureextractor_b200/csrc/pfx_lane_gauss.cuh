@@ -768,6 +768,17 @@ struct GaussLaneT {
         ws.blk[HY_TC + 3] = ev.bg;
         PFX_PROF_ADD(PROF_LMPAR, pt0);
     }
+    // trial_prep with at most `budget` lmpar iterations (block-synchronous kernel): false = not finished yet
+    PFX_HD bool trial_prep_budget(const LaneWs& ws, LmparState& st, bool pending, int budget) {
+        if (!lm.trial_begin_budget(ws, st, pending, budget)) return false;
+        G4Eval ev;
+        ev.set(lm.xnew, fl);
+        ws.blk[HY_TC + 0] = ev.mu;
+        ws.blk[HY_TC + 1] = ev.inv;
+        ws.blk[HY_TC + 2] = ev.amx;
+        ws.blk[HY_TC + 3] = ev.bg;
+        return true;
+    }
     PFX_HD void trial_close(const LaneWs& ws) {
         PFX_PROF_T0(pt2);
         const int r = lm.trial_end(sqrt(ws.blk[HY_TS]));

@@ -308,6 +308,9 @@ PFX_HD inline double fast_rsqrt(double x) {
 // square root instead of two divisions and a square root, which shortens the dependency chain
 // that bounds the latency of the trust-region solve (measured: the shared-memory version took
 // ~3e5 cycles per call, more than a whole Jacobian pass).
+#if defined(PFX_COUNT_LMPAR) && !defined(__CUDA_ARCH__)
+static long long g_lmpar_hist[2][12];
+#endif
 template <int N>
 struct SmallLM {
     double r[N][N];      // r[i][j]: upper triangle = R, strictly lower = S^T (qrsolv work)
@@ -412,9 +415,9 @@ struct SmallLM {
         for (int j = 0; j < N; ++j) put(x, ipvt[j], wa[j]);
     }
 
-    // lmpar; x = step (un-negated), returns through par
-    PFX_HD void lmpar(double delta, double& par, double (&x)[N], double (&sdiag)[N]) {
-        const double p1 = 0.1, p001 = 0.001;
+    // lmpar in two pieces (see lmpar_begin / lmpar_iter in pfx_lm.cuh); x = step (un-negated), returns through par
+    PFX_HD bool lmpar_begin(double delta, double& par, double (&x)[N], LmparState& st) {
+        const double p1 = 0.1;
         double wa1[N], wa2[N];
         int nsing = N;
 #pragma unroll
@@ -435,14 +438,17 @@ struct SmallLM {
         }
 #pragma unroll
         for (int j = 0; j < N; ++j) put(x, ipvt[j], wa1[j]);
-        int iter = 0;
+        st.iter = 0;
 #pragma unroll
         for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
-        double dxnorm = nrm(wa2);
-        double fp = dxnorm - delta;
+        const double dxnorm = nrm(wa2);
+        const double fp = dxnorm - delta;
         if (fp <= p1 * delta) {
+#if defined(PFX_COUNT_LMPAR) && !defined(__CUDA_ARCH__)
+            g_lmpar_hist[0][0]++;
+#endif
             par = 0.0;
-            return;
+            return true;
         }
         double parl = 0.0;
         if (nsing >= N) {
@@ -474,36 +480,56 @@ struct SmallLM {
         par = fmax(par, parl);
         par = fmin(par, paru);
         if (par == 0.0) par = gnorm / dxnorm;
-        for (;;) {
-            ++iter;
-            if (par == 0.0) par = fmax(LM_DWARF, p001 * paru);
-            double temp = sqrt(par);
+        st.parl = parl;
+        st.paru = paru;
+        st.fp = fp;
+        return false;
+    }
+    // one iteration on a freshly loaded sub-problem (qrsolv leaves its factor below the diagonal of r)
+    PFX_HD bool lmpar_iter(double delta, double& par, double (&x)[N], double (&sdiag)[N], LmparState& st) {
+        const double p1 = 0.1, p001 = 0.001;
+        double wa1[N], wa2[N];
+        ++st.iter;
+        if (par == 0.0) par = fmax(LM_DWARF, p001 * st.paru);
+        double temp = sqrt(par);
 #pragma unroll
-            for (int j = 0; j < N; ++j) wa1[j] = temp * diag[j];
-            qrsolv(wa1, x, sdiag);
+        for (int j = 0; j < N; ++j) wa1[j] = temp * diag[j];
+        qrsolv(wa1, x, sdiag);
 #pragma unroll
-            for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
-            dxnorm = nrm(wa2);
-            temp = fp;
-            fp = dxnorm - delta;
-            if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
+        const double dxnorm = nrm(wa2);
+        temp = st.fp;
+        const double fp = dxnorm - delta;
+        st.fp = fp;
+        if (fabs(fp) <= p1 * delta || (st.parl == 0.0 && fp <= temp && temp < 0.0) || st.iter == 10) {
+#if defined(PFX_COUNT_LMPAR) && !defined(__CUDA_ARCH__)
+            g_lmpar_hist[0][st.iter]++;
+#endif
+            return true;
+        }
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const int l = ipvt[j];
-                wa1[j] = sel(diag, l) * (sel(wa2, l) / dxnorm);
-            }
+        for (int j = 0; j < N; ++j) {
+            const int l = ipvt[j];
+            wa1[j] = sel(diag, l) * (sel(wa2, l) / dxnorm);
+        }
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                wa1[j] = wa1[j] / sdiag[j];
-                const double t = wa1[j];
+        for (int j = 0; j < N; ++j) {
+            wa1[j] = wa1[j] / sdiag[j];
+            const double t = wa1[j];
 #pragma unroll
-                for (int i = j + 1; i < N; ++i) wa1[i] -= r[i][j] * t;
-            }
-            temp = nrm(wa1);
-            const double parc = ((fp / delta) / temp) / temp;
-            if (fp > 0.0) parl = fmax(parl, par);
-            if (fp < 0.0) paru = fmin(paru, par);
-            par = fmax(parl, par + parc);
+            for (int i = j + 1; i < N; ++i) wa1[i] -= r[i][j] * t;
+        }
+        temp = nrm(wa1);
+        const double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) st.parl = fmax(st.parl, par);
+        if (fp < 0.0) st.paru = fmin(st.paru, par);
+        par = fmax(st.parl, par + parc);
+        return false;
+    }
+    PFX_HD void lmpar(double delta, double& par, double (&x)[N], double (&sdiag)[N]) {
+        LmparState st;
+        if (lmpar_begin(delta, par, x, st)) return;
+        while (!lmpar_iter(delta, par, x, sdiag, st)) {
         }
     }
 };
@@ -943,19 +969,80 @@ struct LaneLM {
             rpnorm = SmallLM<N>::nrm(w3);
         } else {
             lmpar_seq(N, N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.sdiag, s.wa1, s.wa2);
-            for (int j = 0; j < N; ++j) s.wa1[j] = 0.0;
-            for (int j = 0; j < N; ++j) {
-                double temp = -s.step[s.ipvt[j]];
-                for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + N * j] * temp;
-            }
-            rpnorm = enorm_seq(N, s.wa1);
-#pragma unroll
-            for (int j = 0; j < N; ++j) stepv[j] = s.step[j];
+            trial_point_seq(s);
+            return;
         }
         double sq = 0.0;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             double p = -stepv[j];
+            xnew[j] = x[j] + p;
+            double t = diag[j] * p;
+            sq += t * t;
+        }
+        pnorm = sqrt(sq);
+        if (iter == 1) delta = fmin(delta, pnorm);
+    }
+    // trial_begin with the register-resident sub-problem (N <= 4) and at most `budget` iterations of lmpar per
+    // call: returns false when lmpar is not finished (call again with pending = true; st carries the iteration)
+    PFX_HD bool trial_begin_budget(const LaneWs& s, LmparState& st, bool pending, int budget) {
+        SmallLM<N> q;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) q.r[i][j] = (i <= j) ? s.r[i + N * j] : 0.0;
+            q.ipvt[j] = (ipv >> (8 * j)) & 0xff;
+            q.diag[j] = diag[j];
+            q.qtb[j] = s.qtf[j];
+        }
+        double stepv[N], sd[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) stepv[j] = sd[j] = 0.0;
+        bool done = pending ? false : q.lmpar_begin(delta, par, stepv, st);
+        for (int it = 0; !done && it < budget; ++it) done = q.lmpar_iter(delta, par, stepv, sd, st);
+        if (!done) return false;
+        double w3[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) w3[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double temp = -SmallLM<N>::sel(stepv, q.ipvt[j]);
+#pragma unroll
+            for (int i = 0; i <= j; ++i) w3[i] += q.r[i][j] * temp;
+        }
+        rpnorm = SmallLM<N>::nrm(w3);
+        double sq = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double p = -stepv[j];
+            xnew[j] = x[j] + p;
+            double t = diag[j] * p;
+            sq += t * t;
+        }
+        pnorm = sqrt(sq);
+        if (iter == 1) delta = fmin(delta, pnorm);
+        return true;
+    }
+    // the rolled (workspace) form of trial_begin in pieces, for kernels that spread the iterations of lmpar
+    // over several trips: lmpar_start, lmpar_step until done, then trial_point_seq
+    PFX_HD bool lmpar_start(const LaneWs& s, LmparState& st) {
+        return lmpar_begin(N, N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.wa1, s.wa2, st);
+    }
+    PFX_HD bool lmpar_step(const LaneWs& s, LmparState& st) {
+        return lmpar_iter(N, N, s.r, s.ipvt, s.diag, s.qtf, delta, par, s.step, s.sdiag, s.wa1, s.wa2, st);
+    }
+    // predicted reduction and the trial point from the step in s.step
+    PFX_HD void trial_point_seq(const LaneWs& s) {
+        for (int j = 0; j < N; ++j) s.wa1[j] = 0.0;
+        for (int j = 0; j < N; ++j) {
+            double temp = -s.step[s.ipvt[j]];
+            for (int i = 0; i <= j; ++i) s.wa1[i] += s.r[i + N * j] * temp;
+        }
+        rpnorm = enorm_seq(N, s.wa1);
+        double sq = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double p = -s.step[j];
             xnew[j] = x[j] + p;
             double t = diag[j] * p;
             sq += t * t;

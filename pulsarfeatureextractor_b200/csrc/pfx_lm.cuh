@@ -141,11 +141,21 @@ PFX_HD PFX_NOINLINE void qrsolv_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qt
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
 }
 
-// MINPACK lmpar.
+#if defined(PFX_COUNT_LMPAR) && !defined(__CUDA_ARCH__)
+static long long g_lmpar_hist8[12];
+#endif
+// MINPACK lmpar, split so that a kernel can spread the iterations of a hard sub-problem over several
+// trips (lmpar_begin, then lmpar_iter until it returns true); lmpar_seq runs them back to back.  What an
+// iteration needs from the previous one are four scalars (LmparState) and par; the vectors are rebuilt.
+struct LmparState {
+    double parl, paru, fp;
+    int iter;
+};
+// returns true when the Gauss-Newton step is accepted (par = 0): no iterations needed
 template <class RV, class IV>
-PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, double delta, double& par,
-                                   RV x, RV sdiag, RV wa1, RV wa2) {
-    const double p1 = 0.1, p001 = 0.001;
+PFX_HD PFX_NOINLINE bool lmpar_begin(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, double delta, double& par,
+                                     RV x, RV wa1, RV wa2, LmparState& st) {
+    const double p1 = 0.1;
     int nsing = n;
     PFX_ROLL
     for (int j = 0; j < n; ++j) {
@@ -164,14 +174,17 @@ PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb
     PFX_ROLL
     for (int j = 0; j < n; ++j) x[ipvt[j]] = wa1[j];
 
-    int iter = 0;
+    st.iter = 0;
     PFX_ROLL
     for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
     double dxnorm = enorm_seq(n, wa2);
     double fp = dxnorm - delta;
     if (fp <= p1 * delta) {
+#if defined(PFX_COUNT_LMPAR) && !defined(__CUDA_ARCH__)
+        if (n == 8) g_lmpar_hist8[0]++;
+#endif
         par = 0.0;
-        return;
+        return true;
     }
     double parl = 0.0;
     if (nsing >= n) {
@@ -203,37 +216,60 @@ PFX_HD PFX_NOINLINE void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb
     par = fmax(par, parl);
     par = fmin(par, paru);
     if (par == 0.0) par = gnorm / dxnorm;
+    st.parl = parl;
+    st.paru = paru;
+    st.fp = fp;
+    return false;
+}
+// one iteration; returns true when par is final (x and sdiag then hold the step and the diagonal of S)
+template <class RV, class IV>
+PFX_HD PFX_NOINLINE bool lmpar_iter(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, double delta, double& par,
+                                    RV x, RV sdiag, RV wa1, RV wa2, LmparState& st) {
+    const double p1 = 0.1, p001 = 0.001;
+    ++st.iter;
+    if (par == 0.0) par = fmax(LM_DWARF, p001 * st.paru);
+    double temp = sqrt(par);
     PFX_ROLL
-    for (;;) {
-        ++iter;
-        if (par == 0.0) par = fmax(LM_DWARF, p001 * paru);
-        double temp = sqrt(par);
+    for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
+    qrsolv_seq(n, ld, r, ipvt, wa1, qtb, x, sdiag, wa2);
+    PFX_ROLL
+    for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
+    const double dxnorm = enorm_seq(n, wa2);
+    temp = st.fp;
+    const double fp = dxnorm - delta;
+    st.fp = fp;
+    if (fabs(fp) <= p1 * delta || (st.parl == 0.0 && fp <= temp && temp < 0.0) || st.iter == 10) {
+#if defined(PFX_COUNT_LMPAR) && !defined(__CUDA_ARCH__)
+        if (n == 8) g_lmpar_hist8[st.iter]++;
+#endif
+        return true;
+    }
+    PFX_ROLL
+    for (int j = 0; j < n; ++j) {
+        int l = ipvt[j];
+        wa1[j] = diag[l] * (wa2[l] / dxnorm);
+    }
+    PFX_ROLL
+    for (int j = 0; j < n; ++j) {
+        wa1[j] = wa1[j] / sdiag[j];
+        double t = wa1[j];
         PFX_ROLL
-        for (int j = 0; j < n; ++j) wa1[j] = temp * diag[j];
-        qrsolv_seq(n, ld, r, ipvt, wa1, qtb, x, sdiag, wa2);
-        PFX_ROLL
-        for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
-        dxnorm = enorm_seq(n, wa2);
-        temp = fp;
-        fp = dxnorm - delta;
-        if (fabs(fp) <= p1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
-        PFX_ROLL
-        for (int j = 0; j < n; ++j) {
-            int l = ipvt[j];
-            wa1[j] = diag[l] * (wa2[l] / dxnorm);
-        }
-        PFX_ROLL
-        for (int j = 0; j < n; ++j) {
-            wa1[j] = wa1[j] / sdiag[j];
-            double t = wa1[j];
-            PFX_ROLL
-            for (int i = j + 1; i < n; ++i) wa1[i] -= r[i + ld * j] * t;
-        }
-        temp = enorm_seq(n, wa1);
-        double parc = ((fp / delta) / temp) / temp;
-        if (fp > 0.0) parl = fmax(parl, par);
-        if (fp < 0.0) paru = fmin(paru, par);
-        par = fmax(parl, par + parc);
+        for (int i = j + 1; i < n; ++i) wa1[i] -= r[i + ld * j] * t;
+    }
+    temp = enorm_seq(n, wa1);
+    double parc = ((fp / delta) / temp) / temp;
+    if (fp > 0.0) st.parl = fmax(st.parl, par);
+    if (fp < 0.0) st.paru = fmin(st.paru, par);
+    par = fmax(st.parl, par + parc);
+    return false;
+}
+template <class RV, class IV>
+PFX_HD inline void lmpar_seq(int n, int ld, RV r, IV ipvt, RV diag, RV qtb, double delta, double& par,
+                             RV x, RV sdiag, RV wa1, RV wa2) {
+    LmparState st;
+    if (lmpar_begin(n, ld, r, ipvt, diag, qtb, delta, par, x, wa1, wa2, st)) return;
+    PFX_ROLL
+    while (!lmpar_iter(n, ld, r, ipvt, diag, qtb, delta, par, x, sdiag, wa1, wa2, st)) {
     }
 }
 

@@ -266,3 +266,8 @@ extern "C" unsigned hs_hist_lane(const void* profile, int dtype, int m, double* 
 extern "C" void hs_pfd_params(const void* profile, int dtype, int n, double* snr, double* width) {
     pfd_params(profile, dtype, 0, n, *snr, *width);
 }
+#if defined(PFX_COUNT_LMPAR)
+extern "C" void hs_lmpar_hist(long long* out24) {
+    for (int k = 0; k < 12; ++k) { out24[k] = pfx::g_lmpar_hist[0][k]; out24[12 + k] = pfx::g_lmpar_hist8[k]; }
+}
+#endif
