@@ -31,9 +31,10 @@ namespace pfx {
 // MINPACK qrfac (pivoting) on an n x n matrix a (column major, leading dimension NPMAX), applied
 // to the triangular factor accumulated by the row rotations.  acnorm/rdiag/wa are preset by the
 // caller to the streamed column norms of the full Jacobian.
-template <class RV, class IV>
-PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, double* rdiag, double* wa) {
-    double acn0[NPMAX];      // column norms of the full Jacobian (permuted along with rdiag)
+// (rdiag, wa and the scratch vector acn0 may live in registers/local memory or in the lane's workspace)
+template <class RV, class IV, class DV>
+PFX_HD PFX_NOINLINE void qrfac_small(int n, int ld, RV a, IV ipvt, DV rdiag, DV wa, DV acn0) {
+    // acn0: column norms of the full Jacobian (permuted along with rdiag)
     PFX_ROLL
     for (int j = 0; j < n; ++j) {
         ipvt[j] = j;
@@ -880,7 +881,63 @@ struct LaneLM {
 #pragma unroll
                 for (int i = 0; i < N; ++i) s.r[i + N * j] = (i <= j) ? R[ridx(i < j ? i : j, j)] : 0.0;
         }
-        qrfac_small(N, N, s.r, s.ipvt, rdiag, wa);
+        if constexpr (N > 4) {
+            // the vectors of the factorisation in the lane's workspace (the lmpar scratch rows, idle here): as local
+            // arrays they are indexed dynamically and every access is a local-memory round trip (ncu on the final-fit
+            // kernels: two thirds of the samples of qrfac_small waiting on them)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                s.step[j] = rdiag[j];
+                s.sdiag[j] = wa[j];
+                s.wa2[j] = acnorm[j];
+            }
+            qrfac_small(N, N, s.r, s.ipvt, s.step, s.sdiag, s.wa1);
+            if (iter == 1) {
+                double sq = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    diag[j] = acnorm[j];
+                    if (acnorm[j] == 0.0) diag[j] = 1.0;
+                    double t = diag[j] * x[j];
+                    sq += t * t;
+                }
+                xnorm = sqrt(sq);
+                delta = 100.0 * xnorm;
+                if (delta == 0.0) delta = 100.0;
+            }
+            // Q^T f (unrolled: w4 stays in registers)
+            double w4[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) w4[j] = q[j];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double ajj = s.r[j + N * j];
+                if (ajj != 0.0) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = j; i < N; ++i) sum = PFX_FMA(s.r[i + N * j], w4[i], sum);
+                    double temp = -sum / ajj;
+#pragma unroll
+                    for (int i = j; i < N; ++i) w4[i] = PFX_FMA(s.r[i + N * j], temp, w4[i]);
+                }
+                s.r[j + N * j] = s.step[j];
+                s.qtf[j] = w4[j];
+            }
+            gnorm = 0.0;
+            if (fnorm != 0.0) {
+                for (int j = 0; j < N; ++j) {
+                    const int l = s.ipvt[j];
+                    const double al = s.wa2[l];
+                    if (al != 0.0) {
+                        double sum = 0.0;
+                        for (int i = 0; i <= j; ++i) sum += s.r[i + N * j] * (s.qtf[i] / fnorm);
+                        gnorm = fmax(gnorm, fabs(sum / al));
+                    }
+                }
+            }
+        } else {
+        double acn0[N];
+        qrfac_small(N, N, s.r, s.ipvt, &rdiag[0], &wa[0], &acn0[0]);
         if (N <= 4) {
             ipv = 0;
 #pragma unroll
@@ -925,6 +982,7 @@ struct LaneLM {
                     gnorm = fmax(gnorm, fabs(sum / al));
                 }
             }
+        }
         }
         }
         if (gnorm <= 0.0) {     // gtol = 0
