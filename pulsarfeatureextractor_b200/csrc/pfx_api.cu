@@ -54,6 +54,11 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
         cudaEventCreateWithFlags(&ctx->fork_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->hist_ev[i], cudaEventDisableTiming);
+        int lo_pr = 0, hi_pr = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pr, &hi_pr);
+        cudaStreamCreateWithPriority(&ctx->hi[i], cudaStreamNonBlocking, hi_pr);
+        cudaEventCreateWithFlags(&ctx->fill_ev[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->main_ev[i], cudaEventDisableTiming);
     }
     for (int i = 0; i < MAX_SUB; ++i) {
         cudaStreamCreateWithFlags(&ctx->sub[i], cudaStreamNonBlocking);
@@ -74,10 +79,14 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     else if (getenv("PFX_HYBRID") || getenv("PFX_WAVE")) ctx->gauss_slots = 0;
     ctx->final_slots = 1;      // PFX_FINAL_SLOTS=0: the lane-pair final-fit kernel
     if (const char* e = getenv("PFX_FINAL_SLOTS")) ctx->final_slots = atoi(e) != 0;
+    ctx->fill = 0;
+    if (const char* e = getenv("PFX_FILL")) ctx->fill = atoi(e);
     ctx->lmpar_budget = 2;
     if (const char* e = getenv("PFX_LMPAR_BUDGET")) ctx->lmpar_budget = atoi(e);
     ctx->hy_k = 0;
     ctx->hy_warps = 8;
+    ctx->hy_pad = 8;
+    if (const char* e = getenv("PFX_HY_PAD")) ctx->hy_pad = atoi(e);
     if (const char* e = getenv("PFX_HY_K")) ctx->hy_k = atoi(e);
     if (const char* e = getenv("PFX_HY_WARPS")) ctx->hy_warps = atoi(e);
     if (const char* e = getenv("PFX_DM_EXACT")) ctx->dm_exact = atoi(e) != 0;
@@ -103,6 +112,9 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
         cudaStreamDestroy(ctx->streams[i]);
         cudaStreamDestroy(ctx->side[i]);
         cudaStreamDestroy(ctx->side2[i]);
+        cudaStreamDestroy(ctx->hi[i]);
+        cudaEventDestroy(ctx->fill_ev[i]);
+        cudaEventDestroy(ctx->main_ev[i]);
         cudaEventDestroy(ctx->join2_ev[i]);
         cudaEventDestroy(ctx->fork_ev[i]);
         cudaEventDestroy(ctx->join_ev[i]);
@@ -394,12 +406,26 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
                 rc = set_err(ctx, PFX_ERR_CUDA, "fork of the side streams failed: %s", cudaGetErrorString(cudaGetLastError()));
             if (!rc) rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, set, 3);
             if (!rc && trace) cudaEventRecord(ctx->ev[5], sd);
+            if (ctx->fill && !trace) {
+                // The chain runs on a high-priority stream and the sinusoid kernel, cut into short blocks, is
+                // released when the histogram stage is done: the block scheduler serves the chain's kernels
+                // first, so the sinusoid blocks land on the SMs the tails of the Gaussian kernels leave idle.
+                cudaStream_t hs = ctx->hi[par];
+                cudaStreamWaitEvent(hs, ctx->fork_ev[par], 0);
+                if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, set, 4);
+                if (!rc) rc = launch_hist_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, hs, set, ctx->fill_ev[par], &launches);
+                cudaEventRecord(ctx->main_ev[par], hs);
+                cudaStreamWaitEvent(sd2, ctx->fill_ev[par], 0);
+                if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0, ctx->fill > 1 ? ctx->fill : 64);
+                cudaStreamWaitEvent(st, ctx->main_ev[par], 0);
+            } else {
             if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0);
             if (!rc && trace) cudaEventRecord(ctx->ev[2], sd2);
             if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, set, 4);
             if (!rc) rc = launch_hist_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, st, set,
                                             trace ? ctx->ev[3] : nullptr, &launches);
             if (!rc && trace) cudaEventRecord(ctx->ev[4], st);
+            }
             cudaEventRecord(ctx->join_ev[par], sd);
             cudaStreamWaitEvent(st, ctx->join_ev[par], 0);
             cudaEventRecord(ctx->join2_ev[par], sd2);

@@ -66,7 +66,11 @@ struct pfx_ctx {
     int n_grid_cache;
     int hist_u8;              // 1: warp-cooperative histogram set-up for uint8 profiles of <= 128 bins (default)
     int gauss_wave;           // 1: wave form of the rounds kernel (state in global memory, phases per block)
+    int hy_pad;               // elements between the data vectors of neighbouring slots beyond the bins (bank spread)
     int hy_k, hy_warps;       // hybrid rounds kernel: candidates per warp (32: first layout, 0: as many as fit), warps per block
+    int fill;                 // 1: main chain on a high-priority stream, sinusoid kernel in short blocks behind the histogram stage
+    cudaStream_t hi[2];
+    cudaEvent_t fill_ev[2], main_ev[2];
     int lmpar_budget;         // block-synchronous kernels: lmpar iterations per trip (<= 0: no limit)
     int final_slots;          // 1: block-synchronous final-fit kernel, 0: lane-pair kernel
     int gauss_slots;          // 1: block-synchronous hybrid kernel (phases of a trip are block-wide)
@@ -136,7 +140,7 @@ __device__ __forceinline__ long long next_candidate(const G& g, u64* counter) {
 
 // launchers, one per translation unit
 int launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                    int64_t ld, int8_t* ier, cudaStream_t st, pfx_scratch_set* set, int ck);
+                    int64_t ld, int8_t* ier, cudaStream_t st, pfx_scratch_set* set, int ck, int chunk = 0);
 int launch_hist(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
                 int64_t ld, int8_t* ier, int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck);
 int launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,

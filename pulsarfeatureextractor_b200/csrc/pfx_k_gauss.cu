@@ -1162,7 +1162,7 @@ static bool hybrid_layout(pfx_ctx* ctx, int m, int k_req, int* threads, size_t* 
 
 // block-synchronous kernel: eight warps, as many candidates per warp as fit (at most k_req; 0: at most 24)
 static bool slots_layout(pfx_ctx* ctx, int m, int k_req, int* threads, size_t* smem, int* slots_out, int* pitch, int* k_out) {
-    *pitch = align_up(m, 8) + 8;
+    *pitch = align_up(m, 8) + ctx->hy_pad;
     const size_t budget = (size_t)ctx->smem_optin;
     const int warps = ctx->hy_warps > 0 ? ctx->hy_warps : 8;
     const int kmax = k_req > 0 ? (k_req < 32 ? k_req : 32) : 24;

@@ -15,8 +15,15 @@ constexpr int SIN_LANES = PFX_SIN_LANES;      // lanes per candidate (LaneGroup)
 
 __global__ void __launch_bounds__(128, 3)
 k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
-           int8_t* ier, u64* counter) {
+           int8_t* ier, u64* counter, int chunk) {
     extern __shared__ double smem[];
+    // chunk > 0: the block owns candidates [blockIdx.x * chunk, + chunk) (short-lived blocks that the block
+    // scheduler can place in the gaps other kernels leave, see score_dev_impl); else one global work queue
+    __shared__ int s_ctr;
+    if (threadIdx.x == 0) s_ctr = 0;
+    __syncthreads();
+    const long long base = chunk > 0 ? (long long)blockIdx.x * chunk : 0;
+    const long long limit = chunk > 0 ? ((base + chunk < n) ? base + chunk : n) : n;
     LaneWs ws;
     ws.carve(smem + threadIdx.x, blockDim.x, 2);
     typedef LaneGroup<SIN_LANES> G;
@@ -38,9 +45,9 @@ k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, doub
             }
             if (more) {
                 long long c = 0;
-                if (G::rank() == 0) c = (long long)atomicAdd(counter, 1ULL);
+                if (G::rank() == 0) c = chunk > 0 ? base + atomicAdd(&s_ctr, 1) : (long long)atomicAdd(counter, 1ULL);
                 c = G::bcast(c);
-                if (c < n) g.start(profile, dtype, c, m);
+                if (c < limit) g.start(profile, dtype, c, m);
                 else more = false;
             }
         }
@@ -52,7 +59,7 @@ k_sinusoid(const void* __restrict__ profile, int dtype, long long n, int m, doub
 }  // namespace
 
 int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile, double* feat,
-                         int64_t ld, int8_t* ier, cudaStream_t st, pfx_scratch_set* set, int ck) {
+                         int64_t ld, int8_t* ier, cudaStream_t st, pfx_scratch_set* set, int ck, int chunk) {
     if (s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "nbin < 2");
     // one warp per block: a block leaves when its 32 lanes are done, so the tail of slow candidates
     // holds little shared memory and the Gaussian kernels' blocks fit next to it
@@ -63,8 +70,9 @@ int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void
     if (rc) return rc;
     const int per_block = threads / SIN_LANES;
     if ((long long)grid * per_block > n) grid = (int)((n + per_block - 1) / per_block);
+    if (chunk > 0) grid = (int)((n + chunk - 1) / chunk);
     k_sinusoid<<<grid, threads, smem, st>>>(profile, s->dtype, n, s->nbin, feat, ld, ier,
-                                             take_counter(set, ck, st));
+                                             take_counter(set, ck, st), chunk);
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }
