@@ -494,7 +494,7 @@ def main():
             # duration of the dominant kernel pair
             achieved = n * (b_in + b_out) / (gauss_ms / 1000.0) / 1e9 if gauss_ms > 0 else step_gbs
             line["roofline"] = {
-                "bound": "hbm", "kernel": "k_gauss_rounds + k_gauss_final (scores 8-11, 10 LM solves per candidate)",
+                "bound": "hbm", "kernel": "k_gauss_rounds_s + k_gauss_final_s (scores 8-11, 10 LM solves per candidate)",
                 "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": n * traffic,
                 "kernel_ms": gauss_ms, "kernel_share_of_step": gauss_ms / (ms_dev / args.steps) if gauss_ms else None,
@@ -503,13 +503,13 @@ def main():
                         "per candidate in this kernel pair), so its HBM fraction is tiny by construction: see "
                         "roofline_fp64 for the pipe that bounds it and roofline_lyon for the HBM-bound kernel of the "
                         "path.  traffic: ncu dram read+write per candidate (%s)"
-                        % prof_g.get("source", "profiles/r01_gauss_final_build_summary.csv")}
+                        % prof_g.get("source", "profiles/r02_fp64_ops.csv")}
             flops = read_json("profiles/r02_fp64_flops.json")
             if flops and gauss_ms > 0 and name in ("htru100k", "target10m"):
                 per_cand = flops["gauss_pair_fp64_flop_per_candidate"]
                 ach = n * per_cand / (gauss_ms / 1000.0) / 1e12
                 line["roofline_fp64"] = {
-                    "bound": "fp64", "kernel": "k_gauss_rounds + k_gauss_final", "achieved": ach,
+                    "bound": "fp64", "kernel": "k_gauss_rounds_s + k_gauss_final_s", "achieved": ach,
                     "peak": FP64_PEAK_TFLOPS, "peak_kind": "measured DFMA micro-benchmark (profiles/r01_fp64_microbench.txt)",
                     "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "flop_per_candidate": per_cand,
                     "kernel_ms": gauss_ms,
