@@ -319,10 +319,21 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the
+        # one JSON line (file descriptor 1 points at stderr until the first collective is through)
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(keep, 1)
+            os.close(keep)
     name = args.config
     c = CONFIGS[name]
     total = args.total or (c["total"] if not args.n else 0)
