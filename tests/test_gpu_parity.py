@@ -613,6 +613,40 @@ def test_dm_fit_lane_form_knob(eng):
         assert np.mean(_rel(f1[ok, c], f0[ok, c]) <= 1e-6) >= 0.75, c + 1
 
 
+def test_gaussian_kernels_do_not_depend_on_scheduling(eng, monkeypatch):
+    """The block-synchronous kernels of scores 8-11 deal the rows of a fit to eight lanes by row index only:
+    how many candidates a warp owns, how many lmpar iterations run per trip, and whether the phases of a
+    trip are block-wide (k_gauss_rounds_s) or per warp (the hybrid kernel it grew out of) must not change
+    a bit of the result.  The lane-pair final-fit kernel merges two factors instead of eight: scores 10, 11
+    differ from it by re-association only, everything else is identical."""
+    from pulsarfeatureextractor_b200.engine import Engine
+    b = synth.generate(43, 0, 3000)
+    knobs = ("PFX_SLOTS", "PFX_HYBRID", "PFX_WAVE", "PFX_HY_K", "PFX_LMPAR_BUDGET", "PFX_FINAL_SLOTS", "PFX_FILL")
+
+    def run(env):
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = Engine(0)          # the knobs are read when the context is created
+        try:
+            return _dev(e, b)
+        finally:
+            e.close()
+            for k in env:
+                monkeypatch.delenv(k, raising=False)
+
+    f0, s0, i0 = _dev(eng, b)
+    for env in ({"PFX_HY_K": "9"}, {"PFX_LMPAR_BUDGET": "10"}, {"PFX_HYBRID": "1", "PFX_HY_K": "32"}, {"PFX_FILL": "1"}):
+        f, s_, i_ = run(env)
+        assert np.array_equal(f, f0, equal_nan=True) and np.array_equal(s_, s0) and np.array_equal(i_, i0), env
+    f, s_, i_ = run({"PFX_FINAL_SLOTS": "0"})
+    cols = [c for c in range(30) if c not in (9, 10)]
+    assert np.array_equal(f[:, cols], f0[:, cols], equal_nan=True) and np.array_equal(s_, s0)
+    ok = (s0 & O.ST_FAIL_MASK) == 0
+    assert np.mean(_rel(f0[ok, 10], f[ok, 10]) <= 1e-6) >= 0.6       # (the oracle's own twins agree on 72 %)
+
+
 def test_superb_golden(eng):
     """SUPERB candidates (64-bin, section 0; SUPERBPHCXFile.py:80,102-113,242) against the outputs of
     the reference's own SUPERBPHCX class (tests/golden/ref_superb_v1.npz)."""
