@@ -57,6 +57,13 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
         int lo_pr = 0, hi_pr = 0;
         cudaDeviceGetStreamPriorityRange(&lo_pr, &hi_pr);
         cudaStreamCreateWithPriority(&ctx->hi[i], cudaStreamNonBlocking, hi_pr);
+        {
+            // stream of the final-fit kernel when it runs next to the rounds kernel (PFX_PIPE_PRIO=0: lowest priority)
+            const char* pe = getenv("PFX_PIPE_PRIO");
+            cudaStreamCreateWithPriority(&ctx->pf[i], cudaStreamNonBlocking, (pe && atoi(pe) == 0) ? lo_pr : hi_pr);
+        }
+        cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->pipe_done_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->fill_ev[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->main_ev[i], cudaEventDisableTiming);
     }
@@ -81,6 +88,10 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     if (const char* e = getenv("PFX_FINAL_SLOTS")) ctx->final_slots = atoi(e) != 0;
     ctx->fill = 0;
     if (const char* e = getenv("PFX_FILL")) ctx->fill = atoi(e);
+    ctx->pipe = 1;             // PFX_PIPE=0: the final-fit kernel starts when the rounds kernel has ended
+    if (const char* e = getenv("PFX_PIPE")) ctx->pipe = atoi(e) != 0;
+    ctx->chain_on_hi = 0;
+    ctx->chain_par = 0;
     ctx->lmpar_budget = 2;
     if (const char* e = getenv("PFX_LMPAR_BUDGET")) ctx->lmpar_budget = atoi(e);
     ctx->hy_k = 0;
@@ -102,7 +113,7 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     cudaFree(ctx->counters);
     for (int i = 0; i < N_SETS; ++i) {
         pfx_scratch_set& t = ctx->sets[i];
-        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp, &t.wave_state, &t.wave_ws, &t.wave_list};
+        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp, &t.wave_state, &t.wave_ws, &t.wave_list, &t.ready};
         for (pfx_buf* b : bufs)
             if (b->p) cudaFree(b->p);
         cudaEventDestroy(t.done);
@@ -113,6 +124,9 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
         cudaStreamDestroy(ctx->side[i]);
         cudaStreamDestroy(ctx->side2[i]);
         cudaStreamDestroy(ctx->hi[i]);
+        cudaStreamDestroy(ctx->pf[i]);
+        cudaEventDestroy(ctx->pipe_ev[i]);
+        cudaEventDestroy(ctx->pipe_done_ev[i]);
         cudaEventDestroy(ctx->fill_ev[i]);
         cudaEventDestroy(ctx->main_ev[i]);
         cudaEventDestroy(ctx->join2_ev[i]);
@@ -337,6 +351,7 @@ static int launch_hist_gauss(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, co
         return launch_gauss(ctx, shape, n, profile, feat, ld, ier, status, st, set, 2);
     }
     const int par = ctx->fork_rr & 1;
+    ctx->chain_on_hi = 0;        // (sub-batches run on streams of their own: no hand-over between the Gaussian kernels)
     cudaEventRecord(ctx->hist_ev[par], st);
     const size_t es = elem_size(shape->dtype);
     for (int k = 0; k < nsub; ++k) {
@@ -406,17 +421,21 @@ static int score_dev_impl(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, uint3
                 rc = set_err(ctx, PFX_ERR_CUDA, "fork of the side streams failed: %s", cudaGetErrorString(cudaGetLastError()));
             if (!rc) rc = launch_dmfit(ctx, shape, n, dmcurve, params, feat, feat_ld, ier, status, sd, set, 3);
             if (!rc && trace) cudaEventRecord(ctx->ev[5], sd);
-            if (ctx->fill && !trace) {
+            if ((ctx->fill || (ctx->pipe && !ctx->pipe_suspend)) && !trace) {
                 // The chain runs on a high-priority stream and the sinusoid kernel, cut into short blocks, is
                 // released when the histogram stage is done: the block scheduler serves the chain's kernels
                 // first, so the sinusoid blocks land on the SMs the tails of the Gaussian kernels leave idle.
                 cudaStream_t hs = ctx->hi[par];
                 cudaStreamWaitEvent(hs, ctx->fork_ev[par], 0);
                 if (!rc) rc = launch_subband(ctx, shape, n, profile, subbands, params, feat, feat_ld, status, sd, set, 4);
+                if (!ctx->fill && !rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0);
+                ctx->chain_on_hi = 1;
+                ctx->chain_par = par;
                 if (!rc) rc = launch_hist_gauss(ctx, shape, n, profile, feat, feat_ld, ier, status, hs, set, ctx->fill_ev[par], &launches);
+                ctx->chain_on_hi = 0;
                 cudaEventRecord(ctx->main_ev[par], hs);
-                cudaStreamWaitEvent(sd2, ctx->fill_ev[par], 0);
-                if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0, ctx->fill > 1 ? ctx->fill : 64);
+                if (ctx->fill) cudaStreamWaitEvent(sd2, ctx->fill_ev[par], 0);
+                if (ctx->fill && !rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0, ctx->fill > 1 ? ctx->fill : 64);
                 cudaStreamWaitEvent(st, ctx->main_ev[par], 0);
             } else {
             if (!rc) rc = launch_sinusoid(ctx, shape, n, profile, feat, feat_ld, ier, sd2, set, 0);
@@ -615,9 +634,13 @@ extern "C" int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, u
         if (lyon)
             PFX_TRY(cudaMemcpyAsync(base + L.dmstat, (const char*)dmstat + (size_t)done * shape->n_dmstat * ess,
                                     (size_t)cn * shape->n_dmstat * ess, cudaMemcpyHostToDevice, st));
+        // (several chunks in flight: the hand-over between the Gaussian kernels is left out -- with the next chunk's
+        // kernels arriving behind it, it measured 3 % slower end to end; a batch of one chunk keeps it)
+        ctx->pipe_suspend = n > chunk;
         rc = score_dev_impl(ctx, shape, cn, features, base + L.profile, base + L.subbands, base + L.dmcurve,
                             base + L.dmstat, (const double*)(base + L.params), (double*)(base + L.feat), ncol,
                             bates && ier ? (int8_t*)(base + L.ier) : nullptr, (int32_t*)(base + L.status), st, 0);
+        ctx->pipe_suspend = 0;
         if (rc) goto out;
         launches += ctx->last_launches;
         if (feat_ld == ncol) {

@@ -42,6 +42,7 @@ struct pfx_scratch_set {
     pfx_buf lane[2];          // per-lane data vectors of the Gaussian lane kernels (long profiles)
     pfx_buf wave_state, wave_ws, wave_list;   // wave form of the rounds kernel: fit state, n x n workspaces, active lists
     pfx_buf hist_lane;        // per-lane arrays of k_hist_lane
+    pfx_buf ready;            // candidates the rounds kernel has finished, in order of completion (hand-over to the final fit)
     pfx_buf ovf;              // candidates whose histogram overflowed the per-lane capacity
     pfx_buf hist_warp;        // global histogram slots of the warp-form kernel
     cudaEvent_t done;
@@ -68,6 +69,11 @@ struct pfx_ctx {
     int gauss_wave;           // 1: wave form of the rounds kernel (state in global memory, phases per block)
     int hy_pad;               // elements between the data vectors of neighbouring slots beyond the bins (bank spread)
     int hy_k, hy_warps;       // hybrid rounds kernel: candidates per warp (32: first layout, 0: as many as fit), warps per block
+    int pipe;                 // 1: the final-fit kernel runs next to the rounds kernel and takes candidates as they finish
+    int pipe_suspend;         // set by pfx_score_host while a batch of several chunks is in flight
+    int chain_on_hi, chain_par;   // set by score_dev_impl around the chain: it runs on hi[chain_par]
+    cudaStream_t pf[2];
+    cudaEvent_t pipe_ev[2], pipe_done_ev[2];
     int fill;                 // 1: main chain on a high-priority stream, sinusoid kernel in short blocks behind the histogram stage
     cudaStream_t hi[2];
     cudaEvent_t fill_ev[2], main_ev[2];

@@ -336,6 +336,24 @@ k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m
 //     ws[HY_WSN][slots] | stg[20][threads] | nrows[slots], list[2][slots] int | dat[slot][pitch] | xs[slot][pitch]
 constexpr int SL_MAXT = 256;
 
+// ---- hand-over of finished candidates from the rounds kernel to the final-fit kernel --------------------
+// Both kernels end in a tail set by their slowest candidates (34 and 42 ms at 100 000 candidates), and a kernel
+// boundary between them puts the two tails in series.  With the hand-over the final-fit kernel is launched next
+// to the rounds kernel (lower stream priority, so the rounds kernel's blocks are placed first): its blocks
+// start on the SMs the rounds kernel's blocks leave and take candidates from a list the rounds kernel appends
+// to as candidates finish.  Producer: carry record, fence, slot of the list (initialised to -1).  Consumer:
+// an owner holds a ticket (its position in the list) and polls it once per trip, never blocking its block;
+// when the last block of the rounds kernel has left, `done` holds the final count + 1.
+struct PipeOut {
+    int* list;              // nullptr: no hand-over (the final-fit kernel runs after the rounds kernel)
+    u64 *produced, *exited, *done;
+};
+struct PipeIn {
+    const int* list;
+    u64* taken;
+    const u64* done;
+};
+
 // Set-up and close of a fit as block-wide TASKS: run by the owner's warp (as in the hybrid kernel) they
 // serialise inside that warp, and a trip waits for the warp with the most fits ending (ncu: 11.5 % of all
 // samples at the barrier after the owners' phase).  Owners instead post a record in the idle workspace of
@@ -348,7 +366,7 @@ static_assert(SR_NR < HY_WSN, "task record exceeds the slot workspace");
 __global__ void __launch_bounds__(SL_MAXT, 1)
 k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
                  int8_t* ier, int32_t* status, u64* counter, GaussCarry* carry, double* gdat,
-                 unsigned short* gxs, int pitch, int K, int lmpar_budget) {
+                 unsigned short* gxs, int pitch, int K, int lmpar_budget, PipeOut po) {
     extern __shared__ double smem[];
     __shared__ int s_cnt[3], s_next[3];
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -419,7 +437,15 @@ k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m
                 if (st_fin < 8) op = 1;          // (the close of the last round has no pass over the data)
             }
             if (g.phase == GP_IDLE) {
-                if (g.cand >= 0) flush_rounds(g, feat, ld, ier, status, carry);
+                if (g.cand >= 0) {
+                    const long long cf = g.cand;
+                    flush_rounds(g, feat, ld, ier, status, carry);
+                    if (po.list && !carry[cf].skip) {      // hand the candidate to the final-fit kernel
+                        __threadfence();
+                        const u64 pos = atomicAdd(po.produced, 1ULL);
+                        ((volatile int*)po.list)[pos] = (int)cf;
+                    }
+                }
                 if (more) {
                     const long long c = (long long)atomicAdd(counter, 1ULL);
                     if (c < n) {
@@ -548,6 +574,18 @@ k_gauss_rounds_s(const void* __restrict__ profile, int dtype, long long n, int m
         if (tid == 0) {
             s_cnt[1] = 0;
             s_next[1] = 0;
+        }
+    }
+    if (po.list) {
+        // the last block to leave publishes the final count (every list entry is visible before it)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(po.exited, 1ULL) == (u64)gridDim.x - 1) {
+                const u64 total = atomicAdd(po.produced, 0ULL);
+                __threadfence();
+                *(volatile u64*)po.done = total + 1;
+            }
         }
     }
 }
@@ -861,8 +899,8 @@ typedef Gauss8LaneT<FS_GROUP> G8;
 
 __global__ void __launch_bounds__(FS_MAXT, 1)
 k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m, double* feat, long long ld,
-                int8_t* ier, u64* counter, const GaussCarry* __restrict__ carry, double* gdat, int pitch, int K,
-                int lmpar_budget) {
+                int8_t* ier, u64* counter, const GaussCarry* carry, double* gdat, int pitch, int K,
+                int lmpar_budget, PipeIn pin) {
     extern __shared__ double smem[];
     __shared__ int s_cnt[3], s_next[3];
     const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -884,6 +922,7 @@ k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m,
     long long cand = -1;
     int phase = GP_IDLE;
     bool more = owner, istr = false, lpend = false;
+    long long ticket = -1;       // hand-over mode: this owner's position in the list of finished candidates
     LmparState lst;
     lst.parl = lst.paru = lst.fp = 0.0;
     lst.iter = 0;
@@ -921,25 +960,39 @@ k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m,
                 phase = GP_IDLE;
             }
             if (phase == GP_IDLE && more) {
-                // candidates the rounds kernel finished itself (failure, sentinel) are skipped
-                for (;;) {
-                    const long long c = (long long)atomicAdd(counter, 1ULL);
-                    if (c >= n) {
-                        more = false;
-                        break;
-                    }
-                    if (!carry[c].skip) {
+                if (pin.list) {
+                    // hand-over: poll this owner's ticket once per trip (never block the block)
+                    if (ticket < 0) ticket = (long long)atomicAdd(pin.taken, 1ULL);
+                    const int c = (ticket < n) ? ((const volatile int*)pin.list)[ticket] : -1;
+                    if (c >= 0) {
+                        __threadfence();
                         cand = c;
-                        break;
+                        ticket = -1;
+                    } else {
+                        const u64 d = *(const volatile u64*)pin.done;
+                        if (d != 0 && (u64)ticket >= d - 1) more = false;      // the rounds kernel is done and the list is shorter
+                    }
+                } else {
+                    // candidates the rounds kernel finished itself (failure, sentinel) are skipped
+                    for (;;) {
+                        const long long c = (long long)atomicAdd(counter, 1ULL);
+                        if (c >= n) {
+                            more = false;
+                            break;
+                        }
+                        if (!carry[c].skip) {
+                            cand = c;
+                            break;
+                        }
                     }
                 }
                 if (cand >= 0) {
-                    const GaussCarry& cy = carry[cand];
+                    const double* cy = (const double*)(carry + cand);      // p_t1[4] | p1[4] | p2[4] | ...
                     double x0[8];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        x0[k] = cy.p1[k];
-                        x0[4 + k] = cy.p2[k];
+                        x0[k] = __ldcg(cy + 4 + k);
+                        x0[4 + k] = __ldcg(cy + 8 + k);
                     }
                     lm.init(x0);
 #pragma unroll
@@ -961,6 +1014,11 @@ k_gauss_final_s(const void* __restrict__ profile, int dtype, long long n, int m,
         const bool isjac = phase == GP_JAC;
         if (isjac) list0[atomicAdd(&s_cnt[0], 1)] = slot;
         if (!__syncthreads_or((phase != GP_IDLE || more || op) ? 1 : 0)) break;
+        if (pin.list && s_cnt[0] == 0 && s_cnt[2] == 0 && !__syncthreads_or(phase == GP_TRIAL ? 1 : 0)) {
+            // nothing to do yet (the rounds kernel has not finished a candidate for this block): wait a little
+            __nanosleep(2000);
+            continue;
+        }
         // ---- tasks (a warp each), then the rows of the Jacobian passes ----
         {
             const int F = s_cnt[2];
@@ -1242,6 +1300,9 @@ static int gauss_plan(pfx_ctx* ctx, pfx_scratch_set* set, int m, int64_t n, Gaus
     }
     if (rc) return rc;
     p->final_pitch = m;
+    if (ctx->pipe && ctx->gauss_slots && ctx->final_slots && !ctx->gauss_wave) {
+        if ((rc = ensure_buf(ctx, &set->ready, (size_t)(n > 0 ? n : 1) * sizeof(int)))) return rc;
+    }
     if (ctx->final_slots) {
         p->in_smem[1] = final_slots_layout(ctx, m, &p->threads[1], &p->smem[1], &p->per_block[1], &p->final_pitch, &p->final_k);
         rc = persistent_grid(ctx, k_gauss_final_s, p->threads[1], p->smem[1], &p->grid[1]);
@@ -1280,6 +1341,11 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     GaussCarry* carry = (GaussCarry*)set->carry.p;
     double* gdat = nullptr;
     unsigned short* gxs = nullptr;
+    // hand-over of finished candidates to the final-fit kernel (see PipeOut): only when the chain runs on the
+    // context's high-priority stream, so that the rounds kernel's blocks are placed before the final-fit kernel's
+    const bool piped = ctx->pipe && ctx->chain_on_hi && ctx->gauss_slots && ctx->final_slots && !ctx->gauss_wave && n > 0;
+    PipeOut po = {nullptr, nullptr, nullptr, nullptr};
+    PipeIn pin = {nullptr, nullptr, nullptr};
     if (!p.in_smem[0] && !ctx->gauss_wave) {
         rc = lane_scratch(ctx, &set->lane[0], (size_t)p.grid[0] * p.per_block[0], p.pitch, &gdat, &gxs);
         if (rc) return rc;
@@ -1295,10 +1361,23 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
         wb.cap = (int)((n + p.grid[0] - 1) / p.grid[0]);
         k_gauss_wave<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status, carry, wb,
                                                                   p.smem[0] == wave_smem_bytes(p.pitch, true) ? 1 : 0);
-    } else if (ctx->gauss_slots)
+    } else if (ctx->gauss_slots) {
+        if (piped) {
+            // list of finished candidates (-1 = not yet), counters; the final-fit kernel may start once they are set
+            cudaMemsetAsync(set->ready.p, 0xff, (size_t)n * sizeof(int), st);
+            po.list = (int*)set->ready.p;
+            po.produced = take_counter(set, 8, st);
+            pin.taken = take_counter(set, 9, st);
+            po.exited = take_counter(set, 10, st);
+            po.done = take_counter(set, 11, st);
+            pin.list = po.list;
+            pin.done = po.done;
+            cudaEventRecord(ctx->pipe_ev[ctx->chain_par], st);
+        }
         k_gauss_rounds_s<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                                       take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k,
-                                                                      ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10);
+                                                                      ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, po);
+    }
     else if (ctx->gauss_hybrid)
         k_gauss_rounds_h<<<p.grid[0], p.threads[0], p.smem[0], st>>>(profile, s->dtype, n, m, feat, ld, ier, status,
                                                                       take_counter(set, ck, st), carry, gdat, gxs, p.pitch, p.hy_k);
@@ -1312,10 +1391,29 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
         rc = lane_scratch(ctx, &set->lane[1], (size_t)p.grid[1] * p.per_block[1], p.final_pitch, &gdat, &gxs);
         if (rc) return rc;
     }
-    if (ctx->final_slots)
+    if (ctx->final_slots && piped) {
+        // next to the rounds kernel, on a stream of default (lower) priority; a few SMs are never taken by it, so
+        // the rounds kernel makes progress whatever order the block scheduler chooses
+        cudaStream_t sf = ctx->pf[ctx->chain_par];
+        cudaStreamWaitEvent(sf, ctx->pipe_ev[ctx->chain_par], 0);
+        int gridf = p.grid[1];
+        if (gridf > ctx->sm_count - 8) gridf = ctx->sm_count - 8;
+        if (gridf < 1) gridf = 1;
+        k_gauss_final_s<<<gridf, p.threads[1], p.smem[1], sf>>>(profile, s->dtype, n, m, feat, ld, ier, nullptr, carry, gdat,
+                                                                p.final_pitch, p.final_k,
+                                                                ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
+        cudaEventRecord(ctx->pipe_done_ev[ctx->chain_par], sf);
+        // the SMs held back above join in once the rounds kernel has ended (same list, same tickets)
+        if (p.grid[1] > gridf)
+            k_gauss_final_s<<<p.grid[1] - gridf, p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier, nullptr, carry,
+                                                                                gdat ? gdat + (size_t)gridf * p.per_block[1] * p.final_pitch : nullptr,
+                                                                                p.final_pitch, p.final_k,
+                                                                                ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
+        cudaStreamWaitEvent(st, ctx->pipe_done_ev[ctx->chain_par], 0);
+    } else if (ctx->final_slots)
         k_gauss_final_s<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
                                                                      take_counter(set, ck + 4, st), carry, gdat, p.final_pitch, p.final_k,
-                                                                     ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10);
+                                                                     ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
     else
         k_gauss_final<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
                                                                    take_counter(set, ck + 4, st), carry, gdat, gxs);

@@ -621,7 +621,7 @@ def test_gaussian_kernels_do_not_depend_on_scheduling(eng, monkeypatch):
     differ from it by re-association only, everything else is identical."""
     from pulsarfeatureextractor_b200.engine import Engine
     b = synth.generate(43, 0, 3000)
-    knobs = ("PFX_SLOTS", "PFX_HYBRID", "PFX_WAVE", "PFX_HY_K", "PFX_LMPAR_BUDGET", "PFX_FINAL_SLOTS", "PFX_FILL")
+    knobs = ("PFX_SLOTS", "PFX_HYBRID", "PFX_WAVE", "PFX_HY_K", "PFX_LMPAR_BUDGET", "PFX_FINAL_SLOTS", "PFX_FILL", "PFX_PIPE")
 
     def run(env):
         for k in knobs:
@@ -637,7 +637,8 @@ def test_gaussian_kernels_do_not_depend_on_scheduling(eng, monkeypatch):
                 monkeypatch.delenv(k, raising=False)
 
     f0, s0, i0 = _dev(eng, b)
-    for env in ({"PFX_HY_K": "9"}, {"PFX_LMPAR_BUDGET": "10"}, {"PFX_HYBRID": "1", "PFX_HY_K": "32"}, {"PFX_FILL": "1"}):
+    # (PFX_PIPE=0: the final-fit kernel after the rounds kernel instead of next to it, fed through the hand-over list)
+    for env in ({"PFX_HY_K": "9"}, {"PFX_LMPAR_BUDGET": "10"}, {"PFX_HYBRID": "1", "PFX_HY_K": "32"}, {"PFX_FILL": "1"}, {"PFX_PIPE": "0"}):
         f, s_, i_ = run(env)
         assert np.array_equal(f, f0, equal_nan=True) and np.array_equal(s_, s0) and np.array_equal(i_, i0), env
     f, s_, i_ = run({"PFX_FINAL_SLOTS": "0"})
