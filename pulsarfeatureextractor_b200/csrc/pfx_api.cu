@@ -113,7 +113,7 @@ extern "C" void pfx_destroy(pfx_ctx* ctx) {
     cudaFree(ctx->counters);
     for (int i = 0; i < N_SETS; ++i) {
         pfx_scratch_set& t = ctx->sets[i];
-        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp, &t.wave_state, &t.wave_ws, &t.wave_list, &t.ready};
+        pfx_buf* bufs[] = {&t.carry, &t.lane[0], &t.lane[1], &t.hist_lane, &t.ovf, &t.hist_warp, &t.wave_state, &t.wave_ws, &t.wave_list, &t.ready, &t.sub_scratch};
         for (pfx_buf* b : bufs)
             if (b->p) cudaFree(b->p);
         cudaEventDestroy(t.done);
@@ -347,8 +347,9 @@ static int launch_hist_gauss(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, co
     if (after_hist) cudaEventRecord(after_hist, st);
     const int nsub = pick_subbatches(ctx, n);
     if (nsub <= 1) {
-        *launches += 2;
-        return launch_gauss(ctx, shape, n, profile, feat, ld, ier, status, st, set, 2);
+        const int rcg = launch_gauss(ctx, shape, n, profile, feat, ld, ier, status, st, set, 2);
+        *launches += ctx->gauss_launches;
+        return rcg;
     }
     const int par = ctx->fork_rr & 1;
     ctx->chain_on_hi = 0;        // (sub-batches run on streams of their own: no hand-over between the Gaussian kernels)
@@ -498,6 +499,7 @@ extern "C" int pfx_reserve(pfx_ctx* ctx, const pfx_shape* shape, int64_t n_max) 
     for (int i = 0; i < N_SETS; ++i) {
         rc = reserve_hist(ctx, &ctx->sets[i], shape, n_max);
         if (!rc) rc = reserve_gauss(ctx, &ctx->sets[i], shape, n_max);
+        if (!rc) rc = reserve_subband(ctx, &ctx->sets[i], shape);
         if (rc) return rc;
     }
     ctx->reserved = true;

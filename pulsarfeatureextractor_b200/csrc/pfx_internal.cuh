@@ -42,6 +42,7 @@ struct pfx_scratch_set {
     pfx_buf lane[2];          // per-lane data vectors of the Gaussian lane kernels (long profiles)
     pfx_buf wave_state, wave_ws, wave_list;   // wave form of the rounds kernel: fit state, n x n workspaces, active lists
     pfx_buf hist_lane;        // per-lane arrays of k_hist_lane
+    pfx_buf sub_scratch;      // box-car sums of the sub-band kernel for long profiles (per warp)
     pfx_buf ready;            // candidates the rounds kernel has finished, in order of completion (hand-over to the final fit)
     pfx_buf ovf;              // candidates whose histogram overflowed the per-lane capacity
     pfx_buf hist_warp;        // global histogram slots of the warp-form kernel
@@ -70,6 +71,7 @@ struct pfx_ctx {
     int hy_pad;               // elements between the data vectors of neighbouring slots beyond the bins (bank spread)
     int hy_k, hy_warps;       // hybrid rounds kernel: candidates per warp (32: first layout, 0: as many as fit), warps per block
     int pipe;                 // 1: the final-fit kernel runs next to the rounds kernel and takes candidates as they finish
+    int gauss_launches;       // kernels the last launch_gauss started (2, or 3 with the hand-over's held-back blocks)
     int pipe_suspend;         // set by pfx_score_host while a batch of several chunks is in flight
     int chain_on_hi, chain_par;   // set by score_dev_impl around the chain: it runs on hi[chain_par]
     cudaStream_t pf[2];
@@ -163,6 +165,7 @@ int launch_pfd_params(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
                       cudaStream_t st);
 // size the scratch of a set for n candidates of this shape (what the launchers would grow lazily)
 int reserve_hist(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, int64_t n);
+int reserve_subband(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s);
 int reserve_gauss(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, int64_t n);
 int launch_fill_nan(pfx_ctx* ctx, double* feat, int64_t n, int64_t ld, int ncol, cudaStream_t st);
 

@@ -1338,6 +1338,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
     GaussPlan p;
     int rc = gauss_plan(ctx, set, m, n, &p);
     if (rc) return rc;
+    ctx->gauss_launches = 2;
     GaussCarry* carry = (GaussCarry*)set->carry.p;
     double* gdat = nullptr;
     unsigned short* gxs = nullptr;
@@ -1404,6 +1405,7 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
                                                                 ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
         cudaEventRecord(ctx->pipe_done_ev[ctx->chain_par], sf);
         // the SMs held back above join in once the rounds kernel has ended (same list, same tickets)
+        if (p.grid[1] > gridf) ctx->gauss_launches = 3;
         if (p.grid[1] > gridf)
             k_gauss_final_s<<<p.grid[1] - gridf, p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier, nullptr, carry,
                                                                                 gdat ? gdat + (size_t)gridf * p.per_block[1] * p.final_pitch : nullptr,

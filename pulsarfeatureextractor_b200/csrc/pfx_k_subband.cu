@@ -8,10 +8,13 @@ namespace {
 __global__ void __launch_bounds__(BLOCK_THREADS, 4)
 k_subband(const void* __restrict__ profile, const void* __restrict__ subbands, int dtype,
           long long n, int nbin, int nsub, const double* __restrict__ params, double* feat,
-          long long ld, int32_t* status, u64* counter, int work_doubles) {
+          long long ld, int32_t* status, u64* counter, int work_doubles, double* gws) {
     extern __shared__ double smem[];
     Group<WARP> g;
-    double* ws = smem + (threadIdx.x / WARP) * work_doubles;
+    // the box-car sums of the candidate a warp works on: shared memory, or (long profiles) the warp's slot of a
+    // global scratch that stays in L2
+    double* ws = gws ? gws + ((size_t)blockIdx.x * (blockDim.x / WARP) + threadIdx.x / WARP) * work_doubles
+                     : smem + (threadIdx.x / WARP) * work_doubles;
     for (;;) {
         const long long c = next_candidate(g, counter);
         if (c >= n) break;
@@ -23,26 +26,48 @@ k_subband(const void* __restrict__ profile, const void* __restrict__ subbands, i
 
 }  // namespace
 
+namespace {
+struct SubPlan {
+    int wd, threads, grid;
+    size_t smem;
+    bool global;       // box-car sums in the per-warp global scratch
+};
+}  // namespace
+
+// The box-car sums of one candidate (nsub x nbin float64) live in shared memory when the four warps of a block
+// fit (HTRU 16 x 128: 17 KB per candidate, PFD 64 x 64: 33 KB); longer profiles (survey 16 x 1024: 131 KB, which
+// left one warp per SM: 866 ms per 50 000 candidates) keep them in a per-warp global scratch instead, two blocks
+// per SM, L2 resident.
+static int subband_plan(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, SubPlan* p) {
+    p->wd = align_up(sub_work_doubles(s->nbin, s->nsub), 2);
+    p->threads = GROUPS_PER_BLOCK * WARP;
+    p->smem = (size_t)p->wd * 8 * GROUPS_PER_BLOCK;
+    p->global = p->smem > (size_t)ctx->smem_optin;
+    if (p->global) p->smem = 0;
+    int rc = persistent_grid(ctx, k_subband, p->threads, p->smem, &p->grid);
+    if (rc) return rc;
+    if (p->global) {
+        if (p->grid > 2 * ctx->sm_count) p->grid = 2 * ctx->sm_count;
+        rc = ensure_buf(ctx, &set->sub_scratch, (size_t)p->grid * GROUPS_PER_BLOCK * p->wd * 8);
+    }
+    return rc;
+}
+
+int pfx::reserve_subband(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s) {
+    if (s->nsub < 1 || s->nbin < 2) return PFX_OK;
+    SubPlan p;
+    return subband_plan(ctx, set, s, &p);
+}
+
 int pfx::launch_subband(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* profile,
                           const void* subbands, const double* params, double* feat, int64_t ld,
                           int32_t* status, cudaStream_t st, pfx_scratch_set* set, int ck) {
     if (s->nsub < 1 || s->nbin < 2) return set_err(ctx, PFX_ERR_UNSUPPORTED, "bad sub-band shape");
-    const int wd = align_up(sub_work_doubles(s->nbin, s->nsub), 2);
-    // the box-car sums of one candidate (nsub x nbin float64) live in shared memory; as many warps
-    // per block as fit (HTRU 16 x 128: four; survey 16 x 1024: one)
-    int warps = GROUPS_PER_BLOCK;
-    while (warps > 1 && (size_t)wd * 8 * warps > (size_t)ctx->smem_optin) warps >>= 1;
-    const size_t smem = (size_t)wd * 8 * warps;
-    if (smem > (size_t)ctx->smem_optin)
-        return set_err(ctx, PFX_ERR_UNSUPPORTED, "sub-bands %d x %d need %zu bytes of shared memory per candidate, limit %d",
-                       s->nsub, s->nbin, smem, ctx->smem_optin);
-    const int threads = warps * WARP;
-    int grid;
-    int rc = persistent_grid(ctx, k_subband, threads, smem, &grid);
+    SubPlan p;
+    int rc = subband_plan(ctx, set, s, &p);
     if (rc) return rc;
-    k_subband<<<grid, threads, smem, st>>>(profile, subbands, s->dtype, n, s->nbin, s->nsub, params, feat,
-                                                  ld, status, take_counter(set, ck, st), wd);
+    k_subband<<<p.grid, p.threads, p.smem, st>>>(profile, subbands, s->dtype, n, s->nbin, s->nsub, params, feat, ld, status,
+                                                 take_counter(set, ck, st), p.wd, p.global ? (double*)set->sub_scratch.p : nullptr);
     PFX_CUDA(ctx, cudaGetLastError());
     return PFX_OK;
 }
-
