@@ -528,6 +528,10 @@ def main():
                             "x candidates of this step / live kernel time" % flops.get("source", "profiles/")}
             line["stage_ms_serialised"] = {k: v for k, v in stage.items() if k != "launches"}
             line["stage_done_ms_overlapped"] = {k: v for k, v in trace.items() if k not in ("launches", "subband")}
+            line["stage_note"] = ("stage_ms_serialised: groups one after the other on one stream; stage_done_ms_overlapped: "
+                                  "side streams as in production but the final-fit kernel after the rounds kernel; the timed "
+                                  "steps (value, ms_per_step) also overlap the tails of the two Gaussian kernels through the "
+                                  "hand-over list (DESIGN 4.2)")
         else:
             line["roofline"] = {"bound": "hbm", "kernel": "k_lyon8_u8 (the whole step is this kernel)",
                                 "achieved": step_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",

@@ -88,6 +88,8 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     if (const char* e = getenv("PFX_FINAL_SLOTS")) ctx->final_slots = atoi(e) != 0;
     ctx->fill = 0;
     if (const char* e = getenv("PFX_FILL")) ctx->fill = atoi(e);
+    ctx->sin_per_sm = 0;
+    if (const char* e = getenv("PFX_SIN_PER_SM")) ctx->sin_per_sm = atoi(e);
     ctx->pipe = 1;             // PFX_PIPE=0: the final-fit kernel starts when the rounds kernel has ended
     if (const char* e = getenv("PFX_PIPE")) ctx->pipe = atoi(e) != 0;
     ctx->chain_on_hi = 0;

@@ -1,17 +1,19 @@
 // pfx_k_gauss.cu -- scores 8-11: Gaussian + background fit and the double-Gaussian procedure on the
-// rotated profile (ProfileOperations.py:724-768,1061-1483), A GROUP OF C LANES PER CANDIDATE.
+// rotated profile (ProfileOperations.py:724-768,1061-1483).
 //
-// Two persistent kernels (see pfx_lane_gauss.cuh):
-//   k_gauss_rounds   the nine 4-parameter fits (T1 + eight rounds) as a per-group state machine;
-//                    one trip of the loop = one Jacobian pass + one trial point for 32/C candidates.
-//   k_gauss_final    the 8-parameter fit, the combi/final choice and scores 10, 11.
-// Groups pull candidates from a global counter one at a time, so a group whose fits converge
-// quickly simply takes more candidates (the spread in function evaluations is ~100x).
-// The rows of a candidate are dealt to the C lanes of its group (LaneGroup, pfx_lane_lm.cuh): the
-// data vector (float64 values + uint16 bin numbers) is stored once per group in shared memory with
-// the group index fastest; each lane has its own n x n workspace in k_gauss_rounds, the two lanes of
-// a group share one in k_gauss_final (lane 0 runs the n x n steps and broadcasts their results), which
-// lets 96 instead of 64 candidates reside per SM.
+// Two persistent kernels per call (fit logic in pfx_lane_gauss.cuh, Levenberg-Marquardt in pfx_lane_lm.cuh):
+//   rounds   the nine 4-parameter fits (T1 + eight rounds of the double-Gaussian procedure)
+//   final    the 8-parameter fit, the combi/final choice and scores 10, 11
+// THE KERNELS IN USE are the block-synchronous pair k_gauss_rounds_s / k_gauss_final_s (further down): the
+// state of a fit in the registers of an owner lane, data vectors and a small workspace per candidate slot in
+// shared memory, the phases of a trip block-wide, row passes and set-up / close tasks pulled from block lists by
+// groups of eight lanes, and a hand-over list between the two kernels so that their tails overlap.
+// The forms they grew out of stay selectable for comparison:
+//   k_gauss_rounds     one lane (or a group of C lanes) per candidate from its first fit to its last  (PFX_SLOTS=0)
+//   k_gauss_rounds_h   hybrid: owner lanes + eight-lane row groups inside a warp                       (PFX_HYBRID=1)
+//   k_gauss_wave       fit state in global memory, block-wide phases over all candidates of a block  (PFX_WAVE=1)
+//   k_gauss_final      two lanes per candidate, one n x n workspace per pair                           (PFX_FINAL_SLOTS=0)
+// All pull candidates from a global counter, because work per candidate is heavy-tailed (~100x).
 #include "pfx_internal.cuh"
 #include "pfx_lane_gauss.cuh"
 

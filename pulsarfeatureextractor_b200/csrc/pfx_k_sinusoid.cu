@@ -71,6 +71,9 @@ int pfx::launch_sinusoid(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void
     const int per_block = threads / SIN_LANES;
     if ((long long)grid * per_block > n) grid = (int)((n + per_block - 1) / per_block);
     if (chunk > 0) grid = (int)((n + chunk - 1) / chunk);
+    // (development knob: at most sin_per_sm blocks per SM, so that the kernel runs in the background of the
+    // Gaussian kernels with what they leave of an SM)
+    if (chunk <= 0 && ctx->sin_per_sm > 0 && grid > ctx->sin_per_sm * ctx->sm_count) grid = ctx->sin_per_sm * ctx->sm_count;
     k_sinusoid<<<grid, threads, smem, st>>>(profile, s->dtype, n, s->nbin, feat, ld, ier,
                                              take_counter(set, ck, st), chunk);
     PFX_CUDA(ctx, cudaGetLastError());
