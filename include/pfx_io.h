@@ -37,7 +37,8 @@ typedef struct pfx_phcx_info {
     int32_t nsub;      /* nSub attribute of <SubBands>             */
     int32_t n_dm;      /* number of complete 128-blocks            */
     int32_t n_dmstat;  /* decoded length of DataBlock[0]           */
-    int32_t reserved;
+    int32_t lyon_ok;   /* 1: Profile[section] and DataBlock[0] were read -- enough for the Lyon statistics
+                          (--dmprof, PHCXFile.py:320-379) even when ok == 0; nbin and n_dmstat are then valid */
     double params[8];
 } pfx_phcx_info;
 

@@ -40,6 +40,12 @@ class Candidate(object):
 
     # ---- scoring entry points, same names as the reference ----------------------------------------
     def _score(self, engine, features):
+        if features == "lyon" and self.family() != "pfd":
+            # the reference touches only the profile and DataBlock[0] here (PHCXFile.py:320-379)
+            c = phcx_io.read_phcx(self.candidateName, section=1 if self.family() == "phcx" else 0, lyon_only=True)
+            out = engine.score_host(np.ascontiguousarray(c.profile[None]), None, None,
+                                    np.ascontiguousarray(c.dmstat[None]), None, features="lyon")
+            return [float(v) for v in out.features[0]]
         c = self.load()
         if self.family() == "pfd":
             out = engine.score_pfd_host(c.profile[None], c.subbands[None], c.dmcurve[None], c.params[None],

@@ -155,27 +155,39 @@ class DataProcessor(object):
             elif phcx_io.native_available() and not any(".pfd" in os.path.basename(p) for p in chunk):
                 # bulk path: native scanner, rows gathered per shape into pinned buffers
                 scan = phcx_io.Scan(chunk)
+                lyon_only = features == "lyon"      # --dmprof: only the profile and DataBlock[0] are needed
                 groups = {}
                 for k in range(len(chunk)):
-                    if scan.ok(k):
-                        groups.setdefault(scan.shape_key(k), []).append(k)
+                    if scan.ok(k, lyon_only):
+                        groups.setdefault(scan.shape_key(k, lyon_only), []).append(k)
                     else:
                         print("Error reading profile data :\n\t", chunk[k])
                 for _key, ks in groups.items():
-                    score_group(ks, *scan.gather(ks))
+                    if lyon_only:
+                        prof, dms = scan.gather_lyon(ks)
+                        score_group(ks, prof, None, None, dms, None)
+                    else:
+                        score_group(ks, *scan.gather(ks))
                 scan.close()
             else:
                 groups = {}
+                lyon_files = features == "lyon"
                 for k, p in enumerate(chunk):
                     try:
-                        c = Candidate(p, p).load()
+                        cd = Candidate(p, p)
+                        if lyon_files and cd.family() != "pfd":
+                            c = phcx_io.read_phcx(p, section=1 if cd.family() == "phcx" else 0, lyon_only=True)
+                            key = (c.profile.size, None, None, c.dmstat.size)
+                        else:
+                            c = cd.load()
+                            key = (c.profile.size, c.subbands.shape, c.dmcurve.size, c.dmstat.size)
                     except Exception as e:      # noqa: BLE001 - mirrors DataProcessor.py:517
                         print("Error reading profile data :\n\t", type(e).__name__, e)
                         continue
-                    key = (c.profile.size, c.subbands.shape, c.dmcurve.size, c.dmstat.size)
                     groups.setdefault(key, []).append((k, c))
                 for _key, items in groups.items():
-                    stack = lambda name: np.ascontiguousarray(np.stack([getattr(c, name) for _k, c in items]))
+                    stack = lambda name: (None if getattr(items[0][1], name) is None else
+                                          np.ascontiguousarray(np.stack([getattr(c, name) for _k, c in items])))
                     if isinstance(items[0][1], pfd_io.PFDCandidate):
                         out = eng.score_pfd_host(stack("profile"), stack("subbands"), stack("dmcurve"), stack("params"),
                                                  features=features)

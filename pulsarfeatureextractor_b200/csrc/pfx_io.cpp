@@ -194,6 +194,15 @@ bool parse_one(const char* path, int section, Cand* c, pfx_phcx_info* info, std:
     Block b;
     if (!tag_block(*text, "Profile", sec, &b)) return false;
     hex_decode(b.body, &c->profile);
+    // What the Lyon statistics need (PHCXFile.py:320-379, PHCXOperations.py:528-539): this profile and
+    // DataBlock[0].  A file that has them is usable in --dmprof mode even when a tag of the Bates scores is
+    // missing or malformed below (the reference never touches those tags in that mode).
+    if (tag_block(*text, "DataBlock", 0, &b)) {
+        hex_decode(b.body, &c->dmstat);
+        info->lyon_ok = 1;
+        info->nbin = (int32_t)c->profile.size();
+        info->n_dmstat = (int32_t)c->dmstat.size();
+    }
     if (!tag_block(*text, "SubBands", sec, &b)) return false;
     long nbins = 0, nsub = 0;
     if (!attr_int(b.attrs, "nBins", &nbins) || !attr_int(b.attrs, "nSub", &nsub)) return false;
@@ -203,8 +212,7 @@ bool parse_one(const char* path, int section, Cand* c, pfx_phcx_info* info, std:
     std::vector<uint8_t> block;
     if (!tag_block(*text, "DataBlock", sec, &b)) return false;
     hex_decode(b.body, &block);
-    if (!tag_block(*text, "DataBlock", 0, &b)) return false;
-    hex_decode(b.body, &c->dmstat);
+    if (!info->lyon_ok) return false;       // (no DataBlock[0])
     // max of the first 127 values of every complete 128-block (PHCXOperations.py:237-259)
     const size_t nblk = block.size() / 128;
     c->dmcurve.resize(nblk);
@@ -286,7 +294,21 @@ extern "C" int pfx_phcx_scan(const char* const* paths, int64_t n, int section, i
                 ok = false;
             }
             fi.ok = ok ? 1 : 0;
-            if (!ok) h->cands[(size_t)i] = Cand();
+            if (!ok) {
+                Cand& cd = h->cands[(size_t)i];
+                if (fi.lyon_ok) {        // keep what the Lyon statistics need, drop the rest
+                    cd.subbands.clear();
+                    cd.dmcurve.clear();
+                    const int32_t nb = fi.nbin, nd = fi.n_dmstat;
+                    memset(&fi, 0, sizeof(fi));
+                    fi.lyon_ok = 1;
+                    fi.nbin = nb;
+                    fi.n_dmstat = nd;
+                } else {
+                    cd = Cand();
+                    memset(&fi, 0, sizeof(fi));
+                }
+            }
             h->info[(size_t)i] = fi;
             info[i] = fi;
         }
@@ -306,11 +328,16 @@ extern "C" int pfx_phcx_gather(const pfx_scan* scan, const int64_t* idx, int64_t
     const int64_t n = (int64_t)scan->cands.size();
     if (idx[0] < 0 || idx[0] >= n) return -1;
     const pfx_phcx_info& f0 = scan->info[(size_t)idx[0]];
+    // a gather of profile and dmstat alone (Lyon statistics) also accepts files that are only lyon_ok
+    const bool lyon_only = !subbands && !dmcurve && !params;
     for (int64_t r = 0; r < count; ++r) {
         if (idx[r] < 0 || idx[r] >= n) return -1;
         const pfx_phcx_info& f = scan->info[(size_t)idx[r]];
-        if (!f.ok || f.nbin != f0.nbin || f.nsub != f0.nsub || f.n_dm != f0.n_dm || f.n_dmstat != f0.n_dmstat)
+        if (lyon_only) {
+            if (!(f.ok || f.lyon_ok) || f.nbin != f0.nbin || f.n_dmstat != f0.n_dmstat) return -2;
+        } else if (!f.ok || f.nbin != f0.nbin || f.nsub != f0.nsub || f.n_dm != f0.n_dm || f.n_dmstat != f0.n_dmstat) {
             return -2;
+        }
     }
     for (int64_t r = 0; r < count; ++r) {
         const Cand& c = scan->cands[(size_t)idx[r]];

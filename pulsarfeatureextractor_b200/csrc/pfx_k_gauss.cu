@@ -336,7 +336,10 @@ k_gauss_rounds_h(const void* __restrict__ profile, int dtype, long long n, int m
 //     rows     groups pull: residual norm at the trial point
 // Same arithmetic as the hybrid kernel (rows of a fit are dealt to eight lanes by row index only).
 //     ws[HY_WSN][slots] | stg[20][threads] | nrows[slots], list[2][slots] int | dat[slot][pitch] | xs[slot][pitch]
-constexpr int SL_MAXT = 256;
+#ifndef PFX_SL_MAXT
+#define PFX_SL_MAXT 256
+#endif
+constexpr int SL_MAXT = PFX_SL_MAXT;      // (development: more warps per block at fewer registers per thread)
 
 // ---- hand-over of finished candidates from the rounds kernel to the final-fit kernel --------------------
 // Both kernels end in a tail set by their slowest candidates (34 and 42 ms at 100 000 candidates), and a kernel

@@ -36,7 +36,7 @@ _io = None
 
 class PhcxInfo(ctypes.Structure):
     _fields_ = [("ok", ctypes.c_int32), ("nbin", ctypes.c_int32), ("nsub", ctypes.c_int32),
-                ("n_dm", ctypes.c_int32), ("n_dmstat", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("n_dm", ctypes.c_int32), ("n_dmstat", ctypes.c_int32), ("lyon_ok", ctypes.c_int32),
                 ("params", ctypes.c_double * 8)]
 
 
@@ -104,12 +104,28 @@ class Scan(object):
             raise RuntimeError("pfx_phcx_scan failed")
         self.n = n
 
-    def ok(self, i):
-        return bool(self.info[i].ok)
+    def ok(self, i, lyon_only=False):
+        """Whole file readable; with lyon_only, what the Lyon statistics need is readable (profile of the
+        section and DataBlock[0]: the reference touches nothing else in --dmprof mode, PHCXFile.py:320-379)."""
+        return bool(self.info[i].ok) or (lyon_only and bool(self.info[i].lyon_ok))
 
-    def shape_key(self, i):
+    def shape_key(self, i, lyon_only=False):
         f = self.info[i]
-        return (f.nbin, f.nsub, f.n_dm, f.n_dmstat)
+        return (f.nbin, f.n_dmstat) if lyon_only else (f.nbin, f.nsub, f.n_dm, f.n_dmstat)
+
+    def gather_lyon(self, indices):
+        """(profile, dmstat) rows of files that share (nbin, n_dmstat); accepts files that are only lyon_ok."""
+        lib = _load_io()
+        k = len(indices)
+        nbin, n_dms = self.shape_key(indices[0], True)
+        prof = self._buffer((k, nbin), np.uint8)
+        dms = self._buffer((k, n_dms), np.uint8)
+        idx = (ctypes.c_int64 * k)(*indices)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rc = lib.pfx_phcx_gather(self._h, idx, k, p(prof), None, None, p(dms), None)
+        if rc != 0:
+            raise RuntimeError("pfx_phcx_gather failed (%d)" % rc)
+        return prof, dms
 
     @staticmethod
     def _buffer(shape, dtype):
@@ -182,9 +198,10 @@ class PHCXCandidate(object):
     __slots__ = ("profile", "subbands", "dmcurve", "dmstat", "params")
 
 
-def read_phcx(path, section=None):
+def read_phcx(path, section=None, lyon_only=False):
     """Parse one candidate.  ``section`` defaults to 1 for ``.gz`` names, else 0
-    (Candidate.py:141-150 dispatch)."""
+    (Candidate.py:141-150 dispatch).  With lyon_only only the profile and DataBlock[0] are read (what
+    the reference touches in --dmprof mode, PHCXFile.py:320-379): the other arrays stay None."""
     if section is None:
         section = 1 if ".gz" in path else 0
     if ".gz" in path:
@@ -195,6 +212,10 @@ def read_phcx(path, section=None):
             text = fh.read()
     c = PHCXCandidate()
     c.profile = _hex_to_u8(_tag_blocks(text, b"Profile")[section][1])
+    if lyon_only:
+        c.dmstat = _hex_to_u8(_tag_blocks(text, b"DataBlock")[0][1])
+        c.subbands = c.dmcurve = c.params = None
+        return c
     attrs, body = _tag_blocks(text, b"SubBands")[section]
     nbins = int(_attr(attrs, b"nBins"))
     nsub = int(_attr(attrs, b"nSub"))

@@ -142,3 +142,57 @@ def test_pfd_files_through_the_cli_classes(cand_dir, tmp_path):
         c = pfd_io.read_pfd(path)
         ref = O.bates22_pfd_arrays(c.profile, c.subbands, c.dmcurve, c.params)
         assert r == O.format_row(path, ref.features)
+
+
+def test_dmprof_accepts_files_whose_bates_tags_are_broken(tmp_path):
+    """--dmprof touches only the profile of the section and DataBlock[0] (PHCXFile.py:320-379,
+    PHCXOperations.py:528-539): a file whose <Width> is not a number or whose <SubBands> is missing gets its
+    eight Lyon statistics, while the Bates modes log it as a failure -- in the native scanner, in the Python
+    reader and through DataProcessor."""
+    import gzip
+    d = tmp_path / "cands"
+    d.mkdir()
+    b = synth.generate(52, 0, 8)
+    good = str(d / "cand_good.phcx.gz")
+    phcx_io.write_phcx(good, b.profile[0], b.subbands[0], b.dmcurve[0], b.dmstat[0], b.params[0])
+    text = gzip.open(good, "rb").read()
+    assert text.count(b"<Width") == 2 and text.count(b"<SubBands") == 2
+    bad_width = str(d / "cand_badwidth.phcx.gz")
+    with gzip.open(bad_width, "wb") as fh:
+        fh.write(text.replace(b"<Width units='periods'>", b"<Width units='periods'>x"))
+    no_sub = str(d / "cand_nosub.phcx.gz")
+    with gzip.open(no_sub, "wb") as fh:
+        fh.write(text.replace(b"<SubBands", b"<SubBandz").replace(b"</SubBands>", b"</SubBandz>"))
+    no_prof = str(d / "cand_noprofile.phcx.gz")
+    with gzip.open(no_prof, "wb") as fh:
+        fh.write(text.replace(b"<Profile", b"<Profilx").replace(b"</Profile>", b"</Profilx>"))
+    paths = [good, bad_width, no_sub, no_prof]
+    # Python reader
+    for p in (bad_width, no_sub):
+        with pytest.raises(Exception):
+            phcx_io.read_phcx(p)
+        c = phcx_io.read_phcx(p, lyon_only=True)
+        assert np.array_equal(c.profile, b.profile[0]) and np.array_equal(c.dmstat, b.dmstat[0])
+    with pytest.raises(Exception):
+        phcx_io.read_phcx(no_prof, lyon_only=True)
+    # native scanner
+    if phcx_io.native_available():
+        scan = phcx_io.Scan(paths)
+        assert [scan.ok(k) for k in range(4)] == [True, False, False, False]
+        assert [scan.ok(k, True) for k in range(4)] == [True, True, True, False]
+        prof, dms = scan.gather_lyon([0, 1, 2])
+        assert all(np.array_equal(prof[k], b.profile[0]) and np.array_equal(dms[k], b.dmstat[0]) for k in range(3))
+        with pytest.raises(RuntimeError):
+            scan.gather([0, 1])            # a full gather refuses the file that is only lyon_ok
+        scan.close()
+    # through the CLI classes
+    eng = OracleEngine()
+    dp = DataProcessor(False, engine=eng, error_log=str(tmp_path / "e_lyon.txt"))
+    ok, bad = dp.dmprofPHCX(str(d) + "/", False, str(tmp_path / "lyon.csv"), False, False)
+    assert (ok, bad) == (3, 1)
+    rows = open(tmp_path / "lyon.csv").read().strip().split("\n")
+    want = O.format_row("x", O.lyon8(b.profile[0], b.dmstat[0])).split(",", 1)[1]
+    assert len(rows) == 3 and all(r.split(",", 1)[1] == want for r in rows)
+    dp2 = DataProcessor(False, engine=eng, error_log=str(tmp_path / "e_bates.txt"))
+    ok, bad = dp2.processPHCXCollectively(str(d) + "/", False, str(tmp_path / "bates.csv"), False, False, False)
+    assert (ok, bad) == (1, 3)
