@@ -88,6 +88,10 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     if (const char* e = getenv("PFX_FINAL_SLOTS")) ctx->final_slots = atoi(e) != 0;
     ctx->fill = 0;
     if (const char* e = getenv("PFX_FILL")) ctx->fill = atoi(e);
+    ctx->sub_global = 1;
+    ctx->sub_blocks = 0;
+    if (const char* e = getenv("PFX_SUB_GLOBAL")) ctx->sub_global = atoi(e);
+    if (const char* e = getenv("PFX_SUB_BLOCKS")) ctx->sub_blocks = atoi(e);
     ctx->sin_per_sm = 0;
     if (const char* e = getenv("PFX_SIN_PER_SM")) ctx->sin_per_sm = atoi(e);
     ctx->pipe = 1;             // PFX_PIPE=0: the final-fit kernel starts when the rounds kernel has ended

@@ -71,6 +71,7 @@ struct pfx_ctx {
     int hy_pad;               // elements between the data vectors of neighbouring slots beyond the bins (bank spread)
     int hy_k, hy_warps;       // hybrid rounds kernel: candidates per warp (32: first layout, 0: as many as fit), warps per block
     int pipe;                 // 1: the final-fit kernel runs next to the rounds kernel and takes candidates as they finish
+    int sub_global, sub_blocks;   // sub-band kernel: 1 = global scratch also for mid-size shapes; blocks per SM there (development)
     int sin_per_sm;           // > 0: cap of the sinusoid kernel's resident blocks per SM (development)
     int gauss_launches;       // kernels the last launch_gauss started (2, or 3 with the hand-over's held-back blocks)
     int pipe_suspend;         // set by pfx_score_host while a batch of several chunks is in flight

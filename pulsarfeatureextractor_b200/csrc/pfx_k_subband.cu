@@ -42,12 +42,16 @@ static int subband_plan(pfx_ctx* ctx, pfx_scratch_set* set, const pfx_shape* s, 
     p->wd = align_up(sub_work_doubles(s->nbin, s->nsub), 2);
     p->threads = GROUPS_PER_BLOCK * WARP;
     p->smem = (size_t)p->wd * 8 * GROUPS_PER_BLOCK;
-    p->global = p->smem > (size_t)ctx->smem_optin;
+    const bool huge = p->smem > (size_t)ctx->smem_optin;
+    // mid-size shapes (PFD 64 x 64: 133 KB per block of four warps, one block per SM) are faster from the global
+    // scratch too, with four blocks per SM: 66 -> 30 ms per 100 000 candidates (PFX_SUB_GLOBAL=0: shared memory)
+    p->global = huge || (ctx->sub_global > 0 && p->smem > (size_t)ctx->smem_optin / 3);
     if (p->global) p->smem = 0;
     int rc = persistent_grid(ctx, k_subband, p->threads, p->smem, &p->grid);
     if (rc) return rc;
     if (p->global) {
-        if (p->grid > 2 * ctx->sm_count) p->grid = 2 * ctx->sm_count;
+        const int cap = ctx->sub_blocks > 0 ? ctx->sub_blocks : (huge ? 2 : 4);
+        if (p->grid > cap * ctx->sm_count) p->grid = cap * ctx->sm_count;
         rc = ensure_buf(ctx, &set->sub_scratch, (size_t)p->grid * GROUPS_PER_BLOCK * p->wd * 8);
     }
     return rc;
