@@ -100,6 +100,12 @@ extern "C" int pfx_create(int device, pfx_ctx** out) {
     ctx->chain_par = 0;
     ctx->lmpar_budget = 2;
     if (const char* e = getenv("PFX_LMPAR_BUDGET")) ctx->lmpar_budget = atoi(e);
+    ctx->lmpar_budget8 = ctx->lmpar_budget;
+    if (const char* e = getenv("PFX_LMPAR_BUDGET8")) ctx->lmpar_budget8 = atoi(e);
+    ctx->fs_k = 0;
+    if (const char* e = getenv("PFX_FS_K")) ctx->fs_k = atoi(e);
+    ctx->pipe_hold = 8;
+    if (const char* e = getenv("PFX_PIPE_HOLD")) ctx->pipe_hold = atoi(e) > 0 ? atoi(e) : 1;
     ctx->hy_k = 0;
     ctx->hy_warps = 8;
     ctx->hy_pad = 8;

@@ -81,6 +81,7 @@ struct pfx_ctx {
     int fill;                 // 1: main chain on a high-priority stream, sinusoid kernel in short blocks behind the histogram stage
     cudaStream_t hi[2];
     cudaEvent_t fill_ev[2], main_ev[2];
+    int lmpar_budget8, fs_k, pipe_hold;   // final-fit kernel: lmpar iterations per trip, candidates per warp (0: as many as fit), SMs held back
     int lmpar_budget;         // block-synchronous kernels: lmpar iterations per trip (<= 0: no limit)
     int final_slots;          // 1: block-synchronous final-fit kernel, 0: lane-pair kernel
     int gauss_slots;          // 1: block-synchronous hybrid kernel (phases of a trip are block-wide)

@@ -1255,6 +1255,7 @@ static bool final_slots_layout(pfx_ctx* ctx, int m, int* threads, size_t* smem, 
     *threads = warps * 32;
     int k = (budget > 64) ? (int)((budget - 64) / per_slot / warps) : 0;
     if (k > 24) k = 24;
+    if (ctx->fs_k > 0 && k > ctx->fs_k) k = ctx->fs_k;
     if (k >= 4) {
         *k_out = k;
         *slots_out = k * warps;
@@ -1403,11 +1404,11 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
         cudaStream_t sf = ctx->pf[ctx->chain_par];
         cudaStreamWaitEvent(sf, ctx->pipe_ev[ctx->chain_par], 0);
         int gridf = p.grid[1];
-        if (gridf > ctx->sm_count - 8) gridf = ctx->sm_count - 8;
+        if (gridf > ctx->sm_count - ctx->pipe_hold) gridf = ctx->sm_count - ctx->pipe_hold;
         if (gridf < 1) gridf = 1;
         k_gauss_final_s<<<gridf, p.threads[1], p.smem[1], sf>>>(profile, s->dtype, n, m, feat, ld, ier, nullptr, carry, gdat,
                                                                 p.final_pitch, p.final_k,
-                                                                ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
+                                                                ctx->lmpar_budget8 > 0 ? ctx->lmpar_budget8 : 10, pin);
         cudaEventRecord(ctx->pipe_done_ev[ctx->chain_par], sf);
         // the SMs held back above join in once the rounds kernel has ended (same list, same tickets)
         if (p.grid[1] > gridf) ctx->gauss_launches = 3;
@@ -1415,12 +1416,12 @@ int pfx::launch_gauss(pfx_ctx* ctx, const pfx_shape* s, int64_t n, const void* p
             k_gauss_final_s<<<p.grid[1] - gridf, p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier, nullptr, carry,
                                                                                 gdat ? gdat + (size_t)gridf * p.per_block[1] * p.final_pitch : nullptr,
                                                                                 p.final_pitch, p.final_k,
-                                                                                ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
+                                                                                ctx->lmpar_budget8 > 0 ? ctx->lmpar_budget8 : 10, pin);
         cudaStreamWaitEvent(st, ctx->pipe_done_ev[ctx->chain_par], 0);
     } else if (ctx->final_slots)
         k_gauss_final_s<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
                                                                      take_counter(set, ck + 4, st), carry, gdat, p.final_pitch, p.final_k,
-                                                                     ctx->lmpar_budget > 0 ? ctx->lmpar_budget : 10, pin);
+                                                                     ctx->lmpar_budget8 > 0 ? ctx->lmpar_budget8 : 10, pin);
     else
         k_gauss_final<<<p.grid[1], p.threads[1], p.smem[1], st>>>(profile, s->dtype, n, m, feat, ld, ier,
                                                                    take_counter(set, ck + 4, st), carry, gdat, gxs);
