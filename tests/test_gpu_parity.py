@@ -721,6 +721,40 @@ def test_concurrent_chunks_with_large_histograms(eng):
     assert max(nbins) > 256
 
 
+@pytest.mark.timeout(600)
+def test_handover_between_gaussian_kernels_with_calls_in_flight(eng, monkeypatch):
+    """The final-fit kernel runs next to the rounds kernel and takes candidates from the list the rounds
+    kernel appends to (PipeOut / PipeIn in pfx_k_gauss.cu).  Calls of every size, several of them in flight on
+    two streams without a host synchronisation in between (they share the context's streams and rotate its
+    scratch sets), must give the rows of a context that runs the two kernels one after the other."""
+    import torch
+    from pulsarfeatureextractor_b200.engine import Engine
+    b = synth.generate(44, 0, 6000)
+    monkeypatch.setenv("PFX_PIPE", "0")
+    plain = Engine(0)
+    monkeypatch.delenv("PFX_PIPE", raising=False)
+    f0, s0, i0 = _dev(plain, b)
+    plain.close()
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cuts = [(0, 1), (1, 6), (6, 70), (70, 327), (327, 1400), (1400, 6000), (0, 6000), (5999, 6000), (10, 300)]
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(2):
+        for k, (lo, hi) in enumerate(cuts):
+            part = b.slice(lo, hi)
+            args = [t(x) for x in (part.profile, part.subbands, part.dmcurve, part.dmstat, part.params)]
+            st = streams[k % 2]
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                outs.append((lo, hi, args, eng.score_device(*args, features="all")))
+    torch.cuda.synchronize()
+    for lo, hi, _args, out in outs:
+        assert np.array_equal(out.features.cpu().numpy(), f0[lo:hi], equal_nan=True), (lo, hi)
+        assert np.array_equal(out.status.cpu().numpy(), s0[lo:hi]) and np.array_equal(out.ier.cpu().numpy(), i0[lo:hi]), (lo, hi)
+
+
 def test_subbatches_and_reserve_do_not_change_rows(eng, batch_and_oracle):
     """pfx_set_subbatches / pfx_reserve are performance knobs: rows are a function of the candidate."""
     import torch
