@@ -68,12 +68,17 @@ if "cli" in which:
         out = os.path.join(d, "scores_%s.csv" % feats)
         dp = DataProcessor(engine=eng, features=feats, error_log=os.path.join(d, "CandidateErrorLog.txt"))
         with contextlib.redirect_stdout(io.StringIO()):
-            t0 = time.perf_counter()
-            if feats == "lyon":
-                dp.dmprofPHCX(d, False, out, False, False)
-            else:
-                dp.processPHCXCollectively(d, False, out, False, False, False)
-            dt = time.perf_counter() - t0
+            for rep in range(2):          # first pass: kernels load lazily, scratch is allocated; second: steady state
+                if os.path.exists(out):
+                    os.remove(out)
+                t0 = time.perf_counter()
+                if feats == "lyon":
+                    dp.dmprofPHCX(d, False, out, False, False)
+                else:
+                    dp.processPHCXCollectively(d, False, out, False, False, False)
+                dt = time.perf_counter() - t0
+                if rep == 0:
+                    res["cli_%s_first_call_s" % feats] = dt
         rows = sum(1 for _ in open(out))
         res["cli_%s_s" % feats] = dt
         res["cli_%s_files_per_s" % feats] = nfiles / dt
