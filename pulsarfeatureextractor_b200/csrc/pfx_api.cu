@@ -602,10 +602,15 @@ extern "C" int pfx_score_host(pfx_ctx* ctx, const pfx_shape* shape, int64_t n, u
     if (bates && (!subbands || !dmcurve || !params || !status)) return set_err(ctx, PFX_ERR_INVALID, "Bates scores need subbands, dmcurve, params and status");
     if (lyon && !dmstat) return set_err(ctx, PFX_ERR_INVALID, "Lyon statistics need dmstat");
     PFX_CUDA(ctx, cudaSetDevice(ctx->device));
-    // Bates scoring is compute bound (about 14 us of GPU time per candidate against 2.7 KB of
+    // Bates scoring is compute bound (about 5 us of GPU time per candidate against 2.7 KB of
     // input), so copies need no overlap and every chunk pays one tail of slow candidates: use few,
-    // large chunks.  Lyon-only batches are PCIe bound: 1 Mi candidates per chunk, double buffered.
-    if (chunk <= 0) chunk = bates ? 262144 : 1 << 20;
+    // large chunks (end to end on 2 Mi candidates: 226 k / 240 k / 244 k candidates/s with chunks of
+    // 256 Ki / 512 Ki / 1 Mi; staging 2 x 3.2 GB).  Lyon-only batches are PCIe bound: 1 Mi candidates
+    // per chunk, double buffered.
+    if (chunk <= 0) {
+        chunk = 1 << 20;
+        if (const char* e = getenv("PFX_CHUNK")) chunk = atoll(e) > 0 ? atoll(e) : chunk;      // (development)
+    }
     if (chunk > n) chunk = n;
     const StageLayout L = stage_layout(shape, chunk, bates, lyon, ncol);
     for (int b = 0; b < 2; ++b) {
