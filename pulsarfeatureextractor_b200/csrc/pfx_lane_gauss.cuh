@@ -73,6 +73,11 @@ struct GaussCarry {
 
 enum { GP_IDLE = 0, GP_SETUP = 1, GP_JAC = 2, GP_TRIAL = 3, GP_FIN = 4, GP_WAIT = 5 };
 
+#if !defined(__CUDA_ARCH__)
+// host build (tests/hostsim): > 0 = run lmpar of the 4-parameter fits in resumable pieces of that many iterations
+inline int g_host_lmpar_budget = 0;
+#endif
+
 // rows of the 4-parameter family: value = |p2| exp(-((x-p1)/s)^2/2) + b,
 // s = |p0| or p0, b = p3 or |p3|
 struct G4Flags {
@@ -1325,7 +1330,15 @@ struct GaussLaneT {
                 jac_close(ws);
             }
             if (phase == GP_TRIAL) {
-                trial_prep(ws);
+                if (g_host_lmpar_budget > 0) {
+                    // as the block-synchronous kernels do: lmpar in pieces of at most `budget` iterations, the
+                    // sub-problem reloaded from the workspace before every piece
+                    LmparState lst;
+                    bool pending = false;
+                    while (!trial_prep_budget(ws, lst, pending, g_host_lmpar_budget)) pending = true;
+                } else {
+                    trial_prep(ws);
+                }
                 host_group_trial(b, ws);
                 trial_close(ws);
             }

@@ -271,3 +271,6 @@ extern "C" void hs_lmpar_hist(long long* out24) {
     for (int k = 0; k < 12; ++k) { out24[k] = pfx::g_lmpar_hist[0][k]; out24[12 + k] = pfx::g_lmpar_hist8[k]; }
 }
 #endif
+
+// lmpar of the Gaussian rounds in resumable pieces (what k_gauss_rounds_s does with PFX_LMPAR_BUDGET): 0 = in one go
+extern "C" void hs_set_lmpar_budget(int budget) { pfx::g_host_lmpar_budget = budget; }

@@ -343,3 +343,27 @@ def test_lyon_rows(hs):
     out = np.zeros(4)
     hs.hs_lyon4(P(c), 0, 64, P(out))
     assert out[0] == 9 and out[1] == 0 and np.isnan(out[2]) and np.isnan(out[3])
+
+
+def test_lmpar_in_resumable_pieces_changes_nothing(hs):
+    """The block-synchronous kernels run at most two lmpar iterations per trip and carry a hard sub-problem over
+    to the next trip (lmpar_begin / lmpar_iter, four scalars of state, the sub-problem reloaded from the
+    workspace before every piece).  On the host build of the same templates: pieces of one or two iterations
+    give the rows of lmpar run in one go, bit for bit."""
+    b = synth.generate(6, 0, 160)
+    hs.hs_set_lmpar_budget.argtypes = [ctypes.c_int]
+
+    def rows(budget):
+        hs.hs_set_lmpar_budget(budget)
+        try:
+            out = [host_bates(hs, np.ascontiguousarray(b.profile[i]), np.ascontiguousarray(b.subbands[i]),
+                              np.ascontiguousarray(b.dmcurve[i]), np.ascontiguousarray(b.params[i])) for i in range(len(b))]
+        finally:
+            hs.hs_set_lmpar_budget(0)
+        return (np.array([o[0] for o in out]), np.array([o[1] for o in out]), np.array([o[2] for o in out]))
+
+    f0, i0, s0 = rows(0)
+    for budget in (1, 2):
+        f, i_, s_ = rows(budget)
+        assert np.array_equal(f, f0, equal_nan=True) and np.array_equal(s_, s0) and np.array_equal(i_, i0), budget
+    assert np.isfinite(f0[:, 7:11]).any()
